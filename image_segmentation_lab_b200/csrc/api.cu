@@ -1,0 +1,212 @@
+// C-ABI entry points of libb200seg.so: argument validation, workspace zeroing and kernel dispatch.
+// Validation mirrors the Python-side errors of the reference; everything that can be
+// checked without touching device memory is checked here, before any launch.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace b200seg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return 3;
+  }
+  return 0;
+}
+
+int ce_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
+int ce_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st);
+int finalize_dispatch(const b200seg_finalize_desc* d, cudaStream_t st);
+int tile_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
+int tile_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st);
+int up_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st);
+long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac);
+int up_combine_dispatch(const void* ws, void* grad, int dtype, int N, int C, int h, int w, float scale_host,
+                        const float* grad_out, int use_nvalid, const uint64_t* stats, cudaStream_t st);
+int scale_inplace_dispatch(void* x, int dtype, long long n, const float* g, cudaStream_t st);
+
+static int check_shape(const char* who, int N, int C, int h, int w, int H, int W, int ldt, int ydt) {
+  B200SEG_REQUIRE(N >= 0 && C >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "%s: bad shape N=%d C=%d h=%d w=%d H=%d W=%d",
+                  who, N, C, h, w, H, W);
+  B200SEG_REQUIRE(ldt == B200SEG_F32 || ldt == B200SEG_BF16 || ldt == B200SEG_F16, "%s: unsupported logit dtype %d", who, ldt);
+  B200SEG_REQUIRE(ydt >= B200SEG_L_U8 && ydt <= B200SEG_L_F64, "%s: unsupported label dtype %d", who, ydt);
+  B200SEG_REQUIRE(N <= 65535, "%s: batch %d exceeds 65535", who, N);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// top-k counts (accuracy.py:41-60 for arbitrary topk / thresh): rank of the label's logit.
+template <typename T>
+__global__ void __launch_bounds__(256) topk_counts_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
+                                                          int label_dtype, int C, long long HW, int has_ignore,
+                                                          long long ignore, int k0, int k1, int k2, int k3, int nk,
+                                                          int has_thresh, float thresh, unsigned long long* counts) {
+  __shared__ double sred[5 * 32];
+  const int n = blockIdx.y;
+  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int hit[4] = {0, 0, 0, 0};
+  int valid = 0;
+  if (px < HW) {
+    const long long y = load_label(labels, label_dtype, (size_t)n * HW + px);
+    const bool live = has_ignore ? (y != ignore) : true;
+    if (live) {
+      valid = 1;
+      if (y >= 0 && y < (long long)C) {
+        const T* base = logits + (size_t)n * C * HW + px;
+        const float zy = to_float<T>(base[(size_t)y * HW]);
+        int rank = 0;
+        for (int c = 0; c < C; ++c) {
+          const float z = to_float<T>(base[(size_t)c * HW]);
+          rank += (z > zy) || (z == zy && c < (int)y);
+        }
+        const bool pass = has_thresh ? (zy > thresh) : true;
+        const int ks[4] = {k0, k1, k2, k3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hit[j] = (j < nk && pass && rank < ks[j]);
+      }
+    }
+  }
+  double r[5] = {(double)hit[0], (double)hit[1], (double)hit[2], (double)hit[3], (double)valid};
+  block_sum<double, 5>(r, sred);
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < nk; ++j)
+      if (r[j] != 0.0) atomicAdd(counts + j, (unsigned long long)r[j]);
+    if (r[4] != 0.0) atomicAdd(counts + nk, (unsigned long long)r[4]);
+  }
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+extern "C" const char* b200seg_last_error(void) { return g_err; }
+extern "C" int32_t b200seg_abi_version(void) { return B200SEG_ABI_VERSION; }
+extern "C" int64_t b200seg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int b200seg_loss_fwd(const b200seg_loss_desc* d, void* stream) {
+  B200SEG_REQUIRE(d != nullptr, "loss_fwd: NULL descriptor");
+  if (int e = check_shape("loss_fwd", d->N, d->C, d->h, d->w, d->H, d->W, d->logit_dtype, d->label_dtype)) return e;
+  B200SEG_REQUIRE(d->stats != nullptr, "loss_fwd: NULL stats");
+  B200SEG_REQUIRE((d->flags & (B200SEG_WANT_CE | B200SEG_WANT_DICE | B200SEG_WANT_ACC)) != 0, "loss_fwd: nothing requested");
+  B200SEG_REQUIRE(!(d->flags & B200SEG_WANT_LSE) || d->lse, "loss_fwd: WANT_LSE without lse buffer");
+  B200SEG_REQUIRE(!(d->flags & B200SEG_WANT_LOSS_PX) || d->loss_px, "loss_fwd: WANT_LOSS_PX without loss_px buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200SEG_CUDA(cudaMemsetAsync(d->stats, 0, B200SEG_STATS_WORDS * sizeof(uint64_t), st));
+  if (d->flags & B200SEG_WANT_DICE) {
+    B200SEG_REQUIRE(d->dice_part != nullptr, "loss_fwd: WANT_DICE without dice_part");
+    B200SEG_CUDA(cudaMemsetAsync(d->dice_part, 0, (size_t)d->N * d->C * 3 * sizeof(double), st));
+  }
+  if (d->N == 0) return 0;
+  B200SEG_REQUIRE(d->logits && d->labels, "loss_fwd: NULL logits/labels");
+  if (d->flags & B200SEG_WANT_DICE) return tile_fwd_dispatch(d, st);
+  return ce_fwd_dispatch(d, st);
+}
+
+extern "C" int b200seg_loss_finalize(const b200seg_finalize_desc* d, void* stream) {
+  B200SEG_REQUIRE(d != nullptr && d->stats && d->out, "loss_finalize: NULL argument");
+  B200SEG_REQUIRE(!(d->ce_has_avg_factor && d->ce_reduction == B200SEG_RED_SUM),
+                  "avg_factor can not be used with reduction=\"sum\"");  // models/losses/utils.py:78-79
+  B200SEG_REQUIRE(!(d->dice_has_avg_factor && d->dice_reduction == B200SEG_RED_SUM),
+                  "avg_factor can not be used with reduction=\"sum\"");
+  return finalize_dispatch(d, (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream) {
+  B200SEG_REQUIRE(d != nullptr, "loss_bwd: NULL descriptor");
+  if (int e = check_shape("loss_bwd", d->N, d->C, d->h, d->w, d->H, d->W, d->logit_dtype, d->label_dtype)) return e;
+  if (d->N == 0) return 0;
+  B200SEG_REQUIRE(d->logits && d->labels && d->lse && d->grad_logits, "loss_bwd: NULL tensor");
+  B200SEG_REQUIRE(!d->ce_use_nvalid || d->stats, "loss_bwd: ce_use_nvalid without stats");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->flags & B200SEG_WANT_DICE) return tile_bwd_dispatch(d, st);
+  B200SEG_REQUIRE(d->flags & B200SEG_WANT_CE, "loss_bwd: nothing requested");
+  return ce_bwd_dispatch(d, st);
+}
+
+extern "C" int64_t b200seg_loss_fused_workspace_bytes(int32_t N, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W,
+                                                      int32_t align_corners) {
+  return up_fused_workspace(N, C, h, w, H, W, align_corners);
+}
+
+extern "C" int b200seg_loss_fused_fwdbwd(const b200seg_loss_fused_desc* d, void* stream) {
+  B200SEG_REQUIRE(d != nullptr, "loss_fused: NULL descriptor");
+  const b200seg_loss_desc* f = &d->fwd;
+  if (int e = check_shape("loss_fused", f->N, f->C, f->h, f->w, f->H, f->W, f->logit_dtype, f->label_dtype)) return e;
+  B200SEG_REQUIRE(!(f->flags & B200SEG_WANT_DICE), "loss_fused: dice is not supported by the single-pass entry");
+  B200SEG_REQUIRE(f->stats != nullptr, "loss_fused: NULL stats");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200SEG_CUDA(cudaMemsetAsync(f->stats, 0, B200SEG_STATS_WORDS * sizeof(uint64_t), st));
+  if (f->N == 0) return 0;
+  B200SEG_REQUIRE(f->logits && f->labels, "loss_fused: NULL logits/labels");
+  return up_fused_dispatch(d, st);
+}
+
+extern "C" int b200seg_loss_fused_combine(const void* workspace, void* grad_logits, int32_t logit_dtype, int32_t N,
+                                          int32_t C, int32_t h, int32_t w, float scale_host, const float* grad_out,
+                                          int32_t use_nvalid, const uint64_t* stats, void* stream) {
+  B200SEG_REQUIRE(workspace && grad_logits, "loss_fused_combine: NULL buffer");
+  B200SEG_REQUIRE(N >= 0 && C >= 1 && h >= 1 && w >= 1, "loss_fused_combine: bad shape");
+  B200SEG_REQUIRE(!use_nvalid || stats, "loss_fused_combine: use_nvalid without stats");
+  if (N == 0) return 0;
+  return up_combine_dispatch(workspace, grad_logits, logit_dtype, N, C, h, w, scale_host, grad_out, use_nvalid, stats,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_scale_inplace(void* x, int32_t dtype, int64_t n, const float* g, void* stream) {
+  B200SEG_REQUIRE(x && g && n >= 0, "scale_inplace: bad arguments");
+  if (n == 0) return 0;
+  return scale_inplace_dispatch(x, dtype, n, g, (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_topk_counts(const void* logits, const void* labels, int32_t logit_dtype, int32_t label_dtype,
+                                   int32_t N, int32_t C, int64_t HW, int32_t has_ignore, int64_t ignore_index,
+                                   const int32_t* topk_host, int32_t n_topk, int32_t has_thresh, float thresh,
+                                   int64_t* counts, void* stream) {
+  B200SEG_REQUIRE(n_topk >= 1 && n_topk <= 4 && topk_host, "topk_counts: between 1 and 4 k values supported");
+  B200SEG_REQUIRE(N >= 0 && N <= 65535 && C >= 1 && HW >= 1 && counts, "topk_counts: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200SEG_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n_topk + 1) * sizeof(int64_t), st));
+  if (N == 0) return 0;
+  B200SEG_REQUIRE(logits && labels, "topk_counts: NULL tensor");
+  int k[4] = {0, 0, 0, 0};
+  for (int j = 0; j < n_topk; ++j) {
+    B200SEG_REQUIRE(topk_host[j] >= 1 && topk_host[j] <= C, "maxk %d exceeds pred dimension %d", topk_host[j], C);
+    k[j] = topk_host[j];
+  }
+  dim3 grid((unsigned)((HW + 255) / 256), N);
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
+  switch (logit_dtype) {
+    case B200SEG_F32:
+      topk_counts_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, labels, label_dtype, C, HW, has_ignore,
+                                                      ignore_index, k[0], k[1], k[2], k[3], n_topk, has_thresh, thresh, cnt);
+      break;
+    case B200SEG_BF16:
+      topk_counts_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)logits, labels, label_dtype, C, HW,
+                                                              has_ignore, ignore_index, k[0], k[1], k[2], k[3], n_topk,
+                                                              has_thresh, thresh, cnt);
+      break;
+    case B200SEG_F16:
+      topk_counts_kernel<__half><<<grid, 256, 0, st>>>((const __half*)logits, labels, label_dtype, C, HW, has_ignore,
+                                                       ignore_index, k[0], k[1], k[2], k[3], n_topk, has_thresh, thresh, cnt);
+      break;
+    default:
+      set_error("topk_counts: unsupported logit dtype %d", logit_dtype);
+      return 1;
+  }
+  count_launch();
+  return check_launch("topk_counts_kernel");
+}

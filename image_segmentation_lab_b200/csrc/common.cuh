@@ -1,0 +1,332 @@
+// Shared device helpers for libb200seg (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200seg.h"
+
+namespace b200seg {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kSMs = 148;                            // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------- host-side plumbing
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch(int n = 1);
+
+#define B200SEG_REQUIRE(cond, ...)       \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::b200seg::set_error(__VA_ARGS__); \
+      return 1;                          \
+    }                                    \
+  } while (0)
+
+#define B200SEG_CUDA(expr)                                                         \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      ::b200seg::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));        \
+      return 2;                                                                    \
+    }                                                                              \
+  } while (0)
+
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int label_bytes(int dt) {
+  switch (dt) {
+    case B200SEG_L_U8: return 1;
+    case B200SEG_L_I16: return 2;
+    case B200SEG_L_I32: return 4;
+    case B200SEG_L_I64: return 8;
+    case B200SEG_L_F32: return 4;
+    case B200SEG_L_F64: return 8;
+  }
+  return 0;
+}
+inline int logit_bytes(int dt) { return dt == B200SEG_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------- math
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+// ---------------------------------------------------------------- streaming loads / stores
+// Logits are read exactly once: bypass L1 allocation so the L1 keeps the small tables.
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream4(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream2(const void* p) {
+  uint16_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream1(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream8(void* p, uint2 v) {
+  asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream4(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream2(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"((uint16_t)v) : "memory");
+}
+
+// ---------------------------------------------------------------- logit element conversion
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int kBytes = 4;
+  static constexpr int kDtype = B200SEG_F32;
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kBytes = 2;
+  static constexpr int kDtype = B200SEG_BF16;
+};
+template <> struct Elem<__half> {
+  static constexpr int kBytes = 2;
+  static constexpr int kDtype = B200SEG_F16;
+};
+
+template <typename T> __device__ __forceinline__ float to_float(T v);
+template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+// two packed 16-bit elements <-> two floats
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t r, float& lo, float& hi);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t r, float& lo, float& hi) {
+  lo = __uint_as_float(r << 16);
+  hi = __uint_as_float(r & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t r, float& lo, float& hi) {
+  __half2 h = *reinterpret_cast<__half2*>(&r);
+  float2 f = __half22float2(h);
+  lo = f.x;
+  hi = f.y;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Load V consecutive elements of T (V*sizeof(T) in {2,4,8,16} bytes, pointer aligned to that) as floats.
+template <typename T, int V> __device__ __forceinline__ void load_vec(const T* p, float (&o)[V]) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (V == 4) {
+      uint4 r = ld_stream16(p);
+      o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y);
+      o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+    } else if constexpr (V == 2) {
+      uint2 r = ld_stream8(p);
+      o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y);
+    } else {
+      static_assert(V == 1, "fp32: V in {1,2,4}");
+      o[0] = __uint_as_float(ld_stream4(p));
+    }
+  } else {
+    if constexpr (V == 8) {
+      uint4 r = ld_stream16(p);
+      unpack2<T>(r.x, o[0], o[1]); unpack2<T>(r.y, o[2], o[3]);
+      unpack2<T>(r.z, o[4], o[5]); unpack2<T>(r.w, o[6], o[7]);
+    } else if constexpr (V == 4) {
+      uint2 r = ld_stream8(p);
+      unpack2<T>(r.x, o[0], o[1]); unpack2<T>(r.y, o[2], o[3]);
+    } else if constexpr (V == 2) {
+      unpack2<T>(ld_stream4(p), o[0], o[1]);
+    } else {
+      static_assert(V == 1, "16-bit: V in {1,2,4,8}");
+      float hi;
+      unpack2<T>(ld_stream2(p), o[0], hi);
+    }
+  }
+}
+
+template <typename T, int V> __device__ __forceinline__ void store_vec(T* p, const float (&v)[V]) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (V == 4) {
+      st_stream16(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+    } else if constexpr (V == 2) {
+      st_stream8(p, make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1])));
+    } else {
+      st_stream4(p, __float_as_uint(v[0]));
+    }
+  } else {
+    if constexpr (V == 8) {
+      st_stream16(p, make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7])));
+    } else if constexpr (V == 4) {
+      st_stream8(p, make_uint2(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3])));
+    } else if constexpr (V == 2) {
+      st_stream4(p, pack2<T>(v[0], v[1]));
+    } else {
+      st_stream2(p, pack2<T>(v[0], 0.f) & 0xffffu);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- labels
+// Labels are consumed in the dtype the data pipeline delivers (reference: label.long(),
+// cross_entropy_loss.py:283; evaluator ground truth is float32, core/dataset/kvasir_seg.py:37).
+__device__ __forceinline__ long long load_label(const void* p, int dt, size_t i) {
+  switch (dt) {
+    case B200SEG_L_U8: return (long long)((const uint8_t*)p)[i];
+    case B200SEG_L_I16: return (long long)((const int16_t*)p)[i];
+    case B200SEG_L_I32: return (long long)((const int32_t*)p)[i];
+    case B200SEG_L_I64: return ((const long long*)p)[i];
+    case B200SEG_L_F32: return (long long)((const float*)p)[i];
+    default: return (long long)((const double*)p)[i];
+  }
+}
+
+// V consecutive labels starting at element i (i % V == 0 and base 16-byte aligned when V > 1).
+template <int V> __device__ __forceinline__ void load_labels(const void* p, int dt, size_t i, long long (&o)[V]) {
+  if constexpr (V == 1) {
+    o[0] = load_label(p, dt, i);
+  } else {
+    static_assert(V == 2 || V == 4 || V == 8, "V");
+    switch (dt) {
+      case B200SEG_L_I64:
+      case B200SEG_L_F64: {
+        const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p) + i * 8);
+#pragma unroll
+        for (int k = 0; k < V / 2; ++k) {
+          uint4 r = ld_stream16(q + k);
+          long long a = (long long)(((unsigned long long)r.y << 32) | r.x);
+          long long b = (long long)(((unsigned long long)r.w << 32) | r.z);
+          if (dt == B200SEG_L_F64) {
+            a = (long long)__longlong_as_double(a);
+            b = (long long)__longlong_as_double(b);
+          }
+          o[2 * k] = a;
+          o[2 * k + 1] = b;
+        }
+      } break;
+      case B200SEG_L_I32:
+      case B200SEG_L_F32: {
+        uint32_t r[V];
+        const char* q = reinterpret_cast<const char*>(p) + i * 4;
+        if constexpr (V == 8) {
+          uint4 a = ld_stream16(q), b = ld_stream16(q + 16);
+          r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+        } else if constexpr (V == 4) {
+          uint4 a = ld_stream16(q);
+          r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+        } else {
+          uint2 a = ld_stream8(q);
+          r[0] = a.x; r[1] = a.y;
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          o[k] = (dt == B200SEG_L_F32) ? (long long)__uint_as_float(r[k]) : (long long)(int32_t)r[k];
+      } break;
+      case B200SEG_L_I16: {
+        const int16_t* q = reinterpret_cast<const int16_t*>(p) + i;
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = (long long)q[k];
+      } break;
+      default: {  // U8
+        const char* q = reinterpret_cast<const char*>(p) + i;
+        uint32_t r0, r1 = 0;
+        if constexpr (V == 8) {
+          uint2 a = ld_stream8(q);
+          r0 = a.x; r1 = a.y;
+        } else if constexpr (V == 4) {
+          r0 = ld_stream4(q);
+        } else {
+          r0 = ld_stream2(q);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = (long long)(((k < 4 ? r0 : r1) >> (8 * (k & 3))) & 0xffu);
+      } break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- reductions
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of up to NV values per thread; result valid in thread 0. `scratch` holds
+// NV * 32 elements of T. Requires blockDim.x to be a multiple of 32.
+template <typename T, int NV> __device__ __forceinline__ void block_sum(T (&v)[NV], T* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) scratch[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      T x = lane < nwarp ? scratch[k * 32 + lane] : T(0);
+      v[k] = warp_sum(x);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- bilinear source index (ATen)
+// torch/include/ATen/native/UpSample.h:271-312 (area_pixel_compute_scale / _source_index),
+// evaluated in fp32 exactly as ATen does.
+__host__ __device__ __forceinline__ float resize_scale(int in, int out, bool align_corners) {
+  if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  return (float)in / (float)out;
+}
+__device__ __forceinline__ void resize_src(float scale, int dst, int in, bool align_corners, int& i0, int& i1,
+                                           float& l1) {
+  float src;
+  if (align_corners) {
+    src = scale * (float)dst;
+  } else {
+    src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+  }
+  int i = (int)src;
+  i = i < in - 1 ? i : in - 1;
+  i0 = i;
+  i1 = i + (i < in - 1 ? 1 : 0);
+  float l = src - (float)i;
+  l1 = l < 0.f ? 0.f : (l > 1.f ? 1.f : l);
+}
+
+}  // namespace b200seg

@@ -1,0 +1,289 @@
+// Fused arg-max + per-class area histograms (intersect / pred / label), sm_100a.
+//
+// Replaces SegEvaluator.intersect_and_union (core/evaluation/metrics.py:210-270) — three boolean
+// compactions, three float casts, three torch.histc and three .cpu() syncs PER IMAGE — and, in the
+// logits variant, the softmax+argmax of SegEvaluator.process (:101-107), with ONE launch for a
+// whole list of images and no host synchronisation.
+//
+// Semantics kept (file:line): pixels with gt == ignore_index are dropped from all three histograms
+// (:237-241); intersect counts pred where pred == gt (:248); torch.histc(bins=C, min=0, max=C-1)
+// drops values outside [0, C-1] (:249-265), so an out-of-range gt still leaves its pixel in the
+// pred histogram and vice versa. Areas are exact int64 (the reference stores them in fp32).
+//
+// Work split: the images are cut into chunks of kChunk pixels; persistent CTAs (a multiple of the
+// 148 SMs) each take one contiguous range of chunks, so a CTA touches few images and flushes its
+// counters to global memory once per image it touches ("single global flush").
+// Counters: for small C every thread owns a private column cnt[bin][tid] in shared memory
+// (bank == tid, so plain conflict-free LDS/IADD/STS, no atomics — random predictions would
+// otherwise serialise on ATOMS throughput); a pixel needs one update when pred == gt (bin A) and
+// two otherwise (bins B = pred-only, D = gt-only): I = A, P = A + B, L = A + D. For large C a
+// shared-memory atomic histogram with per-thread run-length aggregation is used instead.
+//
+// Roofline: HBM. Algorithmic bytes per pixel: pred bytes + gt bytes (label maps: 8 + 4 = 12;
+// logits: C*s + 4).
+#include "common.cuh"
+
+namespace b200seg {
+
+constexpr int kChunk = 4096;
+
+struct ConfParams {
+  const b200seg_image* images;
+  const long long* chunk_prefix;
+  int n_images;
+  long long total_chunks;
+  int pred_dtype, gt_dtype;
+  int C;
+  long long ignore;
+  long long* areas;
+  long long* const* pred_out;
+};
+
+template <int THREADS, bool PRIVATE> struct Counters {
+  unsigned int* cnt;
+  int C;
+  __device__ __forceinline__ void add(int bin) {
+    if constexpr (PRIVATE) cnt[bin * THREADS + threadIdx.x] += 1u;
+    else atomicAdd(cnt + bin, 1u);
+  }
+  __device__ __forceinline__ void add_n(int bin, unsigned n) {
+    if constexpr (PRIVATE) cnt[bin * THREADS + threadIdx.x] += n;
+    else atomicAdd(cnt + bin, n);
+  }
+  // pv / gv: class index or -1 when outside [0, C)
+  __device__ __forceinline__ void update(int pv, int gv, unsigned n = 1u) {
+    if (pv == gv) {
+      if (pv >= 0) add_n(pv, n);
+    } else {
+      if (pv >= 0) add_n(C + pv, n);
+      if (gv >= 0) add_n(2 * C + gv, n);
+    }
+  }
+  __device__ __forceinline__ void zero() {
+    const int total = PRIVATE ? 3 * C * THREADS : 3 * C;
+    for (int i = threadIdx.x; i < total; i += THREADS) cnt[i] = 0u;
+  }
+  // add this CTA's counters into areas[img] = (I[C], P[C], L[C]) and clear them
+  __device__ __forceinline__ void flush(long long* areas_img) {
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < 3 * C; bin += THREADS) {
+      unsigned long long tot = 0;
+      if constexpr (PRIVATE) {
+        for (int t = 0; t < THREADS; ++t) {
+          const int tt = (t + threadIdx.x) & (THREADS - 1);  // rotate: conflict-free across the warp
+          tot += cnt[bin * THREADS + tt];
+          cnt[bin * THREADS + tt] = 0u;
+        }
+      } else {
+        tot = cnt[bin];
+        cnt[bin] = 0u;
+      }
+      if (tot) {
+        unsigned long long* a = reinterpret_cast<unsigned long long*>(areas_img);
+        const int kind = bin / C, c = bin - kind * C;
+        if (kind == 0) {  // A: matched
+          atomicAdd(a + c, tot);
+          atomicAdd(a + C + c, tot);
+          atomicAdd(a + 2 * C + c, tot);
+        } else if (kind == 1) {  // B: pred only
+          atomicAdd(a + C + c, tot);
+        } else {  // D: gt only
+          atomicAdd(a + 2 * C + c, tot);
+        }
+      }
+    }
+    __syncthreads();
+  }
+};
+
+__device__ __forceinline__ int find_image(const long long* prefix, int n_images, long long chunk) {
+  int lo = 0, hi = n_images - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= chunk) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <typename T, int THREADS, bool PRIVATE, bool FROM_LOGITS>
+__global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Counters<THREADS, PRIVATE> ctr{reinterpret_cast<unsigned int*>(smem_raw), p.C};
+  ctr.zero();
+  __syncthreads();
+  const int C = p.C;
+  const long long per = (p.total_chunks + gridDim.x - 1) / gridDim.x;
+  long long chunk = (long long)blockIdx.x * per;
+  const long long chunk_end = (chunk + per < p.total_chunks) ? chunk + per : p.total_chunks;
+  if (chunk >= chunk_end) return;
+  int img = find_image(p.chunk_prefix, p.n_images, chunk);
+  constexpr int V = 8;
+
+  while (chunk < chunk_end) {
+    while (img + 1 < p.n_images && chunk >= p.chunk_prefix[img + 1]) ++img;  // skips empty images
+    const b200seg_image im = p.images[img];
+    const long long img_chunk_end = p.chunk_prefix[img + 1] < chunk_end ? p.chunk_prefix[img + 1] : chunk_end;
+    const long long px_begin = (chunk - p.chunk_prefix[img]) * kChunk;
+    long long px_end = (img_chunk_end - p.chunk_prefix[img]) * kChunk;
+    if (px_end > im.n_pixels) px_end = im.n_pixels;
+    const bool vec_ok = aligned16(im.pred) && aligned16(im.gt) && (!FROM_LOGITS || (im.n_pixels % V == 0));
+    long long* pout = (FROM_LOGITS && p.pred_out) ? p.pred_out[img] : nullptr;
+
+    for (long long px = px_begin + (long long)threadIdx.x * V; px < px_end; px += (long long)THREADS * V) {
+      long long gt[V];
+      int pv[V];
+      const int nv = (px_end - px >= V) ? V : (int)(px_end - px);
+      if (nv == V && vec_ok) {
+        load_labels<V>(im.gt, p.gt_dtype, (size_t)px, gt);
+        if constexpr (FROM_LOGITS) {
+          float best[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) { best[v] = neg_inf(); pv[v] = 0; }
+          const T* base = reinterpret_cast<const T*>(im.pred) + px;
+          constexpr int LV = 16 / (int)sizeof(T);  // elements per 128-bit load
+          for (int c = 0; c < C; ++c) {
+            float z[V];
+#pragma unroll
+            for (int q = 0; q < V / LV; ++q) {
+              float t[LV];
+              load_vec<T, LV>(base + (size_t)c * im.n_pixels + q * LV, t);
+#pragma unroll
+              for (int k = 0; k < LV; ++k) z[q * LV + k] = t[k];
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              if (z[v] > best[v]) { best[v] = z[v]; pv[v] = c; }  // lowest index wins ties
+            }
+          }
+          if (pout) {
+#pragma unroll
+            for (int v = 0; v < V; v += 2)
+              st_stream16(pout + px + v, make_uint4((unsigned)pv[v], 0u, (unsigned)pv[v + 1], 0u));
+          }
+        } else {
+          long long pl[V];
+          load_labels<V>(im.pred, p.pred_dtype, (size_t)px, pl);
+#pragma unroll
+          for (int v = 0; v < V; ++v) pv[v] = (pl[v] >= 0 && pl[v] < (long long)C) ? (int)pl[v] : -1;
+        }
+      } else {
+        for (int v = 0; v < V; ++v) {
+          gt[v] = p.ignore;
+          pv[v] = -1;
+          if (v < nv) {
+            gt[v] = load_label(im.gt, p.gt_dtype, (size_t)(px + v));
+            if constexpr (FROM_LOGITS) {
+              const T* base = reinterpret_cast<const T*>(im.pred) + px + v;
+              float best = neg_inf();
+              int bi = 0;
+              for (int c = 0; c < C; ++c) {
+                const float z = to_float<T>(base[(size_t)c * im.n_pixels]);
+                if (z > best) { best = z; bi = c; }
+              }
+              pv[v] = bi;
+              if (pout) pout[px + v] = bi;
+            } else {
+              const long long pl = load_label(im.pred, p.pred_dtype, (size_t)(px + v));
+              pv[v] = (pl >= 0 && pl < (long long)C) ? (int)pl : -1;
+            }
+          }
+        }
+      }
+      if constexpr (PRIVATE) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (gt[v] != p.ignore) {
+            const int gv = (gt[v] >= 0 && gt[v] < (long long)C) ? (int)gt[v] : -1;
+            ctr.update(pv[v], gv);
+          }
+        }
+      } else {
+        // run-length aggregation over the thread's V consecutive pixels, then shared atomics
+        int rp = -2, rg = -2;
+        unsigned rn = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const bool live = gt[v] != p.ignore;
+          const int gv = (gt[v] >= 0 && gt[v] < (long long)C) ? (int)gt[v] : -1;
+          if (live && pv[v] == rp && gv == rg) {
+            ++rn;
+          } else {
+            if (rn) ctr.update(rp, rg, rn);
+            rn = live ? 1u : 0u;
+            rp = live ? pv[v] : -2;
+            rg = live ? gv : -2;
+          }
+        }
+        if (rn) ctr.update(rp, rg, rn);
+      }
+    }
+    ctr.flush(p.areas + (size_t)img * 3 * C);
+    chunk = img_chunk_end;
+  }
+}
+
+template <typename T, bool FROM_LOGITS> static int launch_confusion(const ConfParams& p, cudaStream_t st) {
+  // private per-thread counters when they fit in shared memory, else shared atomics
+  const size_t need256 = (size_t)3 * p.C * 256 * 4, need128 = (size_t)3 * p.C * 128 * 4;
+  long long want = (long long)kSMs * 4;
+  if (want > p.total_chunks) want = p.total_chunks;
+  if (want < 1) want = 1;
+  if (need256 <= 72 * 1024) {
+    auto k = confusion_kernel<T, 256, true, FROM_LOGITS>;
+    B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need256));
+    k<<<(unsigned)want, 256, need256, st>>>(p);
+  } else if (need128 <= 200 * 1024) {
+    auto k = confusion_kernel<T, 128, true, FROM_LOGITS>;
+    B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need128));
+    long long w2 = (long long)kSMs * (need128 <= 100 * 1024 ? 2 : 1) * 2;
+    if (w2 > p.total_chunks) w2 = p.total_chunks;
+    k<<<(unsigned)(w2 < 1 ? 1 : w2), 128, need128, st>>>(p);
+  } else {
+    auto k = confusion_kernel<T, 256, false, FROM_LOGITS>;
+    k<<<(unsigned)want, 256, (size_t)3 * p.C * 4, st>>>(p);
+  }
+  count_launch();
+  return check_launch("confusion_kernel");
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+
+extern "C" int32_t b200seg_confusion_chunk_pixels(void) { return kChunk; }
+
+extern "C" int b200seg_confusion_labels(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
+                                        int64_t total_chunks, int32_t chunk_pixels, int32_t pred_dtype,
+                                        int32_t gt_dtype, int32_t C, int64_t ignore_index, int64_t* areas,
+                                        void* stream) {
+  B200SEG_REQUIRE(chunk_pixels == kChunk, "confusion: chunk_pixels must be %d", kChunk);
+  B200SEG_REQUIRE(C >= 1 && C <= 4096, "confusion: num_classes %d out of range [1,4096]", C);
+  B200SEG_REQUIRE(n_images >= 0 && areas, "confusion: bad arguments");
+  if (n_images == 0 || total_chunks == 0) return 0;
+  B200SEG_REQUIRE(images && chunk_prefix, "confusion: NULL image table");
+  ConfParams p{images, (const long long*)chunk_prefix, n_images, total_chunks, pred_dtype, gt_dtype, C,
+               ignore_index, (long long*)areas, nullptr};
+  return launch_confusion<float, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_confusion_logits(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
+                                        int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype,
+                                        int32_t gt_dtype, int32_t C, int64_t ignore_index, int64_t* areas,
+                                        int64_t* const* pred_out, void* stream) {
+  B200SEG_REQUIRE(chunk_pixels == kChunk, "confusion: chunk_pixels must be %d", kChunk);
+  B200SEG_REQUIRE(C >= 1 && C <= 4096, "confusion: num_classes %d out of range [1,4096]", C);
+  B200SEG_REQUIRE(n_images >= 0 && areas, "confusion: bad arguments");
+  if (n_images == 0 || total_chunks == 0) return 0;
+  B200SEG_REQUIRE(images && chunk_prefix, "confusion: NULL image table");
+  ConfParams p{images, (const long long*)chunk_prefix, n_images, total_chunks, 0, gt_dtype, C,
+               ignore_index, (long long*)areas, (long long* const*)pred_out};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (logit_dtype) {
+    case B200SEG_F32: return launch_confusion<float, true>(p, st);
+    case B200SEG_BF16: return launch_confusion<__nv_bfloat16, true>(p, st);
+    case B200SEG_F16: return launch_confusion<__half, true>(p, st);
+  }
+  set_error("confusion: unsupported logit dtype %d", logit_dtype);
+  return 1;
+}

@@ -1,0 +1,452 @@
+// Streaming softmax cross-entropy (+ top-1 accuracy) forward / backward for sm_100a.
+//
+// Replaces, in one pass over the logits each way (reference file:line):
+//   F.interpolate bilinear            utils/ops.py:26            (general-ratio variant, UP=true)
+//   F.cross_entropy(reduction='none') models/losses/cross_entropy_loss.py:56-61
+//   weight / reduce                   models/losses/utils.py:48-80
+//   accuracy top-1                    models/losses/accuracy.py:41-60
+//
+// Data layout: logits NCHW, so for a fixed class the pixels of a row are contiguous. A thread owns
+// V consecutive pixels (V*sizeof(T) = 16 bytes) and walks the class dimension with stride H*W;
+// a warp therefore issues one fully coalesced 512-byte request per class. Classes are consumed in
+// register chunks of CH with an online (running max / rescaled sum) soft-max, so every logit is
+// read from HBM exactly once and never written back.
+//
+// Roofline: HBM. Algorithmic bytes per pixel: fwd C*s + L (+4 lse), bwd 2*C*s + L + 4.
+#include "common.cuh"
+
+namespace b200seg {
+
+struct CeFwdParams {
+  const void* logits;
+  const void* labels;
+  const float* pw;
+  const float* cw;
+  float* lse;
+  float* loss_px;
+  unsigned long long* stats;
+  int label_dtype;
+  int N, C, h, w, H, W;
+  int align_corners;
+  int flags;
+  long long ignore_index;
+  int acc_has_ignore;
+  long long acc_ignore;
+  float lw;
+  float sh, sw;
+};
+
+template <int V> __device__ __forceinline__ void load_f32(const float* p, float (&o)[V]) {
+  if constexpr (V == 8) {
+    float a[4], b[4];
+    load_vec<float, 4>(p, a);
+    load_vec<float, 4>(p + 4, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[k] = a[k]; o[4 + k] = b[k]; }
+  } else {
+    load_vec<float, V>(p, o);
+  }
+}
+template <int V> __device__ __forceinline__ void store_f32(float* p, const float (&v)[V]) {
+  if constexpr (V == 8) {
+    float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+    store_vec<float, 4>(p, a);
+    store_vec<float, 4>(p + 4, b);
+  } else {
+    store_vec<float, V>(p, v);
+  }
+}
+
+// Bilinear taps of one output pixel (UP variant).
+struct Taps {
+  int o00, o01, o10, o11;
+  float w00, w01, w10, w11;
+  float h0, h1, w0, w1;
+};
+__device__ __forceinline__ Taps make_taps(int Y, int X, int h, int w, float sh, float sw, bool ac) {
+  int y0, y1, x0, x1;
+  float ly, lx;
+  resize_src(sh, Y, h, ac, y0, y1, ly);
+  resize_src(sw, X, w, ac, x0, x1, lx);
+  Taps t;
+  t.o00 = y0 * w + x0; t.o01 = y0 * w + x1; t.o10 = y1 * w + x0; t.o11 = y1 * w + x1;
+  t.h1 = ly; t.h0 = 1.f - ly; t.w1 = lx; t.w0 = 1.f - lx;
+  t.w00 = t.h0 * t.w0; t.w01 = t.h0 * t.w1; t.w10 = t.h1 * t.w0; t.w11 = t.h1 * t.w1;
+  return t;
+}
+// ATen evaluation order: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+template <typename T> __device__ __forceinline__ float interp(const T* plane, const Taps& t) {
+  float v00 = to_float<T>(plane[t.o00]), v01 = to_float<T>(plane[t.o01]);
+  float v10 = to_float<T>(plane[t.o10]), v11 = to_float<T>(plane[t.o11]);
+  return t.h0 * (t.w0 * v00 + t.w1 * v01) + t.h1 * (t.w0 * v10 + t.w1 * v11);
+}
+
+template <typename T, int V, int CH, bool UP>
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
+  static_assert(!UP || V == 1, "resize-fused variant is one pixel per thread");
+  __shared__ double sred[5 * 32];
+  const int n = blockIdx.y;
+  const int C = p.C;
+  const long long HW = (long long)p.H * p.W;
+  const long long hw = (long long)p.h * p.w;
+  const long long px0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+
+  float loss_acc = 0.f;
+  int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
+
+  if (px0 < HW) {
+    long long y[V];
+    load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
+
+    float m[V], s[V];
+    int idx[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { m[v] = neg_inf(); s[v] = 0.f; idx[v] = 0; }
+
+    const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * hw;
+    Taps tp;
+    if constexpr (UP) tp = make_taps((int)(px0 / p.W), (int)(px0 % p.W), p.h, p.w, p.sh, p.sw, p.align_corners != 0);
+
+    for (int c0 = 0; c0 < C; c0 += CH) {
+      float z[CH][V];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (c0 + i < C) {
+          if constexpr (UP) {
+            z[i][0] = interp<T>(img + (size_t)(c0 + i) * hw, tp);
+          } else {
+            load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) z[i][v] = neg_inf();
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float cm = m[v];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          if (z[i][v] > cm) { cm = z[i][v]; idx[v] = c0 + i; }  // strict '>' keeps the lowest index
+        }
+        const float nm = -cm * kLog2e;
+        float acc = s[v] * ex2(fmaf(m[v], kLog2e, nm));
+#pragma unroll
+        for (int i = 0; i < CH; ++i) acc += ex2(fmaf(z[i][v], kLog2e, nm));
+        s[v] = acc;
+        m[v] = cm;
+      }
+    }
+
+    float lse[V], lpx[V], pwv[V];
+    if (p.pw) {
+      load_f32<V>(p.pw + (size_t)n * HW + px0, pwv);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) pwv[v] = 1.f;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      lse[v] = m[v] + logf(s[v]);
+      const long long yy = y[v];
+      const bool ign = (yy == p.ignore_index);
+      const bool inr = (yy >= 0 && yy < (long long)C);
+      const bool valid = !ign && inr;
+      n_bad += (!ign && !inr);
+      n_valid += !ign;
+      float l = 0.f;
+      if (valid) {
+        float zy;
+        if constexpr (UP) zy = interp<T>(img + (size_t)yy * hw, tp);
+        else zy = to_float<T>(img[(size_t)yy * HW + px0 + v]);
+        const float wt = p.cw ? __ldg(p.cw + yy) : 1.f;
+        l = wt * (lse[v] - zy) * pwv[v];
+      }
+      lpx[v] = l * p.lw;
+      loss_acc += l;
+      const bool av = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
+      n_acc += av;
+      n_correct += (av && (long long)idx[v] == yy);
+    }
+    if (p.lse) store_f32<V>(p.lse + (size_t)n * HW + px0, lse);
+    if (p.loss_px) store_f32<V>(p.loss_px + (size_t)n * HW + px0, lpx);
+  }
+
+  double r[5] = {(double)loss_acc, (double)n_valid, (double)n_correct, (double)n_bad, (double)n_acc};
+  block_sum<double, 5>(r, sred);
+  if (threadIdx.x == 0) {
+    atomicAdd(reinterpret_cast<double*>(p.stats + B200SEG_ST_CE_SUM), r[0]);
+    atomicAdd(p.stats + B200SEG_ST_N_VALID, (unsigned long long)r[1]);
+    atomicAdd(p.stats + B200SEG_ST_N_CORRECT, (unsigned long long)r[2]);
+    if (r[3] != 0.0) atomicAdd(p.stats + B200SEG_ST_N_BAD, (unsigned long long)r[3]);
+    atomicAdd(p.stats + B200SEG_ST_N_ACC, (unsigned long long)r[4]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct CeBwdParams {
+  const void* logits;
+  const void* labels;
+  const float* pw;
+  const float* cw;
+  const float* lse;
+  const float* grad_out;   // scalar or null
+  const float* grad_px;    // per pixel or null
+  const unsigned long long* stats;
+  void* grad;
+  float* grad_accum;
+  int label_dtype;
+  int N, C, h, w, H, W;
+  int align_corners;
+  int use_nvalid;
+  long long ignore_index;
+  float scale_host;
+  float sh, sw;
+};
+
+__device__ __forceinline__ float ce_global_scale(const CeBwdParams& p) {
+  float G = p.scale_host;
+  if (p.grad_out) G *= __ldg(p.grad_out);
+  if (p.use_nvalid) {
+    const double nv = (double)(long long)p.stats[B200SEG_ST_N_VALID];
+    G = (float)((double)G / (nv + 1.1920928955078125e-07));
+  }
+  return G;
+}
+
+template <typename T, int V, int CH, bool UP>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
+  static_assert(!UP || V == 1, "resize-fused variant is one pixel per thread");
+  const int n = blockIdx.y;
+  const int C = p.C;
+  const long long HW = (long long)p.H * p.W;
+  const long long hw = (long long)p.h * p.w;
+  const long long px0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (px0 >= HW) return;
+  const float G = ce_global_scale(p);
+
+  long long y[V];
+  load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
+  float lse[V], coef[V], nl[V];
+  load_f32<V>(p.lse + (size_t)n * HW + px0, lse);
+  if (p.pw) {
+    load_f32<V>(p.pw + (size_t)n * HW + px0, coef);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) coef[v] = 1.f;
+  }
+  if (p.grad_px) {
+    float g[V];
+    load_f32<V>(p.grad_px + (size_t)n * HW + px0, g);
+#pragma unroll
+    for (int v = 0; v < V; ++v) coef[v] *= g[v];
+  }
+  int yc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const long long yy = y[v];
+    const bool valid = (yy != p.ignore_index) && yy >= 0 && yy < (long long)C;
+    const float wt = (valid && p.cw) ? __ldg(p.cw + yy) : 1.f;
+    coef[v] = valid ? coef[v] * wt * G : 0.f;
+    yc[v] = valid ? (int)yy : -1;
+    nl[v] = -lse[v] * kLog2e;
+  }
+
+  const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * hw;
+  if constexpr (UP) {
+    const Taps tp = make_taps((int)(px0 / p.W), (int)(px0 % p.W), p.h, p.w, p.sh, p.sw, p.align_corners != 0);
+    float* acc = p.grad_accum + (size_t)n * C * hw;
+    if (coef[0] == 0.f) return;
+    for (int c = 0; c < C; ++c) {
+      const float z = interp<T>(img + (size_t)c * hw, tp);
+      float g = coef[0] * ex2(fmaf(z, kLog2e, nl[0]));
+      if (c == yc[0]) g -= coef[0];
+      float* a = acc + (size_t)c * hw;
+      atomicAdd(a + tp.o00, tp.w00 * g);
+      atomicAdd(a + tp.o01, tp.w01 * g);
+      atomicAdd(a + tp.o10, tp.w10 * g);
+      atomicAdd(a + tp.o11, tp.w11 * g);
+    }
+  } else {
+    T* gimg = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW;
+    for (int c0 = 0; c0 < C; c0 += CH) {
+      float z[CH][V];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (c0 + i < C) load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (c0 + i < C) {
+          float g[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            g[v] = coef[v] * ex2(fmaf(z[i][v], kLog2e, nl[v]));
+            if (c0 + i == yc[v]) g[v] -= coef[v];
+          }
+          store_vec<T, V>(gimg + (size_t)(c0 + i) * HW + px0, g);
+        }
+      }
+    }
+  }
+}
+
+template <typename T> __global__ void cast_accum_kernel(const float* __restrict__ a, T* __restrict__ o, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) o[i] = from_float<T>(a[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: statistics -> scalars (models/losses/utils.py:48-80, accuracy.py:51-60, dice_loss.py:31-58)
+__global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_desc d) {
+  __shared__ double sred[32];
+  const double eps = 1.1920928955078125e-07;  // torch.finfo(torch.float32).eps
+  if (threadIdx.x == 0) {
+    const double sum = *reinterpret_cast<const double*>(d.stats + B200SEG_ST_CE_SUM);
+    const double n_valid = (double)(long long)d.stats[B200SEG_ST_N_VALID];
+    const double n_correct = (double)(long long)d.stats[B200SEG_ST_N_CORRECT];
+    const double n_acc = (double)(long long)d.stats[B200SEG_ST_N_ACC];
+    double loss = sum;
+    if (d.ce_reduction == B200SEG_RED_MEAN) {
+      if (d.ce_has_avg_factor) loss = sum / (double)(float)(d.ce_avg_factor + eps);
+      else if (d.ce_avg_non_ignore) loss = sum / (double)(float)(n_valid + eps);
+      else loss = sum / (double)d.n_pixels;
+    }
+    d.out[B200SEG_OUT_LOSS_CE] = (float)((double)d.ce_loss_weight * loss);
+    // accuracy.py:55-60: (correct.float().sum() + eps) * (100.0 / (n + eps)), evaluated in fp32
+    const float r = (float)(100.0 / (n_acc + eps));
+    d.out[B200SEG_OUT_ACC] = ((float)n_correct + (float)eps) * r;
+  }
+  if (d.dice_part == nullptr) {
+    if (threadIdx.x == 0) d.out[B200SEG_OUT_LOSS_DICE] = 0.f;
+    return;
+  }
+  // K: d(loss_dice)/d(per-sample, per-class dice term)
+  double K = (double)d.dice_loss_weight / ((double)d.C * (double)d.N);
+  if (d.dice_has_avg_factor && d.dice_reduction == B200SEG_RED_MEAN) K /= (double)(float)(d.dice_avg_factor + eps);
+  double part = 0.0;
+  for (int i = threadIdx.x; i < d.N * d.C; i += blockDim.x) {
+    const int c = i % d.C;
+    const double A = d.dice_part[(size_t)i * 3 + 0], B = d.dice_part[(size_t)i * 3 + 1], T = d.dice_part[(size_t)i * 3 + 2];
+    const double cwv = d.dice_class_weight ? (double)d.dice_class_weight[c] : 1.0;
+    const bool skip = ((long long)c == d.dice_ignore_index);
+    const double num = 2.0 * A + (double)d.dice_smooth;
+    const double den = B + T + (double)d.dice_smooth;
+    if (!skip) part += cwv * (1.0 - num / den);
+    if (d.dice_coef) {
+      d.dice_coef[(size_t)i * 2 + 0] = skip ? 0.f : (float)(K * cwv * 2.0 / den);
+      d.dice_coef[(size_t)i * 2 + 1] = skip ? 0.f : (float)(K * cwv * num / (den * den));
+    }
+  }
+  double r[1] = {part};
+  block_sum<double, 1>(r, sred);
+  if (threadIdx.x == 0) d.out[B200SEG_OUT_LOSS_DICE] = (float)(K * r[0]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host dispatch
+template <typename T> static int launch_ce_fwd(const CeFwdParams& p, bool up, bool vec, cudaStream_t st) {
+  const long long HW = (long long)p.H * p.W;
+  constexpr int VV = 16 / (int)sizeof(T);
+  if (up) {
+    dim3 grid((unsigned)((HW + 255) / 256), p.N);
+    ce_fwd_kernel<T, 1, 8, true><<<grid, 256, 0, st>>>(p);
+  } else if (vec) {
+    dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
+    ce_fwd_kernel<T, VV, (VV == 4 ? 8 : 4), false><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)((HW + 255) / 256), p.N);
+    ce_fwd_kernel<T, 1, 8, false><<<grid, 256, 0, st>>>(p);
+  }
+  count_launch();
+  return check_launch("ce_fwd_kernel");
+}
+
+template <typename T> static int launch_ce_bwd(const CeBwdParams& p, bool up, bool vec, cudaStream_t st) {
+  const long long HW = (long long)p.H * p.W;
+  constexpr int VV = 16 / (int)sizeof(T);
+  if (up) {
+    const long long nel = (long long)p.N * p.C * p.h * p.w;
+    B200SEG_CUDA(cudaMemsetAsync(p.grad_accum, 0, (size_t)nel * sizeof(float), st));
+    dim3 grid((unsigned)((HW + 255) / 256), p.N);
+    ce_bwd_kernel<T, 1, 8, true><<<grid, 256, 0, st>>>(p);
+    count_launch();
+    if (int e = check_launch("ce_bwd_kernel<UP>")) return e;
+    const int blocks = (int)((nel + 255) / 256 < 4 * kSMs ? (nel + 255) / 256 : 4 * kSMs);
+    cast_accum_kernel<T><<<blocks, 256, 0, st>>>(p.grad_accum, reinterpret_cast<T*>(p.grad), nel);
+    count_launch();
+    return check_launch("cast_accum_kernel");
+  }
+  if (vec) {
+    dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
+    ce_bwd_kernel<T, VV, (VV == 4 ? 8 : 4), false><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)((HW + 255) / 256), p.N);
+    ce_bwd_kernel<T, 1, 8, false><<<grid, 256, 0, st>>>(p);
+  }
+  count_launch();
+  return check_launch("ce_bwd_kernel");
+}
+
+int ce_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
+  CeFwdParams p;
+  p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;
+  p.lse = (d->flags & B200SEG_WANT_LSE) ? d->lse : nullptr;
+  p.loss_px = (d->flags & B200SEG_WANT_LOSS_PX) ? d->loss_px : nullptr;
+  p.stats = reinterpret_cast<unsigned long long*>(d->stats);
+  p.label_dtype = d->label_dtype;
+  p.N = d->N; p.C = d->C; p.h = d->h; p.w = d->w; p.H = d->H; p.W = d->W;
+  p.align_corners = d->align_corners; p.flags = d->flags;
+  p.ignore_index = d->ignore_index; p.acc_has_ignore = d->acc_has_ignore; p.acc_ignore = d->acc_ignore_index;
+  p.lw = d->ce_loss_weight;
+  p.sh = resize_scale(d->h, d->H, d->align_corners != 0);
+  p.sw = resize_scale(d->w, d->W, d->align_corners != 0);
+  const bool up = (d->h != d->H) || (d->w != d->W);
+  const long long HW = (long long)d->H * d->W;
+  const int VV = 16 / logit_bytes(d->logit_dtype);
+  const bool vec = !up && (HW % VV == 0) && aligned16(d->logits) && aligned16(d->labels) &&
+                   (!p.pw || aligned16(p.pw)) && (!p.lse || aligned16(p.lse)) && (!p.loss_px || aligned16(p.loss_px));
+  switch (d->logit_dtype) {
+    case B200SEG_F32: return launch_ce_fwd<float>(p, up, vec, st);
+    case B200SEG_BF16: return launch_ce_fwd<__nv_bfloat16>(p, up, vec, st);
+    case B200SEG_F16: return launch_ce_fwd<__half>(p, up, vec, st);
+  }
+  set_error("unsupported logit dtype %d", d->logit_dtype);
+  return 1;
+}
+
+int ce_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
+  CeBwdParams p;
+  p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;
+  p.lse = d->lse; p.grad_out = d->ce_grad_out; p.grad_px = d->ce_grad_px;
+  p.stats = reinterpret_cast<const unsigned long long*>(d->stats);
+  p.grad = d->grad_logits; p.grad_accum = d->grad_accum;
+  p.label_dtype = d->label_dtype;
+  p.N = d->N; p.C = d->C; p.h = d->h; p.w = d->w; p.H = d->H; p.W = d->W;
+  p.align_corners = d->align_corners; p.use_nvalid = d->ce_use_nvalid;
+  p.ignore_index = d->ignore_index; p.scale_host = d->ce_scale_host;
+  p.sh = resize_scale(d->h, d->H, d->align_corners != 0);
+  p.sw = resize_scale(d->w, d->W, d->align_corners != 0);
+  const bool up = (d->h != d->H) || (d->w != d->W);
+  B200SEG_REQUIRE(!up || d->grad_accum, "loss_bwd: grad_accum scratch is required when (h,w) != (H,W)");
+  const long long HW = (long long)d->H * d->W;
+  const int VV = 16 / logit_bytes(d->logit_dtype);
+  const bool vec = !up && (HW % VV == 0) && aligned16(d->logits) && aligned16(d->labels) && aligned16(d->lse) &&
+                   aligned16(d->grad_logits) && (!p.pw || aligned16(p.pw)) && (!p.grad_px || aligned16(p.grad_px));
+  switch (d->logit_dtype) {
+    case B200SEG_F32: return launch_ce_bwd<float>(p, up, vec, st);
+    case B200SEG_BF16: return launch_ce_bwd<__nv_bfloat16>(p, up, vec, st);
+    case B200SEG_F16: return launch_ce_bwd<__half>(p, up, vec, st);
+  }
+  set_error("unsupported logit dtype %d", d->logit_dtype);
+  return 1;
+}
+
+int finalize_dispatch(const b200seg_finalize_desc* d, cudaStream_t st) {
+  finalize_kernel<<<1, 256, 0, st>>>(*d);
+  count_launch();
+  return check_launch("finalize_kernel");
+}
+
+}  // namespace b200seg

@@ -1,0 +1,237 @@
+/*
+ * b200seg.h — C ABI of libb200seg.so: the B200 (sm_100a) logits -> loss -> metrics hot path.
+ *
+ * This is the drop-in boundary. The reference (HanHan-TR/Image_Segmentation_lab) has no
+ * native code; on this path it calls ATen. Each entry point below replaces one chain of those
+ * calls, cited as reference file:line:
+ *
+ *   b200seg_resize_bilinear_fwd/bwd  utils/ops.py:7-26 (F.interpolate, mode='bilinear'), hot call
+ *                                    models/decode_heads/decode_head.py:266-269
+ *   b200seg_loss_fwd / _bwd          decode_head.py:266-295 fused:
+ *                                      resize              utils/ops.py:26
+ *                                      cross_entropy       models/losses/cross_entropy_loss.py:23-74
+ *                                      weight_reduce_loss  models/losses/utils.py:48-80
+ *                                      DiceLoss.forward    models/losses/dice_loss.py:103-134 (+ :23-58)
+ *                                      accuracy (top-1)    models/losses/accuracy.py:6-61
+ *   b200seg_loss_fused_fwdbwd        the same chain plus its autograd backward in one pass
+ *   b200seg_confusion_labels         SegEvaluator.intersect_and_union core/evaluation/metrics.py:210-270
+ *   b200seg_confusion_logits         SegEvaluator.process argmax :101-107 + intersect_and_union
+ *
+ * Conventions
+ *   - Plain pointers and sizes only. Every pointer is a DEVICE pointer unless marked "host".
+ *   - The caller owns every buffer (inputs, outputs, workspaces). Nothing is allocated or freed.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *     and every call is CUDA-graph capturable.
+ *   - Return value: 0 on success, non-zero on error; b200seg_last_error() returns a thread-local
+ *     message for the last failing call on the calling thread.
+ *   - Tensors are dense, row-major: logits (N,C,h,w), labels / per-pixel maps (N,H,W).
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_ABI_VERSION 3
+
+/* logit element types */
+enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
+/* label element types (read directly; no .long() pass — reference cross_entropy_loss.py:283) */
+enum { B200SEG_L_U8 = 0, B200SEG_L_I16 = 1, B200SEG_L_I32 = 2, B200SEG_L_I64 = 3, B200SEG_L_F32 = 4, B200SEG_L_F64 = 5 };
+
+/* what b200seg_loss_fwd computes (bit flags) */
+enum {
+  B200SEG_WANT_CE      = 1,   /* softmax cross-entropy sum                                   */
+  B200SEG_WANT_DICE    = 2,   /* per-(n,c) dice partial sums                                 */
+  B200SEG_WANT_ACC     = 4,   /* top-1 correct / valid counts                                */
+  B200SEG_WANT_LOSS_PX = 8,   /* write per-pixel CE loss (reduction='none')                  */
+  B200SEG_WANT_LSE     = 16   /* write per-pixel log-sum-exp (saved for the backward)        */
+};
+
+/* Layout of the 64-bit statistics block filled by b200seg_loss_fwd (B200SEG_STATS_WORDS words). */
+enum {
+  B200SEG_ST_CE_SUM    = 0,   /* double : sum_px  pixel_weight * class_weight[y] * nll       */
+  B200SEG_ST_N_VALID   = 1,   /* int64  : #pixels with label != ignore_index                 */
+  B200SEG_ST_N_CORRECT = 2,   /* int64  : #valid pixels whose arg-max class == label         */
+  B200SEG_ST_N_BAD     = 3,   /* int64  : #pixels whose label is neither ignore nor in [0,C) */
+  B200SEG_ST_N_ACC     = 4,   /* int64  : accuracy denominator (honours acc_has_ignore)      */
+  B200SEG_STATS_WORDS  = 8
+};
+
+/* outputs of b200seg_loss_finalize (float32 words) */
+enum { B200SEG_OUT_LOSS_CE = 0, B200SEG_OUT_LOSS_DICE = 1, B200SEG_OUT_ACC = 2, B200SEG_OUT_WORDS = 4 };
+
+/* reductions (models/losses/utils.py:28-80) */
+enum { B200SEG_RED_NONE = 0, B200SEG_RED_MEAN = 1, B200SEG_RED_SUM = 2 };
+
+typedef struct b200seg_loss_desc {
+  /* ---- tensors ---- */
+  const void*  logits;          /* (N,C,h,w)  logit_dtype                                      */
+  const void*  labels;          /* (N,H,W)    label_dtype                                      */
+  const float* pixel_weight;    /* (N,H,W) f32 or NULL   cross_entropy(weight=)                */
+  const float* ce_class_weight; /* (C) f32 or NULL       cross_entropy(class_weight=)          */
+  int32_t logit_dtype, label_dtype;
+  int32_t N, C, h, w, H, W;     /* (h,w) != (H,W) => bilinear resize fused in (utils/ops.py:26) */
+  int32_t align_corners;
+  int32_t flags;                /* B200SEG_WANT_*                                              */
+  int64_t ignore_index;         /* CE ignore_index                                             */
+  int32_t acc_has_ignore;       /* accuracy(ignore_index=None) -> 0                            */
+  int32_t reserved0;
+  int64_t acc_ignore_index;
+  /* ---- dice (models/losses/dice_loss.py) ---- */
+  int64_t dice_ignore_index;
+  float   dice_exponent;
+  float   reserved1;
+  /* ---- outputs ---- */
+  float*   lse;                 /* (N,H,W) f32 or NULL                                         */
+  float*   loss_px;             /* (N,H,W) f32 or NULL : loss_weight*pixel_weight*cw[y]*nll    */
+  float    ce_loss_weight;      /* applied to loss_px only                                     */
+  float    reserved2;
+  uint64_t* stats;              /* B200SEG_STATS_WORDS x 8 bytes, zeroed by the call           */
+  double*  dice_part;           /* (N,C,3) doubles [sum p*t*v, sum p^e, sum t] zeroed by call  */
+} b200seg_loss_desc;
+
+/* Fused forward: resize + log-softmax + NLL (+ dice partial sums) (+ top-1 accuracy counts). */
+int b200seg_loss_fwd(const b200seg_loss_desc* d, void* stream);
+
+typedef struct b200seg_finalize_desc {
+  const uint64_t* stats;
+  const double*   dice_part;        /* or NULL */
+  const float*    dice_class_weight;/* (C) or NULL */
+  int32_t N, C;
+  int64_t n_pixels;                 /* N*H*W                                                   */
+  int32_t ce_reduction;             /* B200SEG_RED_MEAN / _SUM (NONE is handled by loss_px)    */
+  int32_t ce_avg_non_ignore;        /* cross_entropy_loss.py:67-68                             */
+  int32_t ce_has_avg_factor;        /* utils.py:72-76                                          */
+  int32_t dice_has_avg_factor;
+  double  ce_avg_factor;
+  double  dice_avg_factor;
+  float   ce_loss_weight;
+  float   dice_loss_weight;
+  float   dice_smooth;
+  int32_t dice_reduction;
+  int64_t dice_ignore_index;
+  float*  out;                      /* B200SEG_OUT_WORDS floats                                */
+  float*  dice_coef;                /* (N,C,2) f32 [alpha,beta] for the backward, or NULL      */
+} b200seg_finalize_desc;
+
+/* One tiny launch: statistics -> loss_ce, loss_dice, acc_seg scalars (+ dice backward table). */
+int b200seg_loss_finalize(const b200seg_finalize_desc* d, void* stream);
+
+typedef struct b200seg_loss_bwd_desc {
+  const void*  logits;
+  const void*  labels;
+  const float* pixel_weight;
+  const float* ce_class_weight;
+  const float* lse;                 /* (N,H,W) from the forward                                */
+  int32_t logit_dtype, label_dtype;
+  int32_t N, C, h, w, H, W;
+  int32_t align_corners;
+  int32_t flags;                    /* B200SEG_WANT_CE | B200SEG_WANT_DICE                     */
+  int64_t ignore_index;
+  int64_t dice_ignore_index;
+  float   dice_exponent;
+  /* CE coefficient: grad_z = G * pixel_weight * cw[y] * (p - onehot), with
+   *   G = ce_scale_host * (*ce_grad_out or 1) / (ce_use_nvalid ? stats[N_VALID] + eps : 1)
+   * per-pixel upstream gradient (reduction='none') multiplies in through ce_grad_px.            */
+  float   ce_scale_host;
+  const float*    ce_grad_out;      /* scalar f32 (device) or NULL                             */
+  const float*    ce_grad_px;       /* (N,H,W) f32 or NULL                                     */
+  const uint64_t* stats;            /* for n_valid when ce_use_nvalid                          */
+  int32_t ce_use_nvalid;
+  int32_t reserved0;
+  const float* dice_coef;           /* (N,C,2) from finalize                                   */
+  const float* dice_grad_out;       /* scalar f32 (device) or NULL                             */
+  void*   grad_logits;              /* (N,C,h,w) logit_dtype, fully overwritten                */
+  float*  grad_accum;               /* (N,C,h,w) f32 scratch: required when (h,w)!=(H,W)       */
+} b200seg_loss_bwd_desc;
+
+/* Fused backward: d(loss)/d(logits) in one pass (softmax Jacobian, dice, resize transpose). */
+int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream);
+
+/* Bytes of scratch needed by b200seg_loss_fused_fwdbwd for the given problem (0 if none). */
+int64_t b200seg_loss_fused_workspace_bytes(int32_t N, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W,
+                                           int32_t align_corners);
+
+typedef struct b200seg_loss_fused_desc {
+  b200seg_loss_desc fwd;            /* CE (+ACC) only; dice is not supported by this entry     */
+  /* grad_logits = scale * d(sum_px pw*cw*nll)/dz with
+   *   scale = grad_scale_host * (*grad_out or 1) / (use_nvalid ? n_valid + eps : 1)
+   * The upstream gradient is usually unknown while the forward runs: pass grad_out = NULL and
+   * apply it later with b200seg_loss_fused_combine (resize-fused case, defer_combine = 1) or
+   * b200seg_scale_inplace (label-resolution case).                                            */
+  float   grad_scale_host;
+  int32_t use_nvalid;               /* resize-fused case only                                  */
+  const float* grad_out;            /* scalar f32 (device) or NULL                             */
+  void*   grad_logits;              /* (N,C,h,w) logit_dtype; NULL = forward only (resize-fused) */
+  void*   workspace;                /* b200seg_loss_fused_workspace_bytes()                    */
+  int32_t defer_combine;            /* resize-fused: leave the corner sums in `workspace`      */
+  int32_t reserved;
+} b200seg_loss_fused_desc;
+
+/* Forward and backward of resize + CE in ONE pass over the logits (the gradient of a sum/mean
+ * loss does not depend on other pixels, so it is produced while the logits are on chip).      */
+int b200seg_loss_fused_fwdbwd(const b200seg_loss_fused_desc* d, void* stream);
+
+/* Second half of the resize-fused single pass: adds the 4 corner sums around every low-res logit
+ * (fixed order, deterministic) and applies scale_host * (*grad_out or 1) / (n_valid + eps)?.  */
+int b200seg_loss_fused_combine(const void* workspace, void* grad_logits, int32_t logit_dtype, int32_t N, int32_t C,
+                               int32_t h, int32_t w, float scale_host, const float* grad_out, int32_t use_nvalid,
+                               const uint64_t* stats, void* stream);
+
+/* x *= *g in place (n elements of dtype); returns immediately on the device when *g == 1. */
+int b200seg_scale_inplace(void* x, int32_t dtype, int64_t n, const float* g, void* stream);
+
+/* Bilinear resize, ATen semantics (torch/include/ATen/native/UpSample.h:271-312,442-476). */
+int b200seg_resize_bilinear_fwd(const void* in, void* out, int32_t dtype, int32_t NC, int32_t h, int32_t w,
+                                int32_t H, int32_t W, int32_t align_corners, void* stream);
+/* Deterministic transpose (gather form): grad_in (NC,h,w) <- grad_out (NC,H,W). */
+int b200seg_resize_bilinear_bwd(const void* grad_out, void* grad_in, int32_t dtype, int32_t NC, int32_t h,
+                                int32_t w, int32_t H, int32_t W, int32_t align_corners, void* stream);
+/* Nearest resize (F.interpolate default mode of utils/ops.py:7-26). */
+int b200seg_resize_nearest_fwd(const void* in, void* out, int32_t dtype, int32_t NC, int32_t h, int32_t w,
+                               int32_t H, int32_t W, void* stream);
+
+/* One image of an evaluation batch. */
+typedef struct b200seg_image {
+  const void* pred;                 /* label map (H,W) pred_dtype, or logits (C,h,w) logit dtype */
+  const void* gt;                   /* (H,W) gt_dtype                                          */
+  int64_t n_pixels;                 /* H*W                                                     */
+  int32_t h, w;                     /* logits only: source size (== H,W unless resize fused)   */
+  int32_t H, W;
+} b200seg_image;
+
+/* Area histograms from label maps. areas: (n_images,3,C) int64 [intersect, pred, label],
+ * ACCUMULATED into (caller zeroes). `images` is a device array of n_images descriptors.
+ * `chunk_prefix` is a device array of n_images+1 int64: prefix sum of ceil(n_pixels/chunk).  */
+int b200seg_confusion_labels(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
+                             int64_t total_chunks, int32_t chunk_pixels, int32_t pred_dtype, int32_t gt_dtype,
+                             int32_t C, int64_t ignore_index, int64_t* areas, void* stream);
+
+/* Same, with the arg-max over classes fused in (logits (C,H,W) per image; lowest index wins ties);
+ * optionally writes the int64 label map to pred_out[i] ((H,W) each, may be NULL).              */
+int b200seg_confusion_logits(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
+                             int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype, int32_t gt_dtype,
+                             int32_t C, int64_t ignore_index, int64_t* areas, int64_t* const* pred_out,
+                             void* stream);
+int32_t b200seg_confusion_chunk_pixels(void);
+
+/* top-k accuracy counts (models/losses/accuracy.py:6-61) for arbitrary k and thresh:
+ * counts[j] = #valid pixels whose label ranks < topk[j]; counts[n_topk] = #valid pixels.      */
+int b200seg_topk_counts(const void* logits, const void* labels, int32_t logit_dtype, int32_t label_dtype,
+                        int32_t N, int32_t C, int64_t HW, int32_t has_ignore, int64_t ignore_index,
+                        const int32_t* topk_host, int32_t n_topk, int32_t has_thresh, float thresh,
+                        int64_t* counts, void* stream);
+
+const char* b200seg_last_error(void);
+int32_t b200seg_abi_version(void);
+/* number of kernels this library has launched from the calling process (for bench accounting) */
+int64_t b200seg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */
