@@ -1,0 +1,527 @@
+#!/usr/bin/env python
+"""Benchmark of the logits -> loss -> metrics hot path (BASELINE.json metric: Mpix/s, % of B200 HBM peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
+
+Headline workload (config.workload, BASELINE.json configs[1]): FCN-style head at Cityscapes shape — fp32 logits
+(8,19,64,128) bilinearly resized to 512x1024 labels, cross-entropy with ignore_index=255, forward AND backward, plus
+the in-loop top-1 accuracy. A "step" is one such batch per GPU; a pixel is a label-resolution pixel. Under
+torchrun every rank runs the same per-GPU batch (weak scaling, images are independent) and the only exchange is
+one all-reduce of the 8-double statistics vector per step on a side stream.
+
+  value         device-resident throughput: CUDA-graph replays of the step over a ring of input sets larger than L2,
+                timed with CUDA events on the launching stream, max over ranks.
+  e2e           the same step through the public API with HOST inputs: pinned H2D of logits + labels every step,
+                fused_resize_losses + backward, D2H read of the loss.
+  roofline      the dominant kernel (up_fused_kernel) timed alone with CUDA events: algorithmic bytes / time vs the
+                measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline  the oracle (the reference's ATen chain restated, oracle/oracle.py) on the host cores, bounded sample.
+  workloads     extra single-GPU results for BASELINE configs 3, 4 and 5 (HBM-bound shapes), each with its roofline.
+
+`--impl reference` times the reference's CPU implementation of the same workload (the oracle port; the reference is
+pure Python and cannot travel to the GPU box) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'Mpix/s: logits resize+CE fwd/bwd and mIoU eval; % of B200 HBM peak'
+C2 = dict(N=8, C=19, h=64, w=128, H=512, W=1024, ignore=255)
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured'
+    except Exception:
+        return HBM_FALLBACK_GBS, 'fallback'
+
+
+# ---------------------------------------------------------------------------------------------- synthetic data
+def make_logits(shape, seed, dtype=torch.float32, device='cpu'):
+    """randn*2, +1 on one class per pixel, quantised to 2^-6 (no soft-max rounding ties)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    n, c, h, w = shape
+    x = torch.randn(shape, generator=g, device=device) * 2.0
+    hot = torch.randint(0, c, (n, 1, h, w), generator=g, device=device)
+    x.scatter_add_(1, hot, torch.ones((n, 1, h, w), device=device))
+    x = torch.round(x * 64.0) / 64.0
+    return x.to(dtype)
+
+
+def make_labels(shape, num_classes, seed, ignore=255, frac=0.1, block=16, dtype=torch.int64, device='cpu'):
+    """16x16-pixel constant blocks of random classes, ~10% of the blocks set to ignore_index."""
+    g = torch.Generator(device=device).manual_seed(seed + 7)
+    n, h, w = shape
+    bh, bw = (h + block - 1) // block, (w + block - 1) // block
+    y = torch.randint(0, num_classes, (n, bh, bw), generator=g, device=device)
+    if ignore is not None and frac > 0:
+        y[torch.rand((n, bh, bw), generator=g, device=device) < frac] = ignore
+    y = y.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :h, :w].contiguous()
+    return y.to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def cpu_step(x, y, ignore):
+    from oracle import oracle as O
+    x.grad = None
+    out = O.head_losses(x, y, [('ce', {}, 'loss_ce')], align_corners=False, ignore_index=ignore)
+    out['loss_ce'].backward()
+    return out
+
+
+def run_cpu(steps, warmup, n_images):
+    """The reference's CPU path (oracle port) on a bounded sample: n_images of the C2 batch per step."""
+    warnings.simplefilter('ignore')
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = make_logits((n_images, C2['C'], C2['h'], C2['w']), 1234 + 100).requires_grad_(True)
+    y = make_labels((n_images, C2['H'], C2['W']), C2['C'], 1234 + 100, C2['ignore']).unsqueeze(1)
+    for _ in range(warmup):
+        cpu_step(x, y, C2['ignore'])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(x, y, C2['ignore'])
+    dt = time.perf_counter() - t0
+    px = n_images * C2['H'] * C2['W'] * steps
+    return px / dt / 1e6, dt / steps * 1e3
+
+
+def reference_main(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_img = 1
+    value, ms = run_cpu(args.steps, min(args.warmup, 2), n_img)
+    cores = torch.get_num_threads()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': min(args.warmup, 2), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(),
+        'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d of the %d images of the batch per step (resize + CE fwd/bwd + accuracy, torch %s CPU, '
+                                   'os.cpu_count()=%s)' % (n_img, C2['N'], torch.__version__, os.cpu_count())},
+        'e2e': {'value': value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {'workload': 'C2: FCN-style head, Cityscapes shape — fp32 logits (8,19,64,128) bilinear-resized (align_corners=False) '
+                        'to 512x1024, CE ignore_index=255 + top-1 accuracy, forward+backward',
+            'batch_per_gpu': C2['N'], 'num_classes': C2['C'], 'logit_hw': [C2['h'], C2['w']], 'label_hw': [C2['H'], C2['W']],
+            'label_dtype': 'int64', 'pixels_per_step_per_gpu': C2['N'] * C2['H'] * C2['W']}
+
+
+# ---------------------------------------------------------------------------------------------- b200 arm
+def timed_events(fn, iters, stream=None):
+    """ms per call of fn() over iters calls, CUDA events on the current stream."""
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def b200_main(args):
+    import torch.distributed as dist
+
+    import image_segmentation_lab_b200 as B
+    from image_segmentation_lab_b200 import _lib
+    from image_segmentation_lab_b200 import distributed as D
+
+    warnings.simplefilter('ignore')
+    rank, local, world = D.init_from_env()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    else:
+        raise RuntimeError('bench.py needs a CUDA device: the B200 path has no CPU fallback')
+    dev = torch.device('cuda', local)
+    lib = B.load_library()
+    peak, peak_kind = hbm_peak()
+    K, W = args.steps, max(args.warmup, 3)
+    N, Cc, h, w, H, Wd, ign = C2['N'], C2['C'], C2['h'], C2['w'], C2['H'], C2['W'], C2['ignore']
+    px_step = N * H * Wd
+
+    # ---- ring of input sets: 8 x (5.0 MB logits + 33.6 MB labels) = 308 MB > 126 MB L2
+    R = 8
+    seed0 = 1234 + 100 + rank
+    xs = [make_logits((N, Cc, h, w), seed0 + 1000 * i, device=dev).requires_grad_(True) for i in range(R)]
+    ys = [make_labels((N, H, Wd), Cc, seed0 + 1000 * i, ign, device=dev).unsqueeze(1) for i in range(R)]
+    ce = B.CrossEntropyLoss()
+
+    def step(i):
+        xs[i].grad = None
+        r = B.fused_resize_losses(xs[i], ys[i], ce, align_corners=False, ignore_index=ign, return_stats=True)
+        r['loss_ce'].backward()
+        return r
+
+    # launches per step (host counter; graph replays do not pass through the host-side counter)
+    torch.cuda.synchronize()
+    c0 = B.launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches_per_step = B.launch_count() - c0
+
+    # ---- capture one graph per input set
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(R):
+            step(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs, outs = [], []
+    for i in range(R):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs.append(step(i))
+        graphs.append(g)
+    stats = [o['_stats'] for o in outs]
+    comm = torch.cuda.Stream(device=dev)
+    slot_free = [torch.cuda.Event() for _ in range(R)]
+    ready = [torch.cuda.Event() for _ in range(R)]
+
+    def run_step(k):
+        i = k % R
+        cur = torch.cuda.current_stream()
+        if world > 1:
+            cur.wait_event(slot_free[i])
+        graphs[i].replay()
+        if world > 1:  # one 64-byte all-reduce per step, off the compute stream
+            ready[i].record(cur)
+            comm.wait_event(ready[i])
+            with torch.cuda.stream(comm):
+                dist.all_reduce(stats[i], op=dist.ReduceOp.SUM)
+                slot_free[i].record(comm)
+
+    for k in range(W):
+        run_step(k)
+    torch.cuda.current_stream().wait_stream(comm)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for k in range(K):
+        run_step(k)
+    torch.cuda.current_stream().wait_stream(comm)
+    e_ev.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = s_ev.elapsed_time(e_ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * px_step / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e: host inputs, H2D + step + D2H every step, through the public API
+    xh = [make_logits((N, Cc, h, w), seed0 + 77 + i).pin_memory() for i in range(2)]
+    yh = [make_labels((N, H, Wd), Cc, seed0 + 77 + i, ign).unsqueeze(1).pin_memory() for i in range(2)]
+    xd = torch.empty((N, Cc, h, w), device=dev).requires_grad_(True)
+    yd = torch.empty((N, 1, H, Wd), dtype=torch.int64, device=dev)
+    host_loss = []
+
+    def e2e_step(k):
+        with torch.no_grad():
+            xd.copy_(xh[k & 1], non_blocking=True)
+        yd.copy_(yh[k & 1], non_blocking=True)
+        xd.grad = None
+        r = B.fused_resize_losses(xd, yd, ce, align_corners=False, ignore_index=ign)
+        r['loss_ce'].backward()
+        host_loss.append(r['loss_ce'].item())  # D2H read of the step's result (synchronises, as parse_losses does)
+
+    e2e_steps = max(10, min(K, 50))
+    for k in range(3):
+        e2e_step(k)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * px_step * e2e_steps / float(t.item()) / 1e6
+    h2d = xh[0].numel() * 4 + yh[0].numel() * 8
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernel alone (C ABI, CUDA events on the launching stream)
+    roof = None
+    extras = {}
+    cpu_base = None
+    if rank == 0:
+        roof = kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            try:
+                extras = extra_workloads(B, _lib, dev, peak, peak_kind)
+            except Exception as ex:  # extras never invalidate the headline
+                extras = {'error': repr(ex)}
+        v, ms_cpu = run_cpu(6, 1, C2['N'])
+        cpu_base = {'value': v, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                    'sample': 'full C2 batch (8 images), 6 timed steps of resize + CE fwd/bwd + accuracy on the host CPU '
+                              '(torch %s, os.cpu_count()=%s), %.0f ms/step' % (torch.__version__, os.cpu_count(), ms_cpu)}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': dict(workload_config(), l2='ring of %d input sets (%.0f MB) > 126 MB L2; one CUDA graph per set' % (
+                R, R * (xs[0].numel() * 4 + ys[0].numel() * 8) / 1e6), collective='1 all_reduce(8 doubles)/step on a side stream'
+                if world > 1 else 'none (single GPU)'),
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'steps': e2e_steps, 'note': 'pinned host logits+int64 labels copied every step; PCIe-bound'},
+            'gpu_launches': int(launches_per_step * K),
+            'launches_per_step': int(launches_per_step),
+            'roofline': roof,
+        }
+        if cpu_base is not None:
+            line['cpu_baseline'] = cpu_base
+        if extras:
+            line['workloads'] = extras
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind):
+    """up_fused_kernel alone: b200seg_loss_fused_fwdbwd(defer_combine=1) = one 64-byte memset + the kernel."""
+    import ctypes as C
+    dev = xs[0].device
+    R = len(xs)
+    nbytes = lib.b200seg_loss_fused_workspace_bytes(N, Cc, h, w, H, Wd, 0)
+    pbs = [torch.empty(nbytes // 4, dtype=torch.float32, device=dev) for _ in range(2)]
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    descs = []
+    for i in range(R):
+        fu = _lib.LossFusedDesc()
+        fd = fu.fwd
+        fd.logits = xs[i].data_ptr(); fd.labels = ys[i].data_ptr()
+        fd.logit_dtype = _lib.F32; fd.label_dtype = _lib.L_I64
+        fd.N, fd.C, fd.h, fd.w, fd.H, fd.W = N, Cc, h, w, H, Wd
+        fd.flags = _lib.WANT_CE | _lib.WANT_ACC
+        fd.ignore_index = ign; fd.acc_has_ignore = 1; fd.acc_ignore_index = ign
+        fd.dice_exponent = 2.0; fd.ce_loss_weight = 1.0
+        fd.stats = stats.data_ptr()
+        fu.grad_scale_host = 1.0
+        fu.workspace = pbs[i & 1].data_ptr()
+        fu.defer_combine = 1
+        descs.append(fu)
+    stream = _lib.stream_ptr(dev)
+
+    def call(i):
+        rc = lib.b200seg_loss_fused_fwdbwd(C.byref(descs[i % R]), stream)
+        if rc:
+            raise RuntimeError(_lib.last_error())
+
+    for i in range(10):
+        call(i)
+    ms = timed_events(call, 200)
+    s = 4
+    algo = 2 * N * Cc * h * w * s + N * H * Wd * 8          # logits read + gradient written + int64 labels read
+    achieved = algo / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': 'up_fused_kernel<float,20,true>', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'traffic': None, 'peak_kind': peak_kind, 'ms_per_launch': ms,
+            'algorithmic_bytes_per_launch': algo,
+            'note': 'instruction-issue bound (C exps + ~16 C FP32/ALU ops per output pixel), see DESIGN.md; HBM-bound '
+                    'kernels of the path are reported under workloads'}
+
+
+def extra_workloads(B, _lib, dev, peak, peak_kind):
+    """BASELINE configs 3, 4, 5 on one GPU: Mpix/s and HBM-roofline fraction of each kernel group."""
+    out = {}
+
+    def roof(algo_bytes, ms):
+        a = algo_bytes / (ms * 1e-3) / 1e9
+        return {'bound': 'hbm', 'achieved': a, 'peak': peak, 'unit': 'GB/s', 'frac': a / peak, 'peak_kind': peak_kind}
+
+    def bench_losses(name, shape, dtype, losses, label_dtype=torch.int64, iters=20, single=False, plan=''):
+        n, c, hh, ww = shape
+        s = 4 if dtype == torch.float32 else 2
+        xs = [make_logits(shape, 300 + i, dtype=dtype, device=dev).requires_grad_(True) for i in range(2)]
+        ys = [make_labels((n, hh, ww), c, 300 + i, 255, device=dev, dtype=label_dtype).unsqueeze(1) for i in range(2)]
+        L = ys[0].element_size()
+
+        def fwd(i):
+            with torch.no_grad():
+                B.fused_resize_losses(xs[i & 1], ys[i & 1], losses, ignore_index=255)
+
+        def fwdbwd(i):
+            x = xs[i & 1]
+            x.grad = None
+            r = B.fused_resize_losses(x, ys[i & 1], losses, ignore_index=255)
+            tot = None
+            for k, v in r.items():
+                if k.startswith('loss'):
+                    tot = v if tot is None else tot + v
+            tot.backward()
+
+        for i in range(3):
+            fwd(i); fwdbwd(i)
+        ms_f = timed_events(fwd, iters)
+        ms_fb = timed_events(fwdbwd, iters)
+        px = n * hh * ww
+        elems = n * c * hh * ww
+        algo_f = elems * s + px * L
+        algo_fb = (2 * elems * s + px * L) if single else (3 * elems * s + 2 * px * L)
+        out[name] = {'shape': list(shape), 'dtype': str(dtype).replace('torch.', ''), 'pixels': px,
+                     'fwd': dict(ms=ms_f, mpix_s=px / ms_f / 1e3, roofline=roof(algo_f, ms_f)),
+                     'fwd_bwd': dict(ms=ms_fb, mpix_s=px / ms_fb / 1e3, roofline=roof(algo_fb, ms_fb),
+                                     plan=plan),
+                     'algorithmic_bytes': {'fwd': algo_f, 'fwd_bwd': algo_fb}}
+        del xs, ys
+        torch.cuda.empty_cache()
+
+    cw = torch.linspace(0.5, 1.5, 150).tolist()
+    bench_losses('C3_ade20k_bf16_ce_dice', (16, 150, 512, 512), torch.bfloat16,
+                 [B.CrossEntropyLoss(class_weight=cw), B.DiceLoss(loss_weight=3.0)], iters=10,
+                 plan='tile_fwd_kernel + finalize, tile_bwd_kernel (class-split register tiles)')
+    bench_losses('C4_voc_fp32_ce', (32, 21, 512, 512), torch.float32, B.CrossEntropyLoss(), iters=20, single=True,
+                 plan='flat_fused_kernel: forward+backward in one pass')
+    ce2 = B.CrossEntropyLoss()
+    ce2.single_pass = False
+    bench_losses('C4_voc_fp32_ce_two_pass', (32, 21, 512, 512), torch.float32, ce2, iters=10,
+                 plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
+
+    # ---- C5: mIoU sweep. (i) 500 label maps 1024x2048 int64 + float32 gt, one launch; (ii) from logits, 100 images
+    Cn, n_img = 19, 500
+    g = torch.Generator(device=dev).manual_seed(555)
+    gts = [make_labels((1, 1024, 2048), Cn, 500 + i, 255, device=dev)[0].float() for i in range(4)]
+    gt_all = [gts[i % 4] for i in range(n_img)]
+    pred_base = [torch.randint(0, Cn, (1024, 2048), generator=g, device=dev) for _ in range(8)]
+    preds = [pred_base[i % 8].clone() for i in range(n_img)]      # 500 distinct int64 buffers: 8.4 GB
+    gt_all = [t.clone() for t in gt_all]                          # 500 distinct fp32 buffers: 2.1 GB
+
+    def sweep(i):
+        B.areas_device(preds, gt_all, Cn, 255)
+
+    sweep(0)
+    ms = timed_events(sweep, 5)
+    px = n_img * 1024 * 2048
+    out['C5i_miou_label_maps'] = {'images': n_img, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
+                                  'roofline': roof(px * 12, ms), 'algorithmic_bytes': px * 12,
+                                  'note': 'one b200seg_confusion_labels launch for the 500-image list; random predictions '
+                                          '(worst case for the histogram), blocky ground truth'}
+    del preds, pred_base
+    torch.cuda.empty_cache()
+    n_l = 100
+    lbase = [make_logits((1, Cn, 1024, 2048), 900 + i, device=dev) for i in range(4)]
+    logits = [lbase[i % 4].clone() for i in range(n_l)]           # 100 x 159 MB = 15.9 GB
+    gl = gt_all[:n_l]
+
+    def sweep2(i):
+        B.areas_device(logits, gl, Cn, 255, from_logits=True)
+
+    sweep2(0)
+    ms = timed_events(sweep2, 3)
+    px = n_l * 1024 * 2048
+    out['C5ii_miou_from_logits'] = {'images': n_l, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
+                                    'roofline': roof(px * (Cn * 4 + 4), ms), 'algorithmic_bytes': px * (Cn * 4 + 4),
+                                    'note': '100 of the 500 images (15.9 GB of fp32 logits), fused arg-max + areas'}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-extras', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_main(args)
+    else:
+        b200_main(args)
+
+
+if __name__ == '__main__':
+    main()

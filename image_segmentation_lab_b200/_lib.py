@@ -19,7 +19,9 @@ WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
+LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
+    0, 1, 2, 3, 4, 5, 6, 7, 8
 
 LOGIT_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 LABEL_DTYPES = {
@@ -57,7 +59,7 @@ class FinalizeDesc(C.Structure):
         ("ce_loss_weight", C.c_float), ("dice_loss_weight", C.c_float),
         ("dice_smooth", C.c_float), ("dice_reduction", C.c_int32),
         ("dice_ignore_index", C.c_int64),
-        ("out", C.c_void_p), ("dice_coef", C.c_void_p),
+        ("out", C.c_void_p), ("dice_coef", C.c_void_p), ("log_vec", C.c_void_p),
     ]
 
 

@@ -223,25 +223,37 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
   }
 }
 
+// Persistent grid: exactly (SMs x resident CTAs per SM), so the static chunk partition has no tail wave.
+template <typename K> static int persistent_grid(K kernel, int threads, size_t smem, long long total_chunks, int* grid) {
+  int per_sm = 0;
+  B200SEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long g = (long long)kSMs * per_sm;
+  if (g > total_chunks) g = total_chunks;
+  *grid = (int)(g < 1 ? 1 : g);
+  return 0;
+}
+
 template <typename T, bool FROM_LOGITS> static int launch_confusion(const ConfParams& p, cudaStream_t st) {
   // private per-thread counters when they fit in shared memory, else shared atomics
   const size_t need256 = (size_t)3 * p.C * 256 * 4, need128 = (size_t)3 * p.C * 128 * 4;
-  long long want = (long long)kSMs * 4;
-  if (want > p.total_chunks) want = p.total_chunks;
-  if (want < 1) want = 1;
+  int grid = 1;
   if (need256 <= 72 * 1024) {
     auto k = confusion_kernel<T, 256, true, FROM_LOGITS>;
-    B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need256));
-    k<<<(unsigned)want, 256, need256, st>>>(p);
+    static bool attr = false;
+    if (!attr) { B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); attr = true; }
+    if (int e = persistent_grid(k, 256, need256, p.total_chunks, &grid)) return e;
+    k<<<grid, 256, need256, st>>>(p);
   } else if (need128 <= 200 * 1024) {
     auto k = confusion_kernel<T, 128, true, FROM_LOGITS>;
-    B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need128));
-    long long w2 = (long long)kSMs * (need128 <= 100 * 1024 ? 2 : 1) * 2;
-    if (w2 > p.total_chunks) w2 = p.total_chunks;
-    k<<<(unsigned)(w2 < 1 ? 1 : w2), 128, need128, st>>>(p);
+    static bool attr = false;
+    if (!attr) { B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (int e = persistent_grid(k, 128, need128, p.total_chunks, &grid)) return e;
+    k<<<grid, 128, need128, st>>>(p);
   } else {
     auto k = confusion_kernel<T, 256, false, FROM_LOGITS>;
-    k<<<(unsigned)want, 256, (size_t)3 * p.C * 4, st>>>(p);
+    if (int e = persistent_grid(k, 256, (size_t)3 * p.C * 4, p.total_chunks, &grid)) return e;
+    k<<<grid, 256, (size_t)3 * p.C * 4, st>>>(p);
   }
   count_launch();
   return check_launch("confusion_kernel");

@@ -51,7 +51,7 @@ struct UpParams {
 };
 
 template <typename T, int CPT, bool GRAD>
-__global__ void __launch_bounds__(256, 2) up_fused_kernel(const UpParams p) {
+__global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(const UpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sred[5 * 32];
   __shared__ float lam_y[32];  // cell-relative vertical weight of every row of the band
@@ -315,7 +315,12 @@ template <typename T, int CPT, bool GRAD> static int launch_up(const UpParams& p
   size_t smem = (size_t)((p.C * 2 * ncol + 3) & ~3) * 4;
   if (GRAD) smem += (size_t)p.C * 256 * sizeof(float2);
   auto k = up_fused_kernel<T, CPT, GRAD>;
-  B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr = false;
+  if (!attr) {
+    B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  B200SEG_REQUIRE(smem <= 100 * 1024, "loss_fused: shared-memory tile too large (%zu bytes)", smem);
   const int NU = (p.W + p.S / 2 + 3) / 4;
   dim3 grid((NU + p.NG - 1) / p.NG, p.h + 1, p.N);
   k<<<grid, 256, smem, st>>>(p);

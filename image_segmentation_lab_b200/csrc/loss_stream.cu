@@ -317,6 +317,16 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
     // accuracy.py:55-60: (correct.float().sum() + eps) * (100.0 / (n + eps)), evaluated in fp32
     const float r = (float)(100.0 / (n_acc + eps));
     d.out[B200SEG_OUT_ACC] = ((float)n_correct + (float)eps) * r;
+    if (d.log_vec) {
+      d.log_vec[B200SEG_LOG_CE_SUM] = sum;
+      d.log_vec[B200SEG_LOG_N_VALID] = n_valid;
+      d.log_vec[B200SEG_LOG_N_CORRECT] = n_correct;
+      d.log_vec[B200SEG_LOG_N_ACC] = n_acc;
+      d.log_vec[B200SEG_LOG_N_BAD] = (double)(long long)d.stats[B200SEG_ST_N_BAD];
+      d.log_vec[B200SEG_LOG_N_PIXELS] = (double)d.n_pixels;
+      d.log_vec[B200SEG_LOG_DICE_SUM] = 0.0;
+      d.log_vec[B200SEG_LOG_N_IMAGES] = (double)d.N;
+    }
   }
   if (d.dice_part == nullptr) {
     if (threadIdx.x == 0) d.out[B200SEG_OUT_LOSS_DICE] = 0.f;
@@ -341,7 +351,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
   }
   double r[1] = {part};
   block_sum<double, 1>(r, sred);
-  if (threadIdx.x == 0) d.out[B200SEG_OUT_LOSS_DICE] = (float)(K * r[0]);
+  if (threadIdx.x == 0) {
+    d.out[B200SEG_OUT_LOSS_DICE] = (float)(K * r[0]);
+    // sum over (n,c) of cw_c * (1 - num/den): additive over images, so ranks can all-reduce it
+    if (d.log_vec) d.log_vec[B200SEG_LOG_DICE_SUM] = r[0];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

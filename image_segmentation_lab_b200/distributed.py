@@ -111,18 +111,12 @@ def all_reduce_areas(areas: Dict[str, torch.Tensor], group=None) -> Dict[str, to
     return dict(zip(keys, red))
 
 
-def stats_vector(stats: torch.Tensor, n_pixels: int) -> torch.Tensor:
-    """float64 [ce_sum, n_valid, n_correct, n_acc, n_pixels] from the int64 statistics block of the loss kernel."""
-    head = stats[:1].view(torch.float64)
-    cnt = stats[[_lib.ST_N_VALID, _lib.ST_N_CORRECT, _lib.ST_N_ACC]].to(torch.float64)
-    return torch.cat([head, cnt, torch.tensor([float(n_pixels)], dtype=torch.float64, device=stats.device)])
-
-
 def global_loss_scalars(vec: torch.Tensor, loss_weight: float = 1.0, avg_non_ignore: bool = False):
-    """Global-batch loss / accuracy from a reduced :func:`stats_vector` (== the reference run once on the
-    concatenated batch): loss = lw * sum / (N_global*H*W), acc = 100 * correct / n_acc."""
+    """Global-batch CE loss / accuracy from the all-reduced statistics vector of the fused loss
+    (``fused_resize_losses(..., return_stats=True)['_stats']``, layout B200SEG_LOG_*): identical to running the
+    reference once on the concatenated batch — loss = lw * sum / (N_global*H*W), acc = 100 * correct / n_acc."""
     eps = float(torch.finfo(torch.float32).eps)
-    denom = (vec[1] + eps) if avg_non_ignore else vec[4]
-    loss = (loss_weight * vec[0] / denom).to(torch.float32)
-    acc = (100.0 * (vec[2] + eps) / (vec[3] + eps)).to(torch.float32)
+    denom = (vec[_lib.LOG_N_VALID] + eps) if avg_non_ignore else vec[_lib.LOG_N_PIXELS]
+    loss = (loss_weight * vec[_lib.LOG_CE_SUM] / denom).to(torch.float32)
+    acc = (100.0 * (vec[_lib.LOG_N_CORRECT] + eps) / (vec[_lib.LOG_N_ACC] + eps)).to(torch.float32)
     return loss, acc

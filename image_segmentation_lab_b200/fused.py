@@ -30,12 +30,14 @@ def _merge_spec(ce, dice, device, seg_weight, ignore_index, align_corners, want_
     return spec
 
 
-def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False, ignore_index=255, seg_weight=None):
+def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False, ignore_index=255, seg_weight=None,
+                        return_stats=False):
     """{loss_name: loss, ..., 'acc_seg': (1,) tensor} for low- or full-resolution ``seg_logit``.
 
     ``losses_decode`` is a loss module or a list / ModuleList of them (this package's CrossEntropyLoss and
     DiceLoss are fused into a single kernel launch; any other nn.Module loss is called on the materialised
-    resize). Same-named losses are summed, as decode_head.py:283-293 does.
+    resize). Same-named losses are summed, as decode_head.py:283-293 does. ``return_stats`` adds the float64
+    statistics vector of the fused launch under '_stats' (see distributed.py).
     """
     if isinstance(losses_decode, nn.Module) and not isinstance(losses_decode, nn.ModuleList):
         losses_decode = [losses_decode]
@@ -68,7 +70,7 @@ def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False
             out[name] = out[name] + value
 
     spec = _merge_spec(fused_ce, fused_dice, seg_logit.device, seg_weight, ignore_index, align_corners, True)
-    l_ce, l_dice, acc = run_fused(src, seg_label, seg_weight, spec)
+    l_ce, l_dice, acc, log_vec = run_fused(src, seg_label, seg_weight, spec, with_log=True)
     # keep the reference's insertion order of the loss dict
     for m in losses_decode:
         if m is fused_ce:
@@ -79,6 +81,8 @@ def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False
             label = seg_label.squeeze(1) if seg_label.dim() == 4 else seg_label
             add(m.loss_name, m(src, label, weight=seg_weight, ignore_index=ignore_index))
     out['acc_seg'] = acc
+    if return_stats:
+        out['_stats'] = log_vec
     return out
 
 

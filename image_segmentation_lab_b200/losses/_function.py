@@ -66,7 +66,10 @@ def _none_int(v, default):
 
 
 class FusedLossFunction(torch.autograd.Function):
-    """(logits, labels, pixel_weight, spec) -> (loss_ce, loss_dice, acc_seg)."""
+    """(logits, labels, pixel_weight, spec) -> (loss_ce, loss_dice, acc_seg, log_vec).
+
+    ``log_vec`` is the float64 vector of additive per-call statistics (include/b200seg.h B200SEG_LOG_*): the
+    payload of the single per-step all-reduce under data parallelism (distributed.py)."""
 
     @staticmethod
     def forward(ctx, logits, labels, pixel_weight, spec):
@@ -101,11 +104,12 @@ class FusedLossFunction(torch.autograd.Function):
 
         with torch.cuda.device(dev):
             nc = N * Cc if spec.want_dice else 0
-            ws = torch.empty(_lib.STATS_WORDS + 2 + 4 * nc, dtype=torch.int64, device=dev)
+            ws = torch.empty(_lib.STATS_WORDS + 2 + _lib.LOG_WORDS + 4 * nc, dtype=torch.int64, device=dev)
             base = ws.data_ptr()
             stats_p = base
             out_p = base + 8 * _lib.STATS_WORDS
-            part_p = out_p + 16
+            log_p = out_p + 16
+            part_p = log_p + 8 * _lib.LOG_WORDS
             coef_p = part_p + 24 * nc
             out_f = ws[_lib.STATS_WORDS:_lib.STATS_WORDS + 2].view(torch.float32)
 
@@ -194,12 +198,14 @@ class FusedLossFunction(torch.autograd.Function):
             fin.dice_ignore_index = fd.dice_ignore_index
             fin.out = out_p
             fin.dice_coef = coef_p if (spec.want_dice and needs_grad) else None
+            fin.log_vec = log_p
             _lib.check(lib.b200seg_loss_finalize(C.byref(fin), stream))
 
         loss_ce = loss_px if ce_none else out_f[_lib.OUT_LOSS_CE]
         loss_dice = out_f[_lib.OUT_LOSS_DICE]
         acc = out_f[_lib.OUT_ACC:_lib.OUT_ACC + 1]
-        ctx.mark_non_differentiable(acc)
+        log_vec = ws[_lib.STATS_WORDS + 2:_lib.STATS_WORDS + 2 + _lib.LOG_WORDS].view(torch.float64)
+        ctx.mark_non_differentiable(acc, log_vec)
         if needs_grad:
             ctx.spec = spec
             ctx.plan = plan
@@ -213,11 +219,10 @@ class FusedLossFunction(torch.autograd.Function):
             ctx.save_for_backward(logits_c, labels, pw if pw is not None else ws, lse if lse is not None else ws,
                                   grad if grad is not None else ws, pb if pb is not None else ws)
             ctx.has = (pw is not None, lse is not None, grad is not None, pb is not None)
-        ctx.stats = ws[:_lib.STATS_WORDS]
-        return loss_ce, loss_dice, acc
+        return loss_ce, loss_dice, acc, log_vec
 
     @staticmethod
-    def backward(ctx, g_ce, g_dice, g_acc):
+    def backward(ctx, g_ce, g_dice, g_acc, g_log):
         lib = _lib.load()
         spec = ctx.spec
         logits, labels, pw, lse, grad, pb = ctx.saved_tensors
@@ -298,5 +303,8 @@ class FusedLossFunction(torch.autograd.Function):
         return out, None, None, None
 
 
-def run_fused(logits, labels, pixel_weight, spec):
-    return FusedLossFunction.apply(logits, labels, pixel_weight, spec)
+def run_fused(logits, labels, pixel_weight, spec, with_log=False):
+    loss_ce, loss_dice, acc, log_vec = FusedLossFunction.apply(logits, labels, pixel_weight, spec)
+    if with_log:
+        return loss_ce, loss_dice, acc, log_vec
+    return loss_ce, loss_dice, acc

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 3
+#define B200SEG_ABI_VERSION 4
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -63,6 +63,11 @@ enum {
 
 /* outputs of b200seg_loss_finalize (float32 words) */
 enum { B200SEG_OUT_LOSS_CE = 0, B200SEG_OUT_LOSS_DICE = 1, B200SEG_OUT_ACC = 2, B200SEG_OUT_WORDS = 4 };
+
+/* layout of b200seg_finalize_desc.log_vec */
+enum { B200SEG_LOG_CE_SUM = 0, B200SEG_LOG_N_VALID = 1, B200SEG_LOG_N_CORRECT = 2, B200SEG_LOG_N_ACC = 3,
+       B200SEG_LOG_N_BAD = 4, B200SEG_LOG_N_PIXELS = 5, B200SEG_LOG_DICE_SUM = 6, B200SEG_LOG_N_IMAGES = 7,
+       B200SEG_LOG_WORDS = 8 };
 
 /* reductions (models/losses/utils.py:28-80) */
 enum { B200SEG_RED_NONE = 0, B200SEG_RED_MEAN = 1, B200SEG_RED_SUM = 2 };
@@ -116,6 +121,9 @@ typedef struct b200seg_finalize_desc {
   int64_t dice_ignore_index;
   float*  out;                      /* B200SEG_OUT_WORDS floats                                */
   float*  dice_coef;                /* (N,C,2) f32 [alpha,beta] for the backward, or NULL      */
+  double* log_vec;                  /* B200SEG_LOG_WORDS doubles or NULL: the additive quantities of
+                                     * this call as float64 (exact below 2^53), i.e. the payload of the
+                                     * single per-step all-reduce across data-parallel ranks           */
 } b200seg_finalize_desc;
 
 /* One tiny launch: statistics -> loss_ce, loss_dice, acc_seg scalars (+ dice backward table). */

@@ -1,0 +1,464 @@
+"""GPU: parity of the CUDA path (through the Python mirror of the reference interface, which calls the C ABI)
+against (1) the fixtures recorded from the reference's own files and (2) the oracle on the same seeded inputs.
+
+Gates: areas bit-exact; fp32 loss <= 1e-5 relative, fp32 gradients <= 1e-4 relative
+(inf-norm over inf-norm); bf16 / fp16 logits <= 2**-7 relative against the oracle on the fp32-upcast inputs.
+"""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.helpers import (case_tensors, loss_case_cuda, loss_case_oracle, rel_err, synth_labels, synth_logits)
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-5
+GRAD_TOL = 1e-4
+HALF_TOL = 2.0 ** -7
+
+
+@pytest.fixture(scope='module')
+def B():
+    import image_segmentation_lab_b200 as pkg
+    pkg.load_library()
+    warnings.simplefilter('ignore')
+    return pkg
+
+
+def _loss_cases(manifest):
+    return [c for c in manifest['cases'] if c['kind'] in ('ce', 'dice', 'head')]
+
+
+def _check(out, ref, name, loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, acc_tol=1e-3):
+    for k in ref:
+        if k == 'grad':
+            assert rel_err(out[k], ref[k]) <= grad_tol, '%s grad rel err %.3e' % (name, rel_err(out[k], ref[k]))
+        elif k == 'acc':
+            assert abs(float(out[k]) - float(ref[k])) <= acc_tol, '%s acc %r vs %r' % (name, float(out[k]), float(ref[k]))
+        else:
+            assert rel_err(out[k], ref[k]) <= loss_tol, '%s %s rel err %.3e' % (name, k, rel_err(out[k], ref[k]))
+
+
+# ------------------------------------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize('single_pass', [True, False])
+def test_golden_loss_cases_fp32(B, golden, single_pass):
+    data, manifest = golden
+    for case in _loss_cases(manifest):
+        name = case['name']
+        logits, labels, pw = case_tensors(data, name, device='cuda')
+        go = torch.from_numpy(data[name + '/grad_out']).cuda() if (name + '/grad_out') in data else None
+        out = loss_case_cuda(case, logits, labels, pw, go, single_pass=single_pass)
+        ref = {k: torch.from_numpy(data[name + '/' + k]) for k in out}
+        _check(out, ref, name + ('' if single_pass else '[two_pass]'))
+
+
+@pytest.mark.parametrize('label_dtype', [torch.uint8, torch.int32, torch.float32, torch.float64, torch.int16])
+def test_golden_loss_cases_label_dtypes(B, golden, label_dtype):
+    """Labels are consumed in the dtype the data pipeline delivers."""
+    data, manifest = golden
+    ran = 0
+    for case in _loss_cases(manifest):
+        if case['ignore'] < 0 and label_dtype == torch.uint8:
+            continue
+        name = case['name']
+        logits, labels, pw = case_tensors(data, name, device='cuda')
+        go = torch.from_numpy(data[name + '/grad_out']).cuda() if (name + '/grad_out') in data else None
+        out = loss_case_cuda(case, logits, labels, pw, go, label_dtype=label_dtype)
+        ref = {k: torch.from_numpy(data[name + '/' + k]) for k in out}
+        _check(out, ref, '%s[%s]' % (name, label_dtype))
+        ran += 1
+    assert ran >= 15
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_golden_loss_cases_half(B, golden, dtype):
+    """16-bit logits: fp32 math inside; compared with the oracle on the fp32-upcast of the SAME rounded logits."""
+    data, manifest = golden
+    for case in _loss_cases(manifest):
+        name = case['name']
+        logits, labels, pw = case_tensors(data, name, device='cuda')
+        lq = logits.to(dtype)
+        go = torch.from_numpy(data[name + '/grad_out']).cuda() if (name + '/grad_out') in data else None
+        out = loss_case_cuda(case, lq, labels, pw, go)
+        ref = loss_case_oracle(case, lq.float(), labels, pw, go)
+        assert out['grad'].dtype == dtype
+        _check(out, ref, '%s[%s]' % (name, dtype), loss_tol=HALF_TOL, grad_tol=2 * HALF_TOL, acc_tol=0.5)
+
+
+def test_golden_resize(B, golden):
+    data, manifest = golden
+    for case in [c for c in manifest['cases'] if c['kind'] == 'resize']:
+        name = case['name']
+        x = torch.from_numpy(data[name + '/x']).cuda().requires_grad_(True)
+        y = B.resize(x, size=tuple(case['size']), mode='bilinear', align_corners=case['ac'], warning=False)
+        y.backward(torch.from_numpy(data[name + '/go']).cuda())
+        assert rel_err(y, data[name + '/y']) <= 2e-6, name
+        assert rel_err(x.grad, data[name + '/gx']) <= 1e-5, name
+    y = B.resize(torch.from_numpy(data['resize_nearest/x']).cuda(), size=(9, 15))
+    np.testing.assert_array_equal(y.cpu().numpy(), data['resize_nearest/y'])
+    x = torch.randn(2, 3, 5, 7, device='cuda')
+    assert torch.equal(B.resize(x, size=(5, 7), mode='bilinear', align_corners=False), x)   # same size: a copy
+    up = B.Upsample(scale_factor=2, mode='bilinear', align_corners=False)
+    assert rel_err(up(x), torch.nn.functional.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)) <= 2e-6
+
+
+def test_golden_accuracy_topk(B, golden):
+    data, _ = golden
+    r = B.accuracy(torch.from_numpy(data['acc_topk/pred']).cuda(), torch.from_numpy(data['acc_topk/target']).cuda(),
+                   topk=(1, 3), thresh=0.2)
+    np.testing.assert_allclose(np.stack([v.cpu().numpy() for v in r]), data['acc_topk/out'], rtol=1e-6)
+    r = B.accuracy(torch.from_numpy(data['acc_topk4d/pred']).cuda(), torch.from_numpy(data['acc_topk4d/target']).cuda(),
+                   topk=(1, 2, 5), ignore_index=255)
+    np.testing.assert_allclose(np.stack([v.cpu().numpy() for v in r]), data['acc_topk4d/out'], rtol=1e-6)
+    single = B.accuracy(torch.from_numpy(data['acc_topk4d/pred']).cuda(), torch.from_numpy(data['acc_topk4d/target']).cuda(),
+                        ignore_index=255)
+    assert single.shape == (1,) and abs(float(single) - float(data['acc_topk4d/out'][0])) < 1e-4
+    mod = B.Accuracy(topk=(1, 2, 5), ignore_index=255)
+    r2 = mod(torch.from_numpy(data['acc_topk4d/pred']).cuda(), torch.from_numpy(data['acc_topk4d/target']).cuda())
+    np.testing.assert_allclose(np.stack([v.cpu().numpy() for v in r2]), data['acc_topk4d/out'], rtol=1e-6)
+    empty = B.accuracy(torch.zeros(0, 7, device='cuda'), torch.zeros(0, dtype=torch.long, device='cuda'))
+    assert float(empty) == 0.0
+
+
+def test_golden_intersect_and_union_bit_exact(B, golden):
+    data, _ = golden
+    preds = [torch.from_numpy(data['iau/pred%d' % i]).cuda() for i in range(3)]
+    gts = [torch.from_numpy(data['iau/gt%d' % i]) for i in range(3)]      # CPU float32, as the data loader delivers
+    lists = B.SegEvaluator.intersect_and_union(preds, gts, 5, 255)
+    assert len(lists) == 4 and all(len(l) == 3 for l in lists)
+    for j in range(4):
+        got = np.stack([t.numpy() for t in lists[j]])
+        assert got.dtype == np.float32 and not lists[j][0].is_cuda
+        np.testing.assert_array_equal(got, data['iau/areas'][:, j])
+    areas = B.areas_device(preds, [g.cuda() for g in gts], 5, 255)
+    assert areas.dtype == torch.int64 and areas.is_cuda
+    np.testing.assert_array_equal(areas.cpu().numpy(), data['iau/areas'][:, [0, 2, 3]].astype(np.int64))
+    for pdt, gdt in [(torch.int32, torch.int64), (torch.uint8, torch.uint8), (torch.int64, torch.float64)]:
+        a2 = B.areas_device([p.clamp(0, 255).to(pdt) for p in preds], [g.to(gdt).cuda() for g in gts], 5, 255)
+        np.testing.assert_array_equal(a2.cpu().numpy(), data['iau/areas'][:, [0, 2, 3]].astype(np.int64))
+
+
+def test_golden_process_and_metrics(B, golden, capsys):
+    data, _ = golden
+    logits = [torch.from_numpy(data['process/logits%d' % i]).cuda() for i in range(3)]
+    gts = [torch.from_numpy(data['process/gt%d' % i]) for i in range(3)]
+    ev = B.SegEvaluator(epoch=0, num_classes=5, class_names=['c%d' % i for i in range(5)], palette=None, ignore_index=-1,
+                        show_result=False)
+    pred_batch = {'decode': [t.clone() for t in logits], 'aux': [t.clone() for t in logits]}
+    ev.process(0, pred_batch, {'ori_gt': gts})
+    ev.process(1, {'decode': [t.clone() for t in logits[:1]]}, {'ori_gt': gts[:1]})
+    res = ev.results
+    assert set(res.keys()) == {'decode', 'aux'} and len(res['decode'][0]) == 4 and len(res['aux'][0]) == 3
+    got = np.stack([np.stack([t.numpy() for t in res['aux'][j]]) for j in range(4)], axis=1)
+    np.testing.assert_array_equal(got, data['process/areas'])
+    ev2 = B.SegEvaluator(epoch=0, num_classes=5, class_names=['c%d' % i for i in range(5)], palette=None, ignore_index=-1,
+                         show_result=False, keep_pred_maps=True)
+    pb = {'decode': [t.clone() for t in logits]}
+    ev2.process(0, pb, {'ori_gt': gts})
+    for i in range(3):   # the reference replaces the logits by label maps in place (metrics.py:107)
+        assert torch.equal(pb['decode'][i].cpu(), O.argmax_labels(logits[i].cpu()))
+    met = ev2.compute_metrics()['decode']
+    for k in ('aAcc', 'mIoU', 'mAcc', 'mDice', 'mFscore', 'mPrecision', 'mRecall'):
+        assert met[k] == data['process/summary_' + k], k
+    for k in ('IoU', 'Acc', 'Dice', 'Fscore', 'Precision', 'Recall'):
+        np.testing.assert_array_equal(met[k], data['process/class_' + k])
+    assert torch.equal(ev2.area_totals('decode'), torch.from_numpy(data['process/areas'].astype(np.int64).sum(0)))
+
+
+# ------------------------------------------------------------------------------------------------ oracle, larger shapes
+def _head_case(B, shape, size, C, dtype, ce_kw, dice_kw, ac=False, ignore=255, seed=0, pixel_weight=False,
+               loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, single_pass=True, margin=True):
+    n = shape[0]
+    logits = synth_logits(shape, seed, dtype=dtype, device='cuda', margin=margin)
+    labels = synth_labels((n,) + tuple(size), C, seed, ignore_index=ignore, block=8, device='cuda')
+    pw = (torch.rand((n,) + tuple(size), device='cuda') + 0.5) if pixel_weight else None
+    case = dict(kind='head' if dice_kw is not None else 'ce', size=size, ac=ac, ignore=ignore)
+    if dice_kw is not None:
+        case['ce'], case['dice'] = ce_kw, dice_kw
+    else:
+        case['kw'] = ce_kw
+    out = loss_case_cuda(case, logits, labels, pw, single_pass=single_pass)
+    ref = loss_case_oracle(case, logits.float(), labels, pw)   # the unfused ATen chain on the same GPU
+    _check(out, ref, 'head%s' % (shape,), loss_tol=loss_tol, grad_tol=grad_tol, acc_tol=1e-3 if dtype == torch.float32 else 0.5)
+    return out, ref
+
+
+def test_config1_unet_shape(B):
+    """BASELINE config 1: 2x2x256x256, 2 classes, CE, no ignore (ignore_index=-1 as configs/dataset/KvasirSEG.py:8)."""
+    _head_case(B, (2, 2, 256, 256), (256, 256), 2, torch.float32, {}, None, ignore=-1)
+    _head_case(B, (2, 2, 256, 256), (256, 256), 2, torch.float32, {}, None, ignore=-1, single_pass=False)
+
+
+@pytest.mark.parametrize('ac', [False, True])
+def test_config2_cityscapes_shape(B, ac):
+    """BASELINE config 2 at full size: (8,19,64,128) -> 512x1024, CE + ignore_index=255, both align_corners."""
+    out, ref = _head_case(B, (8, 19, 64, 128), (512, 1024), 19, torch.float32, {}, None, ac=ac)
+    assert out['grad'].shape == (8, 19, 64, 128)
+
+
+def test_config2_variants(B):
+    _head_case(B, (2, 19, 32, 64), (512, 1024), 19, torch.float32, dict(avg_non_ignore=True), None, pixel_weight=True)  # S=16
+    _head_case(B, (2, 19, 128, 256), (512, 1024), 19, torch.float32, dict(class_weight=[1.0 + 0.05 * i for i in range(19)]), None)  # S=4
+    _head_case(B, (1, 21, 16, 16), (512, 512), 21, torch.float32, dict(reduction='sum'), None)  # S=32
+    _head_case(B, (2, 32, 40, 24), (320, 192), 32, torch.float32, {}, None)  # C=32, non power-of-two extents
+    _head_case(B, (2, 19, 65, 129), (513, 1025), 19, torch.float32, {}, None, ac=True)  # nx+1 sizes -> general path
+    _head_case(B, (2, 150, 32, 32), (256, 256), 150, torch.float32, {}, None)  # C > 32 -> general path
+    _head_case(B, (2, 19, 64, 128), (512, 1024), 19, torch.bfloat16, {}, None, loss_tol=HALF_TOL, grad_tol=2 * HALF_TOL)
+
+
+def test_config3_ade20k_shape(B):
+    """BASELINE config 3 (batch reduced to 2 for the oracle's 150-iteration Python loop): 150 classes, 512x512, bf16,
+    class-weighted CE + Dice(loss_weight=3)."""
+    cw = torch.linspace(0.5, 1.5, 150).tolist()
+    _head_case(B, (2, 150, 512, 512), (512, 512), 150, torch.bfloat16, dict(class_weight=cw), dict(loss_weight=3.0),
+               loss_tol=HALF_TOL, grad_tol=2 * HALF_TOL)
+    _head_case(B, (2, 150, 128, 128), (128, 128), 150, torch.float32, dict(class_weight=cw), dict(loss_weight=3.0))
+    _head_case(B, (1, 150, 64, 64), (256, 256), 150, torch.float32, dict(class_weight=cw), dict(loss_weight=3.0))  # resize + dice
+
+
+def test_config4_voc_shape(B):
+    """BASELINE config 4 (batch 8 of the 32): 21 classes 512x512 fp32 CE, single-pass and two-pass plans."""
+    _head_case(B, (8, 21, 512, 512), (512, 512), 21, torch.float32, {}, None)
+    _head_case(B, (8, 21, 512, 512), (512, 512), 21, torch.float32, {}, None, single_pass=False)
+    _head_case(B, (4, 21, 512, 512), (512, 512), 21, torch.float32, dict(avg_non_ignore=True), dict(class_weight=[1.0] * 21))
+
+
+def test_ragged_shapes_and_unaligned_views(B):
+    _head_case(B, (3, 7, 37, 53), (37, 53), 7, torch.float32, {}, dict())            # H*W odd -> scalar kernels
+    _head_case(B, (1, 3, 1, 1), (1, 1), 3, torch.float32, {}, dict(), ignore=255)    # a single pixel
+    _head_case(B, (2, 33, 18, 22), (18, 22), 33, torch.float32, {}, dict())          # C just above one chunk
+    _head_case(B, (1, 300, 16, 16), (16, 16), 300, torch.float32, {}, dict())        # 10 class groups x 30
+    _head_case(B, (1, 600, 8, 8), (8, 8), 600, torch.float32, {}, None)              # CE only: any C
+    # a non-contiguous / offset view must give the same answer as its contiguous copy
+    big = synth_logits((2, 6, 20, 24), 3, device='cuda')
+    view = big[:, 1:, 2:18, 1:17]
+    labels = synth_labels((2, 16, 16), 5, 3, device='cuda', block=4)
+    ce = B.CrossEntropyLoss()
+    a = ce(view, labels, ignore_index=255)
+    b = ce(view.contiguous(), labels, ignore_index=255)
+    assert torch.equal(a, b)
+
+
+def test_all_ignored_and_empty(B):
+    x = synth_logits((2, 5, 16, 16), 1, device='cuda').requires_grad_(True)
+    y = torch.full((2, 16, 16), 255, device='cuda')
+    for kw in (dict(), dict(avg_non_ignore=True)):
+        loss = B.CrossEntropyLoss(**kw)(x, y, ignore_index=255)
+        ref = O.cross_entropy_loss_module(x.detach(), y, ignore_index=255, **kw)
+        assert float(loss) == float(ref) == 0.0
+        g, = torch.autograd.grad(loss, x)
+        assert float(g.abs().max()) == 0.0
+    acc = B.accuracy(x.detach(), y, ignore_index=255)
+    assert abs(float(acc) - float(O.accuracy(x.detach(), y, ignore_index=255))) < 1e-4   # eps/eps * 100
+    d = B.DiceLoss()(x, y)
+    assert rel_err(d, O.dice_loss_module(x.detach(), y)) <= LOSS_TOL
+    e = B.CrossEntropyLoss(reduction='sum')(torch.zeros(0, 5, 4, 4, device='cuda'), torch.zeros(0, 4, 4, dtype=torch.long, device='cuda'))
+    assert float(e) == 0.0
+    assert B.areas_device([], [], 5, 255).shape == (0, 3, 5)
+
+
+def test_functional_and_2d_inputs(B):
+    g = torch.Generator().manual_seed(4)
+    p = torch.randn((33, 6), generator=g).cuda().requires_grad_(True)
+    t = torch.randint(0, 6, (33,), generator=g).cuda()
+    w = torch.rand((33,), generator=g).cuda()
+    for kw in (dict(), dict(reduction='none'), dict(reduction='sum', class_weight=[1, 2, 3, 4, 5, 6.0])):
+        kw_o = dict(kw)
+        if 'class_weight' in kw_o:
+            kw_o['class_weight'] = torch.tensor(kw_o['class_weight'], device='cuda')
+        a = B.cross_entropy(p, t, weight=w, ignore_index=2, **kw)
+        b = O.cross_entropy(p.detach(), t, weight=w, ignore_index=2, **kw_o)
+        assert a.shape == b.shape and rel_err(a, b) <= LOSS_TOL
+    x = synth_logits((2, 4, 8, 8), 2, device='cuda')
+    y = synth_labels((2, 8, 8), 4, 2, device='cuda', block=2)
+    assert rel_err(B.dice_loss(x, y, smooth=2, exponent=2), O.dice_loss_module(x, y, smooth=2)) <= LOSS_TOL
+
+
+def test_amp_grad_scale_and_retain(B):
+    """the upstream gradient is an arbitrary device scalar (GradScaler), never 1 by assumption."""
+    x = synth_logits((2, 19, 16, 32), 5, device='cuda')
+    y = synth_labels((2, 128, 256), 19, 5, device='cuda')
+    for xx, size in ((x, (128, 256)), (synth_logits((2, 19, 128, 256), 6, device='cuda'), (128, 256))):
+        xa = xx.clone().requires_grad_(True)
+        r = B.fused_resize_losses(xa, y.unsqueeze(1), B.CrossEntropyLoss(), ignore_index=255)
+        (r['loss_ce'] * 65536.0).backward()
+        xb = xx.clone().requires_grad_(True)
+        full = O.resize(xb, size=size, mode='bilinear', align_corners=False)
+        (O.cross_entropy_loss_module(full, y, ignore_index=255) * 65536.0).backward()
+        assert rel_err(xa.grad, xb.grad) <= GRAD_TOL
+    # under fp16 autocast the loss comes back in float32, as ATen's autocast policy for cross_entropy does
+    with torch.autocast('cuda', dtype=torch.float16):
+        l = B.CrossEntropyLoss()(x.half(), synth_labels((2, 16, 32), 19, 5, device='cuda', block=4), ignore_index=255)
+    assert l.dtype == torch.float32
+    l = B.CrossEntropyLoss()(x.bfloat16(), synth_labels((2, 16, 32), 19, 5, device='cuda', block=4), ignore_index=255)
+    assert l.dtype == torch.bfloat16
+
+
+def test_decode_head_mixin(B):
+    """losses() with the reference's signature and return layout (decode_head.py:261-321)."""
+    import torch.nn as nn
+
+    class Head(B.B200DecodeHeadLossMixin, nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.loss_decode = nn.ModuleList([B.CrossEntropyLoss(loss_weight=1.0), B.DiceLoss(loss_weight=3.0),
+                                              B.CrossEntropyLoss(loss_weight=0.5, loss_name='loss_ce')])
+            self.align_corners = False
+            self.ignore_index = 255
+            self.sampler = None
+
+    head = Head()
+    x = synth_logits((2, 6, 8, 8), 9, device='cuda').requires_grad_(True)
+    y = synth_labels((2, 32, 32), 6, 9, device='cuda', block=4).unsqueeze(1)
+    logits, loss = head.losses(x, y, {}, rescale=False)
+    ref = O.head_losses(x.detach(), y, [('ce', dict(loss_weight=1.0), 'loss_ce'), ('dice', dict(loss_weight=3.0), 'loss_dice'),
+                                        ('ce', dict(loss_weight=0.5), 'loss_ce')], ignore_index=255)
+    assert list(loss.keys()) == ['loss_ce', 'loss_dice', 'acc_seg']
+    for k in ref:
+        assert rel_err(loss[k], ref[k]) <= (LOSS_TOL if k != 'acc_seg' else 1e-4), k
+    assert logits.shape == x.shape
+    infos = {'ori_img_size_hw': [(40, 36), (20, 28)]}
+    resc, _ = head.losses(x.detach(), y, infos, rescale=True)
+    full = O.resize(x.detach(), size=(32, 32), mode='bilinear', align_corners=False)
+    for i, s in enumerate(infos['ori_img_size_hw']):
+        want = O.resize(full[i].unsqueeze(0), size=s, mode='bilinear', align_corners=False)
+        assert resc[i].shape == want.shape and rel_err(resc[i], want) <= 4e-6
+    resc, _ = head.losses(x.detach(), y, {'ori_img_size_hw': (48, 48)}, rescale=True)
+    assert rel_err(resc, O.resize(full, size=(48, 48), mode='bilinear', align_corners=False)) <= 4e-6
+
+
+def test_cuda_graph_capture_replay(B):
+    """Every entry point is stream-ordered and allocation-free inside the C ABI: the step captures and replays."""
+    x = synth_logits((2, 19, 16, 32), 7, device='cuda').requires_grad_(True)
+    y = synth_labels((2, 128, 256), 19, 7, device='cuda').unsqueeze(1)
+    ce = B.CrossEntropyLoss()
+    r = B.fused_resize_losses(x, y, ce, ignore_index=255)
+    r['loss_ce'].backward()
+    want_loss, want_grad = r['loss_ce'].detach().clone(), x.grad.clone()
+    x.grad = None
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            r = B.fused_resize_losses(x, y, ce, ignore_index=255)
+            r['loss_ce'].backward()
+            x.grad = None
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        r = B.fused_resize_losses(x, y, ce, ignore_index=255)
+        r['loss_ce'].backward()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(r['loss_ce'].detach(), want_loss) and torch.equal(x.grad, want_grad)
+
+
+def test_determinism_bitwise(B):
+    """The resize-fused backward is a fixed-order gather (ATen's is an atomicAdd scatter): runs are bit-identical."""
+    x = synth_logits((4, 19, 32, 64), 8, device='cuda')
+    y = synth_labels((4, 256, 512), 19, 8, device='cuda').unsqueeze(1)
+    grads = []
+    for _ in range(3):
+        xa = x.clone().requires_grad_(True)
+        B.fused_resize_losses(xa, y, B.CrossEntropyLoss(), ignore_index=255)['loss_ce'].backward()
+        grads.append(xa.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+
+
+# ------------------------------------------------------------------------------------------------ evaluation at scale
+def _areas_oracle_gpu(preds, gts, C, ignore):
+    """Exact int64 areas with torch.bincount on the GPU (the numpy oracle's rule, for large inputs)."""
+    out = []
+    for p, g in zip(preds, gts):
+        p = p.reshape(-1).long()
+        g = g.reshape(-1).long()
+        keep = g != ignore
+        p, g = p[keep], g[keep]
+        pin = (p >= 0) & (p < C)
+        gin = (g >= 0) & (g < C)
+        I = torch.bincount(p[(p == g) & pin], minlength=C)
+        P = torch.bincount(p[pin], minlength=C)
+        L = torch.bincount(g[gin], minlength=C)
+        out.append(torch.stack([I, P, L]))
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize('C', [2, 19, 60, 150, 400])
+def test_areas_label_maps_all_counter_modes(B, C):
+    """Private per-thread counters (C small), 128-thread variant (C mid) and shared atomics (C large)."""
+    g = torch.Generator().manual_seed(C)
+    sizes = [(257, 301), (64, 64), (1, 1), (511, 7), (1024, 2048)]
+    preds = [torch.randint(-2, C + 3, s, generator=g).cuda() for s in sizes]
+    gts = [synth_labels((1,) + s, C, C + i, ignore_index=255, block=16)[0].float().cuda() for i, s in enumerate(sizes)]
+    gts[0][5, 5] = C + 7
+    got = B.areas_device(preds, gts, C, 255)
+    want = _areas_oracle_gpu(preds, gts, C, 255)
+    assert torch.equal(got, want)
+    small = O.intersect_and_union_int([p.cpu() for p in preds[:3]], [t.cpu() for t in gts[:3]], C, 255)
+    assert np.array_equal(got[:3].cpu().numpy(), small[:, [0, 2, 3]])
+
+
+def test_config5_sweep_properties(B):
+    """BASELINE config 5 (64 of the 500 images on one GPU): 1024x2048, 19 classes; bit-exact against bincount, plus
+    size-independent properties: sum(label) = #non-ignored, I <= min(P,L), U = P + L - I, additivity over shards."""
+    C, n = 19, 64
+    g = torch.Generator().manual_seed(55)
+    gt_all = synth_labels((n, 1024, 2048), C, 55, ignore_index=255, block=16).float().cuda()
+    pred_all = torch.randint(0, C, (n, 1024, 2048), generator=g, dtype=torch.int64).cuda()
+    agree = torch.rand((n, 64, 128), generator=g).cuda().repeat_interleave(16, 1).repeat_interleave(16, 2) < 0.7
+    pred_all = torch.where(agree & (gt_all != 255), gt_all.long(), pred_all)
+    preds, gts = list(pred_all.unbind(0)), list(gt_all.unbind(0))
+    a = B.areas_device(preds, gts, C, 255)
+    assert torch.equal(a, _areas_oracle_gpu(preds, gts, C, 255))
+    I, P, L = a[:, 0], a[:, 1], a[:, 2]
+    valid = (gt_all != 255).sum(dim=(1, 2))
+    assert torch.equal(L.sum(1), valid) and torch.equal(P.sum(1), valid)
+    assert bool((I <= torch.minimum(P, L)).all())
+    first = B.areas_device(preds[:40], gts[:40], C, 255).sum(0)
+    second = B.areas_device(preds[40:], gts[40:], C, 255).sum(0)
+    assert torch.equal(first + second, a.sum(0))
+    # the same totals through the evaluator API + mIoU against the oracle's metric code on the exact totals
+    lists = B.SegEvaluator.intersect_and_union(preds[:8], gts[:8], C, 255)
+    tot = a[:8].sum(0)
+    got = torch.stack([torch.stack(lists[j]).to(torch.int64).sum(0) for j in (0, 2, 3)]).cuda()
+    assert torch.equal(got, tot)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_areas_from_logits(B, dtype):
+    """process(): fused arg-max + areas vs softmax->argmax->histc of the reference on margin inputs."""
+    C = 19
+    shapes = [(1, C, 1024, 2048), (1, C, 300, 333), (1, C, 17, 5)]
+    logits = [synth_logits(s, 60 + i, dtype=dtype, device='cuda') for i, s in enumerate(shapes)]
+    gts = [synth_labels((1,) + s[2:], C, 60 + i, ignore_index=255)[0].float().cuda() for i, s in enumerate(shapes)]
+    got = B.areas_device(logits, gts, C, 255, from_logits=True)
+    preds = [O.argmax_labels(l.float()) for l in logits]
+    assert torch.equal(got, _areas_oracle_gpu(preds, gts, C, 255))
+    # un-margined inputs: report how often softmax rounding changes the arg-max (must stay tiny, never asserted to 0)
+    raw = torch.randn((1, C, 512, 512), device='cuda').to(dtype)
+    mism = int((O.argmax_labels(raw) != raw.float().argmax(1).squeeze(0)).sum())
+    print('softmax->argmax vs argmax(logits) mismatches on un-margined %s logits: %d / %d' % (dtype, mism, 512 * 512))
+    assert mism < 512 * 512 * 0.01
+
+
+def test_ce_properties_full_size(B):
+    """Size-independent properties at BASELINE config 2 / 4 sizes: shift invariance, zero gradient on ignored pixels,
+    per-pixel gradient sums to zero over classes, and loss additivity over image shards."""
+    x = synth_logits((8, 21, 512, 512), 70, device='cuda')
+    y = synth_labels((8, 512, 512), 21, 70, device='cuda')
+    ce = B.CrossEntropyLoss(reduction='sum')
+    xa = x.clone().requires_grad_(True)
+    l = ce(xa, y, ignore_index=255)
+    l.backward()
+    shift = torch.randn((8, 1, 512, 512), device='cuda')
+    l2 = ce(x + shift, y, ignore_index=255)
+    assert rel_err(l2, l) <= 1e-5
+    g = xa.grad
+    assert float(g.sum(1).abs().max()) <= 1e-5
+    assert float(g[(y == 255).unsqueeze(1).expand_as(g)].abs().max()) == 0.0
+    parts = sum(ce(x[i:i + 2], y[i:i + 2], ignore_index=255) for i in range(0, 8, 2))
+    assert rel_err(parts, l) <= 1e-6

@@ -1,0 +1,76 @@
+"""CPU, build container only: the oracle against the LIVE reference files on fresh random inputs."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason='/root/reference is not present on this machine')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    warnings.simplefilter('ignore')
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_head_chain_bitwise(ref, seed):
+    g = torch.Generator().manual_seed(seed)
+    n, c, h, w, H, W = 2, 6, 5, 7, 20, 28
+    x = torch.randn((n, c, h, w), generator=g)
+    y = torch.randint(0, c, (n, 1, H, W), generator=g)
+    y[torch.rand((n, 1, H, W), generator=g) < 0.2] = 255
+    cw = (torch.rand(c, generator=g) + 0.5).tolist()
+    for ac in (False, True):
+        xr = x.clone().requires_grad_(True)
+        full = ref.resize(xr, size=(H, W), mode='bilinear', align_corners=ac, warning=False)
+        l1 = ref.CrossEntropyLoss(class_weight=cw, avg_non_ignore=bool(seed % 2))(full, y.squeeze(1), ignore_index=255)
+        l2 = ref.DiceLoss(loss_weight=3.0, class_weight=cw)(full, y.squeeze(1), ignore_index=255)
+        acc = ref.accuracy(full, y.squeeze(1), ignore_index=255)
+        (l1 + l2).backward()
+        xo = x.clone().requires_grad_(True)
+        o = O.head_losses(xo, y, [('ce', dict(class_weight=cw, avg_non_ignore=bool(seed % 2)), 'loss_ce'),
+                                  ('dice', dict(loss_weight=3.0, class_weight=cw), 'loss_dice')], align_corners=ac,
+                          ignore_index=255)
+        (o['loss_ce'] + o['loss_dice']).backward()
+        assert torch.equal(o['loss_ce'], l1) and torch.equal(o['loss_dice'], l2) and torch.equal(o['acc_seg'], acc)
+        assert torch.equal(xo.grad, xr.grad)
+
+
+def test_binary_cross_entropy_bitwise(ref):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, 3, 6, 6), generator=g)
+    y = torch.randint(0, 3, (2, 6, 6), generator=g)
+    y[0, 0, :2] = 255
+    for kw in (dict(), dict(reduction='sum'), dict(avg_non_ignore=True)):
+        a = ref.binary_cross_entropy(x, y, ignore_index=255, **kw)
+        b = O.binary_cross_entropy(x, y, ignore_index=255, **kw)
+        assert torch.equal(a, b)
+
+
+def test_intersect_and_union_and_metrics(ref):
+    g = torch.Generator().manual_seed(3)
+    C = 19
+    preds = [torch.randint(0, C, (33, 47), generator=g) for _ in range(4)]
+    gts = [torch.randint(0, C, (33, 47), generator=g).float() for _ in range(4)]
+    for t in gts:
+        t[torch.rand(t.shape, generator=g) < 0.1] = 255
+    r = ref_loader.intersect_and_union_cpu(ref, preds, gts, C, 255)
+    a = O.intersect_and_union_int(preds, gts, C, 255)
+    for j in range(4):
+        np.testing.assert_array_equal(np.stack([x.numpy() for x in r[j]]).astype(np.int64), a[:, j])
+    tot = [torch.from_numpy(a[:, j].sum(0)).float() for j in range(4)]
+    rm = ref.SegEvaluator.total_area_to_metrics(*tot, ['mIoU', 'mDice', 'mFscore'], None, 1)
+    om = O.total_area_to_metrics(*tot, ['mIoU', 'mDice', 'mFscore'])
+    for k in rm:
+        np.testing.assert_array_equal(rm[k], om[k])
+
+
+def test_argmax_matches_process(ref):
+    g = torch.Generator().manual_seed(11)
+    l = torch.randn((1, 7, 12, 9), generator=g)
+    assert torch.equal(O.argmax_labels(l), torch.nn.functional.softmax(l, dim=1).argmax(dim=1).squeeze(0))
