@@ -147,7 +147,7 @@ class FusedLossFunction(torch.autograd.Function):
                 if up:
                     if lib.b200seg_loss_fused_workspace_bytes(N, Cc, h, w, H, W, fd.align_corners) > 0:
                         plan = "up_single"
-                elif needs_grad and not use_nvalid:
+                elif needs_grad and not use_nvalid and Cc <= 512:  # register tile: <= 16 class groups x 32
                     plan = "flat_single"
 
             loss_px = lse = grad = pb = None

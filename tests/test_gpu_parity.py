@@ -332,14 +332,21 @@ def test_decode_head_mixin(B):
 
 def test_cuda_graph_capture_replay(B):
     """Every entry point is stream-ordered and allocation-free inside the C ABI: the step captures and replays."""
-    x = synth_logits((2, 19, 16, 32), 7, device='cuda').requires_grad_(True)
+    x0 = synth_logits((2, 19, 16, 32), 7, device='cuda')
     y = synth_labels((2, 128, 256), 19, 7, device='cuda').unsqueeze(1)
     ce = B.CrossEntropyLoss()
-    r = B.fused_resize_losses(x, y, ce, ignore_index=255)
-    r['loss_ce'].backward()
-    want_loss, want_grad = r['loss_ce'].detach().clone(), x.grad.clone()
-    x.grad = None
+
+    def eager():  # own scope: no autograd node of the eager run may outlive it (AccumulateGrad is stream-bound)
+        xe = x0.clone().requires_grad_(True)
+        r = B.fused_resize_losses(xe, y, ce, ignore_index=255)
+        r['loss_ce'].backward()
+        return r['loss_ce'].detach().clone(), xe.grad.clone()
+
+    want_loss, want_grad = eager()
     s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        x = x0.clone().requires_grad_(True)
+    torch.cuda.synchronize()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         for _ in range(2):
