@@ -305,6 +305,51 @@ template <typename T, int NV> __device__ __forceinline__ void block_sum(T (&v)[N
   }
 }
 
+// CTA-wide flush of the per-thread loss / counter partials into the 64-bit statistics block: one REDUX per
+// counter and one shuffle tree for the loss per warp, one shared-memory hop, then <= 5 global atomics per CTA.
+// (The generic block_sum<double,5> costs ~150 instructions per thread; this one ~25.)
+__device__ __forceinline__ void cta_flush_stats(float loss, int n_valid, int n_correct, int n_bad, int n_acc,
+                                                unsigned long long* stats, bool want_ce = true) {
+  __shared__ float s_loss[32];
+  __shared__ int s_cnt[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  loss = warp_sum(loss);
+  n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+  n_correct = __reduce_add_sync(0xffffffffu, n_correct);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  if (lane == 0) {
+    s_loss[warp] = loss;
+    s_cnt[0][warp] = n_valid; s_cnt[1][warp] = n_correct; s_cnt[2][warp] = n_bad; s_cnt[3][warp] = n_acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double l = lane < nwarp ? (double)s_loss[lane] : 0.0;
+    l = warp_sum(l);
+    const int a = __reduce_add_sync(0xffffffffu, lane < nwarp ? s_cnt[0][lane] : 0);
+    const int b = __reduce_add_sync(0xffffffffu, lane < nwarp ? s_cnt[1][lane] : 0);
+    const int c = __reduce_add_sync(0xffffffffu, lane < nwarp ? s_cnt[2][lane] : 0);
+    const int d = __reduce_add_sync(0xffffffffu, lane < nwarp ? s_cnt[3][lane] : 0);
+    if (lane == 0) {
+      if (want_ce) {
+        atomicAdd(reinterpret_cast<double*>(stats + B200SEG_ST_CE_SUM), l);
+        atomicAdd(stats + B200SEG_ST_N_VALID, (unsigned long long)a);
+        if (c) atomicAdd(stats + B200SEG_ST_N_BAD, (unsigned long long)c);
+      }
+      atomicAdd(stats + B200SEG_ST_N_CORRECT, (unsigned long long)b);
+      atomicAdd(stats + B200SEG_ST_N_ACC, (unsigned long long)d);
+    }
+  }
+}
+
+// lg2.approx / rcp.approx: 1 MUFU each (max rel. error 2^-22 / 1 ulp) — used once per pixel
+__device__ __forceinline__ float fast_log(float x) { return __log2f(x) * 0.6931471805599453f; }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------- bilinear source index (ATen)
 // torch/include/ATen/native/UpSample.h:271-312 (area_pixel_compute_scale / _source_index),
 // evaluated in fp32 exactly as ATen does.

@@ -1,0 +1,537 @@
+// Class-split REGISTER-TILE kernels for logits at label resolution, sm_100a:
+//   rt_fwd_kernel<MODE_GRAD>   cross-entropy (+accuracy) forward AND backward in one pass  (b200seg_loss_fused_fwdbwd)
+//   rt_fwd_kernel<MODE_DICE>   Dice partial sums + cross-entropy + accuracy forward        (b200seg_loss_fwd, WANT_DICE)
+//   rt_dice_bwd_kernel         Dice + cross-entropy backward                               (b200seg_loss_bwd,  WANT_DICE)
+//
+// Replaces (reference file:line) DiceLoss.forward models/losses/dice_loss.py:103-134 — F.softmax, F.one_hot (an
+// int64 (N,H,W,C) tensor: 5 GB at ADE20K shape) and the per-class Python loop dice_loss/binary_dice_loss :23-58
+// (>= 7 launches per class) — together with F.cross_entropy / accuracy (cross_entropy_loss.py:56-61,
+// accuracy.py:41-60) and their autograd backwards, with ONE read of the logits per direction.
+//
+// Both Dice (sum_px softmax(z)_c^e for every class) and the single-pass CE gradient need the NORMALISED probability
+// of every (pixel, class) element, so the exponentials must be kept until the per-pixel sum is known. A thread keeps
+// CPT classes x V pixels in registers. If C <= CPT one warp owns all classes of its 32*V pixels and there is no
+// inter-warp traffic at all (SPLIT=false, 4 independent warps per CTA). Otherwise the class dimension is split over
+// G warps (SPLIT=true, CTA = G warps): each warp soft-maxes its own classes against its LOCAL max, the G (max, sum,
+// argmax) partials of a pixel are exchanged through double-buffered shared memory with ONE named barrier per tile
+// and combined online (s = sum_g s_g * 2^((m_g - m) log2e)). Per-pixel work (label, CE term, accuracy, one-hot Dice
+// sums) rotates over the G warps tile by tile. Per-class Dice sums live in per-thread registers across all tiles a
+// CTA visits: one shuffle tree per class per CTA lifetime. One MUFU.EX2 per element.
+//
+// Roofline: HBM. Algorithmic bytes: forward el*s + px*L (+4 px for lse); backward / single pass 2*el*s + px*L.
+#pragma once
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace b200seg {
+
+constexpr float kPad = -1.0e30f;
+enum { MODE_GRAD = 0, MODE_DICE = 1 };
+
+}  // namespace b200seg
+#include "loss_rt_params.cuh"
+namespace b200seg {
+
+__device__ __forceinline__ void cta_named_barrier(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+template <typename T, int V, int CPT, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert(CPT <= 32, "one lane per class in the flush");
+  constexpr int PXW = 32 * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = p.C;
+  const int G = SPLIT ? p.G : 1;
+  const int g = SPLIT ? warp : 0;
+  const int NPG = SPLIT ? 1 : 4;           // pixel groups per CTA
+  const int pgw = SPLIT ? 0 : warp;
+  const int c0 = g * p.cpg;
+  const int c1 = (c0 + p.cpg < C) ? c0 + p.cpg : C;
+  const int n = blockIdx.y;
+  const long long HW = p.HW;
+
+  // shared memory: SPLIT exchange buffers (x2 parity), per-warp one-hot Dice bins
+  float* xm = reinterpret_cast<float*>(smem_raw);             // [2][G][PXW]
+  float* xs = xm + (SPLIT ? 2 * G * PXW : 0);                 // [2][G][PXW]
+  int* xi = reinterpret_cast<int*>(xs + (SPLIT ? 2 * G * PXW : 0));   // [2][G][PXW]
+  float* xk = reinterpret_cast<float*>(xi + (SPLIT ? 2 * G * PXW : 0));  // [2][PXW]   (MODE_GRAD)
+  int* xy = reinterpret_cast<int*>(xk + (SPLIT ? 2 * PXW : 0));        // [2][PXW]   (MODE_GRAD)
+  float* A_s = reinterpret_cast<float*>(xy + (SPLIT ? 2 * PXW : 0));   // [warps][C] (MODE_DICE)
+  const int nwarps = blockDim.x >> 5;
+  float* T_s = A_s + (MODE == MODE_DICE ? nwarps * C : 0);
+  if constexpr (MODE == MODE_DICE) {
+    for (int i = threadIdx.x; i < 2 * nwarps * C; i += blockDim.x) A_s[i] = 0.f;
+    __syncthreads();
+  }
+
+  const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * HW;
+  T* gimg = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW;
+  const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;
+  const bool e2 = (p.dice_exponent == 2.f);
+  float Gs = 0.f;
+  if constexpr (MODE == MODE_GRAD) Gs = p.ce_scale_host * (p.ce_grad_out ? __ldg(p.ce_grad_out) : 1.f);
+
+  float accB[MODE == MODE_DICE ? CPT : 1];
+#pragma unroll
+  for (int i = 0; i < (MODE == MODE_DICE ? CPT : 1); ++i) accB[i] = 0.f;
+  float loss_acc = 0.f;
+  int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    const long long px0 = ((long long)tile * NPG + pgw) * PXW + (long long)lane * V;
+    const bool active = px0 < HW;
+    const bool owner = SPLIT ? ((tile % G) == g) : true;   // the warp doing this tile's per-pixel work
+    float z[CPT][V];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      if (active && c0 + i < c1) {
+        load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) z[i][v] = kPad;
+      }
+    }
+    long long y[V];
+    float pwv[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { y[v] = p.ignore_index; pwv[v] = 1.f; }
+    if (owner && active) {
+      load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
+      if (p.pw && want_ce) load_vec<float, V>(p.pw + (size_t)n * HW + px0, pwv);
+    }
+    // ---- local soft-max over this thread's classes
+    float m[V], s[V];
+    int idx[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float lm = z[0][v];
+      int li = c0;
+#pragma unroll
+      for (int i = 1; i < CPT; ++i) {
+        if (z[i][v] > lm) { lm = z[i][v]; li = c0 + i; }   // strict '>': lowest index wins
+      }
+      const float nm = -lm * kLog2e;
+      float ls = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        z[i][v] = ex2(fmaf(z[i][v], kLog2e, nm));   // padded classes: 2^(-huge) = 0
+        ls += z[i][v];
+      }
+      m[v] = lm; s[v] = ls; idx[v] = li;
+    }
+    // per-pixel CE coefficient and label of this tile (owner), shared with the other class groups in MODE_GRAD
+    float kk[V];
+    int yc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const long long yy = y[v];
+      const bool valid = owner && active && (yy != p.ignore_index) && yy >= 0 && yy < (long long)C;
+      kk[v] = valid ? pwv[v] * (p.cw ? __ldg(p.cw + yy) : 1.f) : 0.f;
+      yc[v] = valid ? (int)yy : -1;
+    }
+    float f[V];
+    if constexpr (SPLIT) {
+      const int par = it & 1;
+      float* bm = xm + par * G * PXW;
+      float* bs = xs + par * G * PXW;
+      int* bi = xi + par * G * PXW;
+      const int slot = g * PXW + lane * V;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { bm[slot + v] = m[v]; bs[slot + v] = s[v]; bi[slot + v] = idx[v]; }
+      if (MODE == MODE_GRAD && owner) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { xk[par * PXW + lane * V + v] = kk[v]; xy[par * PXW + lane * V + v] = yc[v]; }
+      }
+      cta_named_barrier(32 * G);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float gm = bm[lane * V + v];
+        int gi = bi[lane * V + v];
+        for (int gg = 1; gg < G; ++gg) {
+          const float t = bm[gg * PXW + lane * V + v];
+          if (t > gm) { gm = t; gi = bi[gg * PXW + lane * V + v]; }
+        }
+        float gsum = 0.f;
+        for (int gg = 0; gg < G; ++gg)
+          gsum = fmaf(bs[gg * PXW + lane * V + v], ex2((bm[gg * PXW + lane * V + v] - gm) * kLog2e), gsum);
+        f[v] = ex2((m[v] - gm) * kLog2e) * fast_rcp(gsum);
+        m[v] = gm; s[v] = gsum; idx[v] = gi;
+        if constexpr (MODE == MODE_GRAD) { kk[v] = xk[par * PXW + lane * V + v]; yc[v] = xy[par * PXW + lane * V + v]; }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) f[v] = fast_rcp(s[v]);
+    }
+
+    if (active) {
+      if constexpr (MODE == MODE_DICE) {
+        if (e2) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float pr = z[i][v] * f[v];
+              accB[i] = fmaf(pr, pr, accB[i]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float pr = z[i][v] * f[v];
+              accB[i] += pr > 0.f ? __powf(pr, p.dice_exponent) : 0.f;
+            }
+          }
+        }
+      } else {
+        float kg[V], rr[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { kg[v] = kk[v] * Gs; rr[v] = kg[v] * f[v]; }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          if (c0 + i < c1) {
+            float gr[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              gr[v] = rr[v] * z[i][v];
+              if (c0 + i == yc[v]) gr[v] -= kg[v];
+            }
+            store_vec<T, V>(gimg + (size_t)(c0 + i) * HW + px0, gr);
+          }
+        }
+      }
+    }
+
+    if (owner) {  // per-pixel terms: CE, accuracy, one-hot Dice sums
+      float lse[V], lpx[V], pyv[V];
+      int ycl[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) { lse[v] = 0.f; lpx[v] = 0.f; pyv[v] = 0.f; ycl[v] = -1; }
+      if (active) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          lse[v] = m[v] + fast_log(s[v]);
+          const long long yy = y[v];
+          const bool ign = (yy == p.ignore_index);
+          const bool inr = (yy >= 0 && yy < (long long)C);
+          const int ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);   // torch.clamp, dice_loss.py:120
+          float zy = 0.f;
+          if (MODE == MODE_DICE || (want_ce && !ign && inr)) zy = to_float<T>(img[(size_t)ycc * HW + px0 + v]);
+          if (want_ce) {
+            n_bad += (!ign && !inr);
+            n_valid += !ign;
+            const float l = kk[v] * (lse[v] - zy);   // kk = 0 unless the label is valid
+            lpx[v] = l * p.lw;
+            loss_acc += l;
+          }
+          if constexpr (MODE == MODE_DICE) {
+            ycl[v] = ycc;
+            pyv[v] = (yy != p.dice_ignore) ? ex2((zy - lse[v]) * kLog2e) : 0.f;   // valid_mask, dice_loss.py:122
+          }
+          const bool av = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
+          n_acc += av;
+          n_correct += (av && (long long)idx[v] == yy);
+        }
+        if (p.lse_out) store_vec<float, V>(p.lse_out + (size_t)n * HW + px0, lse);
+        if (p.loss_px) store_vec<float, V>(p.loss_px + (size_t)n * HW + px0, lpx);
+      }
+      if constexpr (MODE == MODE_DICE) {
+        // warp-aggregated scatter of (p_y * valid, 1) into this warp's class bins
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int cls = ycl[v];
+          unsigned rem = __ballot_sync(0xffffffffu, cls >= 0);
+          while (rem) {
+            const int leader = __ffs(rem) - 1;
+            const int lc = __shfl_sync(0xffffffffu, cls, leader);
+            const bool mine = (cls == lc);
+            const float sum = warp_sum(mine ? pyv[v] : 0.f);
+            const unsigned mm = __ballot_sync(0xffffffffu, mine);
+            if (lane == leader) {
+              A_s[warp * C + lc] += sum;
+              T_s[warp * C + lc] += (float)__popc(mm);
+            }
+            rem &= ~mm;
+          }
+        }
+      }
+    }
+  }
+
+  if constexpr (MODE == MODE_DICE) {
+    float mineB = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const float tot = warp_sum(accB[i]);
+      if (lane == i) mineB = tot;
+    }
+    if (lane < CPT && c0 + lane < c1) atomicAdd(p.dice_part + ((size_t)n * C + c0 + lane) * 3 + 1, (double)mineB);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f, t = 0.f;
+      for (int q = 0; q < nwarps; ++q) { a += A_s[q * C + c]; t += T_s[q * C + c]; }
+      if (t != 0.f) {
+        atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 0, (double)a);
+        atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 2, (double)t);
+      }
+    }
+  }
+  cta_flush_stats(loss_acc, n_valid, n_correct, n_bad, n_acc, p.stats, want_ce || MODE == MODE_GRAD);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward: grad_z_j = p_j * (g_j - sum_c p_c g_c) [dice, g = dL/dp]  +  k * (p_j - onehot_j) [CE]
+template <typename T, int V, int CPT, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const RtParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PXW = 32 * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = p.C;
+  const int G = SPLIT ? p.G : 1;
+  const int g = SPLIT ? warp : 0;
+  const int NPG = SPLIT ? 1 : 4;
+  const int pgw = SPLIT ? 0 : warp;
+  const int c0 = g * p.cpg;
+  const int c1 = (c0 + p.cpg < C) ? c0 + p.cpg : C;
+  const int n = blockIdx.y;
+  const long long HW = p.HW;
+
+  float* xd = reinterpret_cast<float*>(smem_raw);     // [2][G][PXW] partial dots
+  float* xk = xd + 2 * G * PXW;                        // [2][PXW] CE coefficient
+  float* xa = xk + 2 * PXW;                            // [2][PXW] dice one-hot coefficient
+  int* xy = reinterpret_cast<int*>(xa + 2 * PXW);      // [2][PXW] clamped label
+
+  const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;
+  const bool e2 = (p.dice_exponent == 2.f);
+  float Gce = 0.f;
+  if (want_ce) {
+    Gce = p.ce_scale_host;
+    if (p.ce_grad_out) Gce *= __ldg(p.ce_grad_out);
+    if (p.ce_use_nvalid) {
+      const double nv = (double)(long long)p.stats[B200SEG_ST_N_VALID];
+      Gce = (float)((double)Gce / (nv + 1.1920928955078125e-07));
+    }
+  }
+  const float god = p.dice_grad_out ? __ldg(p.dice_grad_out) : 1.f;
+  float beta[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i)
+    beta[i] = (c0 + i < c1) ? p.dice_exponent * god * __ldg(p.dice_coef + ((size_t)n * C + c0 + i) * 2 + 1) : 0.f;
+
+  const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * HW;
+  T* gimg = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    const long long px0 = ((long long)tile * NPG + pgw) * PXW + (long long)lane * V;
+    const bool active = px0 < HW;
+    const bool owner = SPLIT ? ((tile % G) == g) : true;
+    float z[CPT][V];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      if (active && c0 + i < c1) {
+        load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) z[i][v] = kPad;
+      }
+    }
+    float nl[V];
+    {
+      float lse[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) lse[v] = 0.f;
+      if (active) load_vec<float, V>(p.lse_in + (size_t)n * HW + px0, lse);
+#pragma unroll
+      for (int v = 0; v < V; ++v) nl[v] = -lse[v] * kLog2e;
+    }
+    float dotp[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) dotp[v] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float pr = ex2(fmaf(z[i][v], kLog2e, nl[v]));
+        z[i][v] = pr;
+        if (e2) {
+          dotp[v] = fmaf(beta[i] * pr, pr, dotp[v]);
+        } else {
+          const float gd = pr > 0.f ? beta[i] * __powf(pr, p.dice_exponent - 1.f) : 0.f;
+          dotp[v] = fmaf(gd, pr, dotp[v]);
+        }
+      }
+    }
+    float kk[V], da[V];
+    int yc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { kk[v] = 0.f; da[v] = 0.f; yc[v] = -1; }
+    if (owner && active) {
+      long long y[V];
+      float pwv[V], gpx[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) { pwv[v] = 1.f; gpx[v] = 1.f; }
+      load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
+      if (want_ce && p.pw) load_vec<float, V>(p.pw + (size_t)n * HW + px0, pwv);
+      if (want_ce && p.ce_grad_px) load_vec<float, V>(p.ce_grad_px + (size_t)n * HW + px0, gpx);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const long long yy = y[v];
+        yc[v] = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);
+        if (yy != p.dice_ignore) {
+          da[v] = god * __ldg(p.dice_coef + ((size_t)n * C + yc[v]) * 2 + 0);
+          const float zy = to_float<T>(img[(size_t)yc[v] * HW + px0 + v]);
+          dotp[v] -= da[v] * ex2(fmaf(zy, kLog2e, nl[v]));
+        }
+        const bool valid = (yy != p.ignore_index) && yy >= 0 && yy < (long long)C;
+        if (want_ce && valid) kk[v] = Gce * pwv[v] * gpx[v] * (p.cw ? __ldg(p.cw + yy) : 1.f);
+      }
+    }
+    float sub[V];
+    if constexpr (SPLIT) {
+      const int par = it & 1;
+      float* bd = xd + par * G * PXW;
+      const int ps = par * PXW + lane * V;
+#pragma unroll
+      for (int v = 0; v < V; ++v) bd[g * PXW + lane * V + v] = dotp[v];
+      if (owner) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { xk[ps + v] = kk[v]; xa[ps + v] = da[v]; xy[ps + v] = yc[v]; }
+      }
+      cta_named_barrier(32 * G);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float t = 0.f;
+        for (int gg = 0; gg < G; ++gg) t += bd[gg * PXW + lane * V + v];
+        kk[v] = xk[ps + v];
+        da[v] = xa[ps + v];
+        yc[v] = xy[ps + v];
+        sub[v] = kk[v] - t;   // grad = p * (gd + k - dot)
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) sub[v] = kk[v] - dotp[v];
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        if (c0 + i < c1) {
+          float gr[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float pr = z[i][v];
+            float gd;
+            if (e2) gd = beta[i] * pr;
+            else gd = pr > 0.f ? beta[i] * __powf(pr, p.dice_exponent - 1.f) : 0.f;
+            float gv = pr * (gd + sub[v]);
+            if (c0 + i == yc[v]) gv -= fmaf(pr, da[v], kk[v]);
+            gr[v] = gv;
+          }
+          store_vec<T, V>(gimg + (size_t)(c0 + i) * HW + px0, gr);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int resident_ctas(int threads, int regs_hint) {
+  const int by_regs = 65536 / (threads * regs_hint);
+  const int by_threads = 2048 / threads;
+  int r = by_regs < by_threads ? by_regs : by_threads;
+  return r < 1 ? 1 : r;
+}
+
+template <typename T, int V, int CPT, int MODE> static int launch_rt_fwd(RtParams p, cudaStream_t st) {
+  const bool split = p.C > CPT;
+  p.G = split ? (p.C + CPT - 1) / CPT : 1;
+  p.cpg = (p.C + p.G - 1) / p.G;
+  const int npg = split ? 1 : 4;
+  const long long per_tile = (long long)npg * 32 * V;
+  p.tiles = (int)((p.HW + per_tile - 1) / per_tile);
+  const int threads = split ? 32 * p.G : 128;
+  const int nwarps = threads / 32;
+  size_t smem = 0;
+  if (split) smem += (size_t)(3 * 2 * p.G + 2 * 2) * 32 * V * 4;
+  if (MODE == MODE_DICE) smem += (size_t)2 * nwarps * p.C * 4;
+  int gx = (kSMs * resident_ctas(threads, 128) * (split ? 1 : 2) + p.N - 1) / p.N;
+  if (gx > p.tiles) gx = p.tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, p.N);
+  if constexpr (CPT == 32) {
+    if (split) rt_fwd_kernel<T, V, CPT, MODE, true><<<grid, threads, smem, st>>>(p);
+    else rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
+  } else {
+    rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
+  }
+  count_launch();
+  return check_launch("rt_fwd_kernel");
+}
+
+template <typename T, int V, int CPT> static int launch_rt_bwd(RtParams p, cudaStream_t st) {
+  const bool split = p.C > CPT;
+  p.G = split ? (p.C + CPT - 1) / CPT : 1;
+  p.cpg = (p.C + p.G - 1) / p.G;
+  const int npg = split ? 1 : 4;
+  const long long per_tile = (long long)npg * 32 * V;
+  p.tiles = (int)((p.HW + per_tile - 1) / per_tile);
+  const int threads = split ? 32 * p.G : 128;
+  const size_t smem = split ? (size_t)(2 * p.G + 3 * 2) * 32 * V * 4 : 0;
+  int gx = (kSMs * resident_ctas(threads, 128) * (split ? 1 : 2) + p.N - 1) / p.N;
+  if (gx > p.tiles) gx = p.tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, p.N);
+  if constexpr (CPT == 32) {
+    if (split) rt_dice_bwd_kernel<T, V, CPT, true><<<grid, threads, smem, st>>>(p);
+    else rt_dice_bwd_kernel<T, V, CPT, false><<<grid, threads, smem, st>>>(p);
+  } else {
+    rt_dice_bwd_kernel<T, V, CPT, false><<<grid, threads, smem, st>>>(p);
+  }
+  count_launch();
+  return check_launch("rt_dice_bwd_kernel");
+}
+
+// classes per thread: the smallest instantiation that holds all C classes in one warp; above 32 classes the class
+// dimension is split over up to 16 warps of <= 32 classes. The scalar (V=1) fallback for odd H*W only has 8 / 32.
+static int pick_cpt(int C, int V) {
+  if (V == 1) return C <= 8 ? 8 : 32;
+  if (C <= 32) return C <= 4 ? 4 : (C <= 8 ? 8 : (C <= 12 ? 12 : (C <= 16 ? 16 : (C <= 20 ? 20 : (C <= 24 ? 24 : 32)))));
+  return 32;
+}
+
+#define B200SEG_RT_CASE(CPTV)                                                                      \
+  case CPTV:                                                                                       \
+    if (kind == 0) return launch_rt_fwd<T, V, CPTV, MODE_GRAD>(p, st);                             \
+    if (kind == 1) return launch_rt_fwd<T, V, CPTV, MODE_DICE>(p, st);                             \
+    return launch_rt_bwd<T, V, CPTV>(p, st);
+
+template <typename T, int V> static int rt_pick(const RtParams& p, int kind, cudaStream_t st) {
+  switch (pick_cpt(p.C, V)) {
+    B200SEG_RT_CASE(8)
+    B200SEG_RT_CASE(32)
+    default: break;
+  }
+  if constexpr (V == 2) {
+    switch (pick_cpt(p.C, V)) {
+      B200SEG_RT_CASE(4)
+      B200SEG_RT_CASE(12)
+      B200SEG_RT_CASE(16)
+      B200SEG_RT_CASE(20)
+      B200SEG_RT_CASE(24)
+      default: break;
+    }
+  }
+  set_error("internal: no register-tile instantiation for C=%d", p.C);
+  return 1;
+}
+
+template <typename T> int rt_run(const RtParams& p, int kind, bool vec, cudaStream_t st) {
+  return vec ? rt_pick<T, 2>(p, kind, st) : rt_pick<T, 1>(p, kind, st);
+}
+
+}  // namespace b200seg

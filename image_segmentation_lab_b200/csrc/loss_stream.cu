@@ -82,9 +82,8 @@ template <typename T> __device__ __forceinline__ float interp(const T* plane, co
 }
 
 template <typename T, int V, int CH, bool UP>
-__global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
+__global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeFwdParams p) {
   static_assert(!UP || V == 1, "resize-fused variant is one pixel per thread");
-  __shared__ double sred[5 * 32];
   const int n = blockIdx.y;
   const int C = p.C;
   const long long HW = (long long)p.H * p.W;
@@ -107,8 +106,8 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
     Taps tp;
     if constexpr (UP) tp = make_taps((int)(px0 / p.W), (int)(px0 % p.W), p.h, p.w, p.sh, p.sw, p.align_corners != 0);
 
-    for (int c0 = 0; c0 < C; c0 += CH) {
-      float z[CH][V];
+    // chunk loader: CH classes x V pixels (streaming 128-bit loads; the resize-fused variant interpolates 4 taps)
+    auto load_chunk = [&](int c0, float (&z)[CH][V]) {
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         if (c0 + i < C) {
@@ -122,6 +121,9 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
           for (int v = 0; v < V; ++v) z[i][v] = neg_inf();
         }
       }
+    };
+    // online soft-max update with one chunk (running max m, rescaled sum s, arg-max idx)
+    auto reduce_chunk = [&](int c0, const float (&z)[CH][V]) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         float cm = m[v];
@@ -136,6 +138,18 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
         s[v] = acc;
         m[v] = cm;
       }
+    };
+    // double-buffered: the loads of chunk k+1 are in flight while chunk k is reduced
+    float za[CH][V], zb[CH][V];
+    load_chunk(0, za);
+    for (int c0 = 0; c0 < C; c0 += 2 * CH) {
+      const bool has_b = c0 + CH < C;
+      if (has_b) load_chunk(c0 + CH, zb);
+      reduce_chunk(c0, za);
+      if (has_b) {
+        if (c0 + 2 * CH < C) load_chunk(c0 + 2 * CH, za);
+        reduce_chunk(c0 + CH, zb);
+      }
     }
 
     float lse[V], lpx[V], pwv[V];
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      lse[v] = m[v] + logf(s[v]);
+      lse[v] = m[v] + fast_log(s[v]);
       const long long yy = y[v];
       const bool ign = (yy == p.ignore_index);
       const bool inr = (yy >= 0 && yy < (long long)C);
@@ -172,15 +186,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const CeFwdParams p) {
     if (p.loss_px) store_f32<V>(p.loss_px + (size_t)n * HW + px0, lpx);
   }
 
-  double r[5] = {(double)loss_acc, (double)n_valid, (double)n_correct, (double)n_bad, (double)n_acc};
-  block_sum<double, 5>(r, sred);
-  if (threadIdx.x == 0) {
-    atomicAdd(reinterpret_cast<double*>(p.stats + B200SEG_ST_CE_SUM), r[0]);
-    atomicAdd(p.stats + B200SEG_ST_N_VALID, (unsigned long long)r[1]);
-    atomicAdd(p.stats + B200SEG_ST_N_CORRECT, (unsigned long long)r[2]);
-    if (r[3] != 0.0) atomicAdd(p.stats + B200SEG_ST_N_BAD, (unsigned long long)r[3]);
-    atomicAdd(p.stats + B200SEG_ST_N_ACC, (unsigned long long)r[4]);
-  }
+  cta_flush_stats(loss_acc, n_valid, n_correct, n_bad, n_acc, p.stats);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,10 +371,10 @@ template <typename T> static int launch_ce_fwd(const CeFwdParams& p, bool up, bo
   constexpr int VV = 16 / (int)sizeof(T);
   if (up) {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
-    ce_fwd_kernel<T, 1, 8, true><<<grid, 256, 0, st>>>(p);
+    ce_fwd_kernel<T, 1, 4, true><<<grid, 256, 0, st>>>(p);
   } else if (vec) {
     dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
-    ce_fwd_kernel<T, VV, (VV == 4 ? 8 : 4), false><<<grid, 256, 0, st>>>(p);
+    ce_fwd_kernel<T, VV, (VV == 4 ? 4 : 2), false><<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
     ce_fwd_kernel<T, 1, 8, false><<<grid, 256, 0, st>>>(p);
