@@ -1,31 +1,30 @@
 // Fused arg-max + per-class area histograms (intersect / pred / label), sm_100a.
 //
-// Replaces SegEvaluator.intersect_and_union (core/evaluation/metrics.py:210-270) — three boolean
-// compactions, three float casts, three torch.histc and three .cpu() syncs PER IMAGE — and, in the
-// logits variant, the softmax+argmax of SegEvaluator.process (:101-107), with ONE launch for a
-// whole list of images and no host synchronisation.
+// Replaces SegEvaluator.intersect_and_union (core/evaluation/metrics.py:210-270) — three boolean compactions, three
+// float casts, three torch.histc and three .cpu() syncs PER IMAGE — and, in the logits variant, the softmax+argmax
+// of SegEvaluator.process (:101-107), with ONE launch for a whole list of images and no host synchronisation.
 //
-// Semantics kept (file:line): pixels with gt == ignore_index are dropped from all three histograms
-// (:237-241); intersect counts pred where pred == gt (:248); torch.histc(bins=C, min=0, max=C-1)
-// drops values outside [0, C-1] (:249-265), so an out-of-range gt still leaves its pixel in the
-// pred histogram and vice versa. Areas are exact int64 (the reference stores them in fp32).
+// Semantics kept (file:line): pixels with gt == ignore_index are dropped from all three histograms (:237-241);
+// intersect counts pred where pred == gt (:248); torch.histc(bins=C, min=0, max=C-1) drops values outside [0, C-1]
+// (:249-265), so an out-of-range gt still leaves its pixel in the pred histogram and vice versa. Areas are exact
+// int64 (the reference stores them in fp32).
 //
-// Work split: the images are cut into chunks of kChunk pixels; persistent CTAs (a multiple of the
-// 148 SMs) each take one contiguous range of chunks, so a CTA touches few images and flushes its
-// counters to global memory once per image it touches ("single global flush").
-// Counters: for small C every thread owns a private column cnt[bin][tid] in shared memory
-// (bank == tid, so plain conflict-free LDS/IADD/STS, no atomics — random predictions would
-// otherwise serialise on ATOMS throughput); a pixel needs one update when pred == gt (bin A) and
-// two otherwise (bins B = pred-only, D = gt-only): I = A, P = A + B, L = A + D. For large C a
-// shared-memory atomic histogram with per-thread run-length aggregation is used instead.
+// Work split: the images are cut into chunks of kChunk pixels; persistent CTAs (SMs x resident CTAs) each take one
+// contiguous range of chunks, so a CTA touches few images and flushes its counters to global memory once per image
+// it touches. Every sample is decoded to a 32-bit class index (>= 0 in range, -1 out of range, -2 ignored) with
+// dtype-specialised integer / float compares — no 64-bit arithmetic in the pixel loop.
+// Counters: for small C every thread owns a private column cnt[bin][tid] in shared memory (bank == tid: plain
+// conflict-free LDS/IADD/STS, no atomics — random predictions would otherwise serialise on ATOMS throughput); a
+// pixel needs one update when pred == gt (bin A) and two otherwise (B = pred only, D = gt only): I = A, P = A + B,
+// L = A + D. For large C a shared-memory atomic histogram with per-thread run-length aggregation is used.
 //
-// Roofline: HBM. Algorithmic bytes per pixel: pred bytes + gt bytes (label maps: 8 + 4 = 12;
-// logits: C*s + 4).
+// Roofline: HBM. Algorithmic bytes per pixel: pred bytes + gt bytes (label maps: 8 + 4 = 12; logits: C*s + 4).
 #include "common.cuh"
 
 namespace b200seg {
 
 constexpr int kChunk = 4096;
+constexpr int kIgnored = -2;
 
 struct ConfParams {
   const b200seg_image* images;
@@ -39,13 +38,89 @@ struct ConfParams {
   long long* const* pred_out;
 };
 
+// Decoder of V consecutive samples of a label-like tensor into class indices.
+struct ClassDecoder {
+  int dt, C;
+  bool has_ignore;
+  unsigned ign_lo, ign_hi;   // 64-bit pattern of ignore_index
+  float ign_f;               // ignore_index as float (labels stored as float compare in float, as the reference)
+  bool ign_fits_i32, ign_fits_u8;
+  int ign_i32;
+
+  __device__ __forceinline__ void init(int dtype, int classes, bool with_ignore, long long ignore) {
+    dt = dtype; C = classes; has_ignore = with_ignore;
+    ign_lo = (unsigned)((unsigned long long)ignore & 0xffffffffull);
+    ign_hi = (unsigned)((unsigned long long)ignore >> 32);
+    ign_f = (float)ignore;
+    ign_fits_i32 = (ignore >= -2147483648ll && ignore <= 2147483647ll);
+    ign_fits_u8 = (ignore >= 0 && ignore <= 255);
+    ign_i32 = (int)ignore;
+  }
+  __device__ __forceinline__ int from_i64(unsigned lo, unsigned hi) const {
+    if (has_ignore && lo == ign_lo && hi == ign_hi) return kIgnored;
+    return (hi == 0u && lo < (unsigned)C) ? (int)lo : -1;
+  }
+  __device__ __forceinline__ int from_i32(int v) const {
+    if (has_ignore && ign_fits_i32 && v == ign_i32) return kIgnored;
+    return ((unsigned)v < (unsigned)C) ? v : -1;
+  }
+  __device__ __forceinline__ int from_f32(float f) const {
+    if (has_ignore && f == ign_f) return kIgnored;
+    return (f >= 0.f && f < (float)C) ? (int)f : -1;   // NaN -> -1
+  }
+  __device__ __forceinline__ int from_generic(long long v) const {
+    if (has_ignore && v == (long long)(((unsigned long long)ign_hi << 32) | ign_lo)) return kIgnored;
+    return (v >= 0 && v < (long long)C) ? (int)v : -1;
+  }
+  // scalar path (any dtype, any alignment)
+  __device__ __forceinline__ int one(const void* p, size_t i) const {
+    switch (dt) {
+      case B200SEG_L_I64: { const uint2 r = reinterpret_cast<const uint2*>(p)[i]; return from_i64(r.x, r.y); }
+      case B200SEG_L_F32: return from_f32(reinterpret_cast<const float*>(p)[i]);
+      case B200SEG_L_I32: return from_i32(reinterpret_cast<const int*>(p)[i]);
+      case B200SEG_L_U8: return from_i32((int)reinterpret_cast<const uint8_t*>(p)[i]);
+      case B200SEG_L_I16: return from_i32((int)reinterpret_cast<const int16_t*>(p)[i]);
+      default: {
+        const double d = reinterpret_cast<const double*>(p)[i];
+        if (has_ignore && d == (double)(long long)(((unsigned long long)ign_hi << 32) | ign_lo)) return kIgnored;
+        return (d >= 0.0 && d < (double)C) ? (int)d : -1;
+      }
+    }
+  }
+  // 8 consecutive samples starting at element i (i % 8 == 0, base 16-byte aligned)
+  __device__ __forceinline__ void eight(const void* p, size_t i, int (&o)[8]) const {
+    const char* b = reinterpret_cast<const char*>(p);
+    if (dt == B200SEG_L_I64) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 r = ld_stream16(b + i * 8 + 16 * k);
+        o[2 * k] = from_i64(r.x, r.y);
+        o[2 * k + 1] = from_i64(r.z, r.w);
+      }
+    } else if (dt == B200SEG_L_F32) {
+      const uint4 a = ld_stream16(b + i * 4), c = ld_stream16(b + i * 4 + 16);
+      o[0] = from_f32(__uint_as_float(a.x)); o[1] = from_f32(__uint_as_float(a.y));
+      o[2] = from_f32(__uint_as_float(a.z)); o[3] = from_f32(__uint_as_float(a.w));
+      o[4] = from_f32(__uint_as_float(c.x)); o[5] = from_f32(__uint_as_float(c.y));
+      o[6] = from_f32(__uint_as_float(c.z)); o[7] = from_f32(__uint_as_float(c.w));
+    } else if (dt == B200SEG_L_I32) {
+      const uint4 a = ld_stream16(b + i * 4), c = ld_stream16(b + i * 4 + 16);
+      o[0] = from_i32((int)a.x); o[1] = from_i32((int)a.y); o[2] = from_i32((int)a.z); o[3] = from_i32((int)a.w);
+      o[4] = from_i32((int)c.x); o[5] = from_i32((int)c.y); o[6] = from_i32((int)c.z); o[7] = from_i32((int)c.w);
+    } else if (dt == B200SEG_L_U8) {
+      const uint2 a = ld_stream8(b + i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = from_i32((int)(((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xffu));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = one(p, i + k);
+    }
+  }
+};
+
 template <int THREADS, bool PRIVATE> struct Counters {
   unsigned int* cnt;
   int C;
-  __device__ __forceinline__ void add(int bin) {
-    if constexpr (PRIVATE) cnt[bin * THREADS + threadIdx.x] += 1u;
-    else atomicAdd(cnt + bin, 1u);
-  }
   __device__ __forceinline__ void add_n(int bin, unsigned n) {
     if constexpr (PRIVATE) cnt[bin * THREADS + threadIdx.x] += n;
     else atomicAdd(cnt + bin, n);
@@ -119,6 +194,9 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
   if (chunk >= chunk_end) return;
   int img = find_image(p.chunk_prefix, p.n_images, chunk);
   constexpr int V = 8;
+  ClassDecoder dgt, dpr;
+  dgt.init(p.gt_dtype, C, true, p.ignore);
+  dpr.init(p.pred_dtype, C, false, 0);
 
   while (chunk < chunk_end) {
     while (img + 1 < p.n_images && chunk >= p.chunk_prefix[img + 1]) ++img;  // skips empty images
@@ -131,11 +209,10 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
     long long* pout = (FROM_LOGITS && p.pred_out) ? p.pred_out[img] : nullptr;
 
     for (long long px = px_begin + (long long)threadIdx.x * V; px < px_end; px += (long long)THREADS * V) {
-      long long gt[V];
-      int pv[V];
+      int gv[V], pv[V];
       const int nv = (px_end - px >= V) ? V : (int)(px_end - px);
       if (nv == V && vec_ok) {
-        load_labels<V>(im.gt, p.gt_dtype, (size_t)px, gt);
+        dgt.eight(im.gt, (size_t)px, gv);
         if constexpr (FROM_LOGITS) {
           float best[V];
 #pragma unroll
@@ -162,17 +239,14 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
               st_stream16(pout + px + v, make_uint4((unsigned)pv[v], 0u, (unsigned)pv[v + 1], 0u));
           }
         } else {
-          long long pl[V];
-          load_labels<V>(im.pred, p.pred_dtype, (size_t)px, pl);
-#pragma unroll
-          for (int v = 0; v < V; ++v) pv[v] = (pl[v] >= 0 && pl[v] < (long long)C) ? (int)pl[v] : -1;
+          dpr.eight(im.pred, (size_t)px, pv);
         }
       } else {
         for (int v = 0; v < V; ++v) {
-          gt[v] = p.ignore;
+          gv[v] = kIgnored;
           pv[v] = -1;
           if (v < nv) {
-            gt[v] = load_label(im.gt, p.gt_dtype, (size_t)(px + v));
+            gv[v] = dgt.one(im.gt, (size_t)(px + v));
             if constexpr (FROM_LOGITS) {
               const T* base = reinterpret_cast<const T*>(im.pred) + px + v;
               float best = neg_inf();
@@ -184,8 +258,7 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
               pv[v] = bi;
               if (pout) pout[px + v] = bi;
             } else {
-              const long long pl = load_label(im.pred, p.pred_dtype, (size_t)(px + v));
-              pv[v] = (pl >= 0 && pl < (long long)C) ? (int)pl : -1;
+              pv[v] = dpr.one(im.pred, (size_t)(px + v));
             }
           }
         }
@@ -193,26 +266,22 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
       if constexpr (PRIVATE) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          if (gt[v] != p.ignore) {
-            const int gv = (gt[v] >= 0 && gt[v] < (long long)C) ? (int)gt[v] : -1;
-            ctr.update(pv[v], gv);
-          }
+          if (gv[v] != kIgnored) ctr.update(pv[v], gv[v]);
         }
       } else {
         // run-length aggregation over the thread's V consecutive pixels, then shared atomics
-        int rp = -2, rg = -2;
+        int rp = -3, rg = -3;
         unsigned rn = 0;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const bool live = gt[v] != p.ignore;
-          const int gv = (gt[v] >= 0 && gt[v] < (long long)C) ? (int)gt[v] : -1;
-          if (live && pv[v] == rp && gv == rg) {
+          const bool live = gv[v] != kIgnored;
+          if (live && pv[v] == rp && gv[v] == rg) {
             ++rn;
           } else {
             if (rn) ctr.update(rp, rg, rn);
             rn = live ? 1u : 0u;
-            rp = live ? pv[v] : -2;
-            rg = live ? gv : -2;
+            rp = live ? pv[v] : -3;
+            rg = live ? gv[v] : -3;
           }
         }
         if (rn) ctr.update(rp, rg, rn);

@@ -32,8 +32,10 @@ def _loss_cases(manifest):
     return [c for c in manifest['cases'] if c['kind'] in ('ce', 'dice', 'head')]
 
 
-def _check(out, ref, name, loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, acc_tol=1e-3):
+def _check(out, ref, name, loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, acc_tol=1e-3, loss_atol=0.0):
     for k in ref:
+        if k.startswith('loss') and loss_atol and float((out[k].double().cpu() - ref[k].double().cpu()).abs().max()) <= loss_atol:
+            continue   # cancellation-dominated value (1 - num/den ~ 1e-3): an fp32 ulp of the terms is the floor
         if k == 'grad':
             assert rel_err(out[k], ref[k]) <= grad_tol, '%s grad rel err %.3e' % (name, rel_err(out[k], ref[k]))
         elif k == 'acc':
@@ -170,7 +172,7 @@ def test_golden_process_and_metrics(B, golden, capsys):
 
 # ------------------------------------------------------------------------------------------------ oracle, larger shapes
 def _head_case(B, shape, size, C, dtype, ce_kw, dice_kw, ac=False, ignore=255, seed=0, pixel_weight=False,
-               loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, single_pass=True, margin=True):
+               loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, single_pass=True, margin=True, loss_atol=0.0):
     n = shape[0]
     logits = synth_logits(shape, seed, dtype=dtype, device='cuda', margin=margin)
     labels = synth_labels((n,) + tuple(size), C, seed, ignore_index=ignore, block=8, device='cuda')
@@ -182,7 +184,8 @@ def _head_case(B, shape, size, C, dtype, ce_kw, dice_kw, ac=False, ignore=255, s
         case['kw'] = ce_kw
     out = loss_case_cuda(case, logits, labels, pw, single_pass=single_pass)
     ref = loss_case_oracle(case, logits.float(), labels, pw)   # the unfused ATen chain on the same GPU
-    _check(out, ref, 'head%s' % (shape,), loss_tol=loss_tol, grad_tol=grad_tol, acc_tol=1e-3 if dtype == torch.float32 else 0.5)
+    _check(out, ref, 'head%s' % (shape,), loss_tol=loss_tol, grad_tol=grad_tol, acc_tol=1e-3 if dtype == torch.float32 else 0.5,
+           loss_atol=loss_atol)
     return out, ref
 
 
@@ -228,7 +231,7 @@ def test_config4_voc_shape(B):
 
 def test_ragged_shapes_and_unaligned_views(B):
     _head_case(B, (3, 7, 37, 53), (37, 53), 7, torch.float32, {}, dict())            # H*W odd -> scalar kernels
-    _head_case(B, (1, 3, 1, 1), (1, 1), 3, torch.float32, {}, dict(), ignore=255)    # a single pixel
+    _head_case(B, (1, 3, 1, 1), (1, 1), 3, torch.float32, {}, dict(), ignore=255, loss_atol=2e-7)    # a single pixel
     _head_case(B, (2, 33, 18, 22), (18, 22), 33, torch.float32, {}, dict())          # C just above one chunk
     _head_case(B, (1, 300, 16, 16), (16, 16), 300, torch.float32, {}, dict())        # 10 class groups x 30
     _head_case(B, (1, 600, 8, 8), (8, 8), 600, torch.float32, {}, None)              # CE only: any C
