@@ -125,7 +125,7 @@ template <int THREADS, bool PRIVATE> struct Counters {
     if constexpr (PRIVATE) cnt[bin * THREADS + threadIdx.x] += n;
     else atomicAdd(cnt + bin, n);
   }
-  // pv / gv: class index or -1 when outside [0, C)
+  // pv / gv: class index or -1 when outside [0, C). Atomic flavour (few, aggregated updates): plain branches.
   __device__ __forceinline__ void update(int pv, int gv, unsigned n = 1u) {
     if (pv == gv) {
       if (pv >= 0) add_n(pv, n);
@@ -133,6 +133,22 @@ template <int THREADS, bool PRIVATE> struct Counters {
       if (pv >= 0) add_n(C + pv, n);
       if (gv >= 0) add_n(2 * C + gv, n);
     }
+  }
+  // Private flavour, one pixel: BRANCH-FREE — two unconditional read-modify-writes of this thread's own column
+  // with a 0/1 increment (random predictions make every per-pixel branch divergent).
+  //   match            : cnt[A + pv] += 1 ; cnt[D + gv] += 0
+  //   mismatch         : cnt[B + pv] += 1 ; cnt[D + gv] += 1      (each only if its index is in range)
+  //   gv == kIgnored   : both increments are 0
+  __device__ __forceinline__ void update_private(unsigned int* mine, int pv, int gv) {
+    const bool pin = pv >= 0, gin = gv >= 0;
+    const bool match = pin & (pv == gv);
+    const bool live = gv != kIgnored;
+    const int b1 = pin ? (match ? pv : C + pv) : 0;
+    const int b2 = gin ? 2 * C + gv : 0;
+    const unsigned i1 = (live & pin) ? 1u : 0u;
+    const unsigned i2 = (live & gin & !match) ? 1u : 0u;
+    mine[b1 * THREADS] += i1;
+    mine[b2 * THREADS] += i2;
   }
   __device__ __forceinline__ void zero() {
     const int total = PRIVATE ? 3 * C * THREADS : 3 * C;
@@ -264,10 +280,9 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
         }
       }
       if constexpr (PRIVATE) {
+        unsigned int* mine = ctr.cnt + threadIdx.x;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if (gv[v] != kIgnored) ctr.update(pv[v], gv[v]);
-        }
+        for (int v = 0; v < V; ++v) ctr.update_private(mine, pv[v], gv[v]);
       } else {
         // run-length aggregation over the thread's V consecutive pixels, then shared atomics
         int rp = -3, rg = -3;

@@ -86,13 +86,19 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParam
     const bool active = px0 < HW;
     const bool owner = SPLIT ? ((tile % G) == g) : true;   // the warp doing this tile's per-pixel work
     float z[CPT][V];
+    {
+      // running pointer over the class dimension: one 64-bit add per class instead of a 64-bit multiply-add
+      const T* q = img + (size_t)c0 * HW + px0;
+      const int ncls = active ? c1 - c0 : 0;
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) {
-      if (active && c0 + i < c1) {
-        load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
-      } else {
+      for (int i = 0; i < CPT; ++i) {
+        if (i < ncls) {
+          load_vec<T, V>(q, z[i]);
+        } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) z[i][v] = kPad;
+          for (int v = 0; v < V; ++v) z[i][v] = kPad;
+        }
+        q += HW;
       }
     }
     long long y[V];
@@ -192,17 +198,23 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParam
         float kg[V], rr[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) { kg[v] = kk[v] * Gs; rr[v] = kg[v] * f[v]; }
+        T* gq = gimg + (size_t)c0 * HW + px0;
+        const int ncls = c1 - c0;
+        int yl[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) yl[v] = yc[v] - c0;
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-          if (c0 + i < c1) {
+          if (i < ncls) {
             float gr[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
               gr[v] = rr[v] * z[i][v];
-              if (c0 + i == yc[v]) gr[v] -= kg[v];
+              if (i == yl[v]) gr[v] -= kg[v];
             }
-            store_vec<T, V>(gimg + (size_t)(c0 + i) * HW + px0, gr);
+            store_vec<T, V>(gq, gr);
           }
+          gq += HW;
         }
       }
     }
@@ -332,13 +344,19 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const Rt
     const bool active = px0 < HW;
     const bool owner = SPLIT ? ((tile % G) == g) : true;
     float z[CPT][V];
+    {
+      // running pointer over the class dimension: one 64-bit add per class instead of a 64-bit multiply-add
+      const T* q = img + (size_t)c0 * HW + px0;
+      const int ncls = active ? c1 - c0 : 0;
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) {
-      if (active && c0 + i < c1) {
-        load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
-      } else {
+      for (int i = 0; i < CPT; ++i) {
+        if (i < ncls) {
+          load_vec<T, V>(q, z[i]);
+        } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) z[i][v] = kPad;
+          for (int v = 0; v < V; ++v) z[i][v] = kPad;
+        }
+        q += HW;
       }
     }
     float nl[V];
@@ -418,9 +436,14 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const Rt
       for (int v = 0; v < V; ++v) sub[v] = kk[v] - dotp[v];
     }
     if (active) {
+      T* gq = gimg + (size_t)c0 * HW + px0;
+      const int ncls = c1 - c0;
+      int yl[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) yl[v] = yc[v] - c0;
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
-        if (c0 + i < c1) {
+        if (i < ncls) {
           float gr[V];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
@@ -429,11 +452,12 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const Rt
             if (e2) gd = beta[i] * pr;
             else gd = pr > 0.f ? beta[i] * __powf(pr, p.dice_exponent - 1.f) : 0.f;
             float gv = pr * (gd + sub[v]);
-            if (c0 + i == yc[v]) gv -= fmaf(pr, da[v], kk[v]);
+            if (i == yl[v]) gv -= fmaf(pr, da[v], kk[v]);
             gr[v] = gv;
           }
-          store_vec<T, V>(gimg + (size_t)(c0 + i) * HW + px0, gr);
+          store_vec<T, V>(gq, gr);
         }
+        gq += HW;
       }
     }
   }

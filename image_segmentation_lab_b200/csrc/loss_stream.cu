@@ -107,19 +107,23 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
     if constexpr (UP) tp = make_taps((int)(px0 / p.W), (int)(px0 % p.W), p.h, p.w, p.sh, p.sw, p.align_corners != 0);
 
     // chunk loader: CH classes x V pixels (streaming 128-bit loads; the resize-fused variant interpolates 4 taps)
+    const T* cls_ptr = UP ? img : img + px0;   // running pointer over the class dimension (one 64-bit add per class)
+    const long long cls_stride = UP ? hw : HW;
     auto load_chunk = [&](int c0, float (&z)[CH][V]) {
+      const int left = C - c0;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        if (c0 + i < C) {
+        if (i < left) {
           if constexpr (UP) {
-            z[i][0] = interp<T>(img + (size_t)(c0 + i) * hw, tp);
+            z[i][0] = interp<T>(cls_ptr, tp);
           } else {
-            load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
+            load_vec<T, V>(cls_ptr, z[i]);
           }
         } else {
 #pragma unroll
           for (int v = 0; v < V; ++v) z[i][v] = neg_inf();
         }
+        cls_ptr += cls_stride;
       }
     };
     // online soft-max update with one chunk (running max m, rescaled sum s, arg-max idx)
@@ -274,24 +278,28 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
       atomicAdd(a + tp.o11, tp.w11 * g);
     }
   } else {
-    T* gimg = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW;
+    T* gq = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW + px0;
+    const T* q = img + px0;
     for (int c0 = 0; c0 < C; c0 += CH) {
       float z[CH][V];
+      const int left = C - c0;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        if (c0 + i < C) load_vec<T, V>(img + (size_t)(c0 + i) * HW + px0, z[i]);
+        if (i < left) load_vec<T, V>(q, z[i]);
+        q += HW;
       }
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        if (c0 + i < C) {
+        if (i < left) {
           float g[V];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
             g[v] = coef[v] * ex2(fmaf(z[i][v], kLog2e, nl[v]));
             if (c0 + i == yc[v]) g[v] -= coef[v];
           }
-          store_vec<T, V>(gimg + (size_t)(c0 + i) * HW + px0, g);
+          store_vec<T, V>(gq, g);
         }
+        gq += HW;
       }
     }
   }
