@@ -463,7 +463,7 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     cw = torch.linspace(0.5, 1.5, 150).tolist()
     bench_losses('C3_ade20k_bf16_ce_dice', (16, 150, 512, 512), torch.bfloat16,
                  [B.CrossEntropyLoss(class_weight=cw), B.DiceLoss(loss_weight=3.0)], iters=10,
-                 plan='tile_fwd_kernel + finalize, tile_bwd_kernel (class-split register tiles)')
+                 plan='ce_fwd_kernel(+one-hot dice sums) + dice_sumsq_kernel + finalize; dice_dot_kernel + dice_grad_kernel')
     bench_losses('C4_voc_fp32_ce', (32, 21, 512, 512), torch.float32, B.CrossEntropyLoss(), iters=20, single=True,
                  plan='flat_fused_kernel: forward+backward in one pass')
     ce2 = B.CrossEntropyLoss()

@@ -19,7 +19,7 @@ WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -75,7 +75,7 @@ class LossBwdDesc(C.Structure):
         ("ce_grad_out", C.c_void_p), ("ce_grad_px", C.c_void_p), ("stats", C.c_void_p),
         ("ce_use_nvalid", C.c_int32), ("reserved0", C.c_int32),
         ("dice_coef", C.c_void_p), ("dice_grad_out", C.c_void_p),
-        ("grad_logits", C.c_void_p), ("grad_accum", C.c_void_p),
+        ("grad_logits", C.c_void_p), ("grad_accum", C.c_void_p), ("scratch_px", C.c_void_p),
     ]
 
 

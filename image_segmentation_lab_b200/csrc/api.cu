@@ -34,6 +34,8 @@ int finalize_dispatch(const b200seg_finalize_desc* d, cudaStream_t st);
 int tile_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
 int tile_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st);
 int up_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st);
+int dice_stream_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
+int dice_stream_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st);
 long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac);
 int up_combine_dispatch(const void* ws, void* grad, int dtype, int N, int C, int h, int w, float scale_host,
                         const float* grad_out, int use_nvalid, const uint64_t* stats, cudaStream_t st);
@@ -112,7 +114,8 @@ extern "C" int b200seg_loss_fwd(const b200seg_loss_desc* d, void* stream) {
   }
   if (d->N == 0) return 0;
   B200SEG_REQUIRE(d->logits && d->labels, "loss_fwd: NULL logits/labels");
-  if (d->flags & B200SEG_WANT_DICE) return tile_fwd_dispatch(d, st);
+  // Dice: <= 32 classes fit one warp's register tile (single read); more classes take the streaming kernels
+  if (d->flags & B200SEG_WANT_DICE) return d->C <= 32 ? tile_fwd_dispatch(d, st) : dice_stream_fwd_dispatch(d, st);
   return ce_fwd_dispatch(d, st);
 }
 
@@ -132,7 +135,7 @@ extern "C" int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream) {
   B200SEG_REQUIRE(d->logits && d->labels && d->lse && d->grad_logits, "loss_bwd: NULL tensor");
   B200SEG_REQUIRE(!d->ce_use_nvalid || d->stats, "loss_bwd: ce_use_nvalid without stats");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->flags & B200SEG_WANT_DICE) return tile_bwd_dispatch(d, st);
+  if (d->flags & B200SEG_WANT_DICE) return d->C <= 32 ? tile_bwd_dispatch(d, st) : dice_stream_bwd_dispatch(d, st);
   B200SEG_REQUIRE(d->flags & B200SEG_WANT_CE, "loss_bwd: nothing requested");
   return ce_bwd_dispatch(d, st);
 }

@@ -28,7 +28,7 @@ int flat_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st) {
   const b200seg_loss_desc* f = &d->fwd;
   B200SEG_REQUIRE(d->grad_logits != nullptr, "loss_fused: grad_logits is NULL");
   B200SEG_REQUIRE(!d->use_nvalid, "loss_fused: avg_non_ignore needs the two-pass path at label resolution");
-  B200SEG_REQUIRE(f->C <= 512, "loss_fused: at most 512 classes (got %d)", f->C);
+  B200SEG_REQUIRE(f->C <= 32, "loss_fused: the label-resolution single pass holds at most 32 classes (got %d)", f->C);
   RtParams p = {};
   p.logits = f->logits; p.labels = f->labels; p.pw = f->pixel_weight; p.cw = f->ce_class_weight;
   p.ce_grad_out = d->grad_out; p.stats = reinterpret_cast<unsigned long long*>(f->stats); p.grad = d->grad_logits;
@@ -44,7 +44,7 @@ int flat_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st) {
 
 int tile_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   B200SEG_REQUIRE(d->h == d->H && d->w == d->W, "dice forward needs logits at label resolution (resize first)");
-  B200SEG_REQUIRE(d->C <= 512, "dice path supports at most 512 classes (got %d)", d->C);
+  B200SEG_REQUIRE(d->C <= 32, "register-tile dice path holds at most 32 classes (got %d)", d->C);
   B200SEG_REQUIRE(d->dice_part != nullptr, "dice_part workspace is NULL");
   B200SEG_REQUIRE(d->dice_exponent > 0.f, "dice exponent must be > 0");
   RtParams p = {};
@@ -66,7 +66,7 @@ int tile_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
 
 int tile_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
   B200SEG_REQUIRE(d->h == d->H && d->w == d->W, "dice backward needs logits at label resolution");
-  B200SEG_REQUIRE(d->C <= 512, "dice path supports at most 512 classes (got %d)", d->C);
+  B200SEG_REQUIRE(d->C <= 32, "register-tile dice path holds at most 32 classes (got %d)", d->C);
   B200SEG_REQUIRE(d->dice_coef != nullptr && d->lse != nullptr, "dice backward needs dice_coef and lse");
   RtParams p = {};
   p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;

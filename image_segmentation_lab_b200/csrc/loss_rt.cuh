@@ -487,12 +487,8 @@ template <typename T, int V, int CPT, int MODE> static int launch_rt_fwd(RtParam
   if (gx > p.tiles) gx = p.tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, p.N);
-  if constexpr (CPT == 32) {
-    if (split) rt_fwd_kernel<T, V, CPT, MODE, true><<<grid, threads, smem, st>>>(p);
-    else rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
-  } else {
-    rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
-  }
+  B200SEG_REQUIRE(!split, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
+  rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
   count_launch();
   return check_launch("rt_fwd_kernel");
 }
@@ -510,12 +506,8 @@ template <typename T, int V, int CPT> static int launch_rt_bwd(RtParams p, cudaS
   if (gx > p.tiles) gx = p.tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, p.N);
-  if constexpr (CPT == 32) {
-    if (split) rt_dice_bwd_kernel<T, V, CPT, true><<<grid, threads, smem, st>>>(p);
-    else rt_dice_bwd_kernel<T, V, CPT, false><<<grid, threads, smem, st>>>(p);
-  } else {
-    rt_dice_bwd_kernel<T, V, CPT, false><<<grid, threads, smem, st>>>(p);
-  }
+  B200SEG_REQUIRE(!split, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
+  rt_dice_bwd_kernel<T, V, CPT, false><<<grid, threads, smem, st>>>(p);
   count_launch();
   return check_launch("rt_dice_bwd_kernel");
 }

@@ -34,6 +34,8 @@ struct CeFwdParams {
   long long acc_ignore;
   float lw;
   float sh, sw;
+  double* dice_part;        // (N,C,3) or NULL: also accumulate the one-hot Dice sums [sum p_y*valid, -, count]
+  long long dice_ignore;
 };
 
 template <int V> __device__ __forceinline__ void load_f32(const float* p, float (&o)[V]) {
@@ -92,6 +94,18 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
 
   float loss_acc = 0.f;
   int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
+  // one-hot Dice terms of this thread's pixels (class clamped to [0,C-1], dice_loss.py:119-122)
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  const bool dice = p.dice_part != nullptr;
+  int ycl[V];
+  float pyv[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { ycl[v] = -1; pyv[v] = 0.f; }
+  if (dice) {
+    float* bins = reinterpret_cast<float*>(smem_dyn);
+    for (int i = threadIdx.x; i < 2 * 8 * C; i += blockDim.x) bins[i] = 0.f;
+    __syncthreads();
+  }
 
   if (px0 < HW) {
     long long y[V];
@@ -173,12 +187,19 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
       n_bad += (!ign && !inr);
       n_valid += !ign;
       float l = 0.f;
-      if (valid) {
+      if (valid || dice) {
+        const long long ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : yy);
         float zy;
-        if constexpr (UP) zy = interp<T>(img + (size_t)yy * hw, tp);
-        else zy = to_float<T>(img[(size_t)yy * HW + px0 + v]);
-        const float wt = p.cw ? __ldg(p.cw + yy) : 1.f;
-        l = wt * (lse[v] - zy) * pwv[v];
+        if constexpr (UP) zy = interp<T>(img + (size_t)ycc * hw, tp);
+        else zy = to_float<T>(img[(size_t)ycc * HW + px0 + v]);
+        if (valid) {
+          const float wt = p.cw ? __ldg(p.cw + yy) : 1.f;
+          l = wt * (lse[v] - zy) * pwv[v];
+        }
+        if (dice) {
+          ycl[v] = (int)ycc;
+          pyv[v] = (yy != p.dice_ignore) ? ex2((zy - lse[v]) * kLog2e) : 0.f;   // valid_mask
+        }
       }
       lpx[v] = l * p.lw;
       loss_acc += l;
@@ -190,6 +211,38 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
     if (p.loss_px) store_f32<V>(p.loss_px + (size_t)n * HW + px0, lpx);
   }
 
+  if (dice) {
+    // warp-aggregated scatter of (p_y * valid, 1) into this warp's class bins, then one flush per CTA
+    float* A_s = reinterpret_cast<float*>(smem_dyn);
+    float* T_s = A_s + 8 * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int cls = ycl[v];
+      unsigned rem = __ballot_sync(0xffffffffu, cls >= 0);
+      while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const int lc = __shfl_sync(0xffffffffu, cls, leader);
+        const bool mine = (cls == lc);
+        const float sum = warp_sum(mine ? pyv[v] : 0.f);
+        const unsigned mm = __ballot_sync(0xffffffffu, mine);
+        if (lane == leader) {
+          A_s[warp * C + lc] += sum;
+          T_s[warp * C + lc] += (float)__popc(mm);
+        }
+        rem &= ~mm;
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f, t = 0.f;
+      for (int q = 0; q < 8; ++q) { a += A_s[q * C + c]; t += T_s[q * C + c]; }
+      if (t != 0.f) {
+        atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 0, (double)a);
+        atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 2, (double)t);
+      }
+    }
+  }
   cta_flush_stats(loss_acc, n_valid, n_correct, n_bad, n_acc, p.stats);
 }
 
@@ -377,15 +430,16 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
 template <typename T> static int launch_ce_fwd(const CeFwdParams& p, bool up, bool vec, cudaStream_t st) {
   const long long HW = (long long)p.H * p.W;
   constexpr int VV = 16 / (int)sizeof(T);
+  const size_t sm = p.dice_part ? (size_t)2 * 8 * p.C * sizeof(float) : 0;   // <= 32 KB for C <= 512
   if (up) {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
-    ce_fwd_kernel<T, 1, 4, true><<<grid, 256, 0, st>>>(p);
+    ce_fwd_kernel<T, 1, 4, true><<<grid, 256, sm, st>>>(p);
   } else if (vec) {
     dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
-    ce_fwd_kernel<T, VV, (VV == 4 ? 4 : 2), false><<<grid, 256, 0, st>>>(p);
+    ce_fwd_kernel<T, VV, (VV == 4 ? 4 : 2), false><<<grid, 256, sm, st>>>(p);
   } else {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
-    ce_fwd_kernel<T, 1, 8, false><<<grid, 256, 0, st>>>(p);
+    ce_fwd_kernel<T, 1, 8, false><<<grid, 256, sm, st>>>(p);
   }
   count_launch();
   return check_launch("ce_fwd_kernel");
@@ -430,6 +484,8 @@ int ce_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   p.lw = d->ce_loss_weight;
   p.sh = resize_scale(d->h, d->H, d->align_corners != 0);
   p.sw = resize_scale(d->w, d->W, d->align_corners != 0);
+  p.dice_part = (d->flags & B200SEG_WANT_DICE) ? d->dice_part : nullptr;
+  p.dice_ignore = d->dice_ignore_index;
   const bool up = (d->h != d->H) || (d->w != d->W);
   const long long HW = (long long)d->H * d->W;
   const int VV = 16 / logit_bytes(d->logit_dtype);

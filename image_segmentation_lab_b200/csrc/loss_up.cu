@@ -41,7 +41,7 @@ struct UpParams {
   int NG;    // thread groups (4 px) per row per CTA = 256 / S
   int GPR;   // groups per run = S / 4
   int RT;    // runs per tile = NG / GPR
-  int logCombos;  // log2(2 * RT)
+  int logNG, logGPR, logRT;
   long long ignore_index;
   int acc_has_ignore;
   long long acc_ignore;
@@ -88,12 +88,12 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
   }
   __syncthreads();
 
-  const int i = tid / NG;        // row within the band (NG is a power of two)
-  const int ul = tid - i * NG;   // group within the tile
+  const int i = tid >> p.logNG;  // row within the band
+  const int ul = tid & (NG - 1); // group within the tile
   const int Y = S * b - S / 2 + i;
   const int u = tile * NG + ul;
   const int X0 = 4 * u - S / 2;
-  const int r = u / GPR;
+  const int r = u >> p.logGPR;
   const bool row_ok = (Y >= 0 && Y < p.H);
   const bool any_ok = row_ok && r <= p.w && X0 + 3 >= 0 && X0 < p.W;
   const float ly = row_ok ? lam_y[i] : 0.f;
@@ -102,25 +102,43 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
   int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
 
   if (any_ok) {
+    // horizontal weights of the 4 pixels: lx[j] = lx0 + j/S (exact for power-of-two S); runs 0 / w are clamped
     float lx[4];
     bool pix_ok[4];
+    {
+      const float invS = 1.f / (float)S;
+      const float lx0 = ((float)X0 + 0.5f) * invS - 0.5f - (float)(r - 1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int X = X0 + j;
-      pix_ok[j] = (X >= 0 && X < p.W);
-      float l;
-      if (r == 0) l = 1.f;
-      else if (r == p.w) l = 0.f;
-      else l = ((float)X + 0.5f) / (float)S - 0.5f - (float)(r - 1);
-      lx[j] = l;
+      for (int j = 0; j < 4; ++j) {
+        const int X = X0 + j;
+        pix_ok[j] = (X >= 0 && X < p.W);
+        lx[j] = (r == 0) ? 1.f : ((r == p.w) ? 0.f : fmaf((float)j, invS, lx0));
+      }
     }
-    long long y[4];
+    // labels of the 4 pixels as 32-bit class indices: >= 0 valid, -1 not in [0,C) ("bad"), -2 ignored
+    int y32[4];
+    bool acc_ok[4];
     const size_t lbase = ((size_t)n * p.H + Y) * p.W;
-    if (X0 >= 0 && X0 + 3 < p.W && ((lbase + X0) & 3) == 0 && aligned16(p.labels)) {
-      load_labels<4>(p.labels, p.label_dtype, lbase + X0, y);
+    if (p.label_dtype == B200SEG_L_I64 && X0 >= 0 && X0 + 3 < p.W && ((lbase + X0) & 1) == 0 && aligned16(p.labels)) {
+      const char* lp = reinterpret_cast<const char*>(p.labels) + (lbase + X0) * 8;
+      const uint4 a = ld_stream16(lp), c = ld_stream16(lp + 16);
+      const unsigned lo[4] = {a.x, a.z, c.x, c.z}, hi[4] = {a.y, a.w, c.y, c.w};
+      const unsigned ig_lo = (unsigned)((unsigned long long)p.ignore_index), ig_hi = (unsigned)((unsigned long long)p.ignore_index >> 32);
+      const unsigned ag_lo = (unsigned)((unsigned long long)p.acc_ignore), ag_hi = (unsigned)((unsigned long long)p.acc_ignore >> 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ign = (lo[j] == ig_lo) & (hi[j] == ig_hi);
+        const bool inr = (hi[j] == 0u) & (lo[j] < (unsigned)C);
+        y32[j] = ign ? -2 : (inr ? (int)lo[j] : -1);
+        acc_ok[j] = p.acc_has_ignore ? !((lo[j] == ag_lo) & (hi[j] == ag_hi)) : true;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) y[j] = pix_ok[j] ? load_label(p.labels, p.label_dtype, lbase + X0 + j) : p.ignore_index;
+      for (int j = 0; j < 4; ++j) {
+        const long long yy = pix_ok[j] ? load_label(p.labels, p.label_dtype, lbase + X0 + j) : p.ignore_index;
+        y32[j] = (yy == p.ignore_index) ? -2 : ((yy >= 0 && yy < (long long)C) ? (int)yy : -1);
+        acc_ok[j] = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
+      }
     }
 
     float e[CPT][4];
@@ -147,13 +165,14 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float nm = -m[j] * kLog2e;
-      float acc = 0.f;
+      float acc0 = 0.f, acc1 = 0.f;   // two chains: more ILP for the 4 warps per scheduler
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         e[c][j] = ex2(fmaf(e[c][j], kLog2e, nm));
-        acc += e[c][j];
+        if (c & 1) acc1 += e[c][j];
+        else acc0 += e[c][j];
       }
-      s[j] = acc;
+      s[j] = acc0 + acc1;
     }
     float coef[4];
     int ycl[4];
@@ -162,26 +181,22 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
       coef[j] = 0.f;
       ycl[j] = -1;
       if (pix_ok[j]) {
-        const long long yy = y[j];
-        const bool ign = (yy == p.ignore_index);
-        const bool inr = (yy >= 0 && yy < (long long)C);
-        n_bad += (!ign && !inr);
-        n_valid += !ign;
-        if (!ign && inr) {
-          const int yc = (int)yy;
-          const float a0 = pc[(yc * 2 + 0) * kPatchStride], a1 = pc[(yc * 2 + 0) * kPatchStride + 1];
-          const float b0 = pc[(yc * 2 + 1) * kPatchStride], b1 = pc[(yc * 2 + 1) * kPatchStride + 1];
+        const int yc = y32[j];
+        n_bad += (yc == -1);
+        n_valid += (yc != -2);
+        if (yc >= 0) {
+          const float* py = pc + yc * (2 * kPatchStride);
+          const float a0 = py[0], a1 = py[1], b0 = py[kPatchStride], b1 = py[kPatchStride + 1];
           const float va = fmaf(ly, b0 - a0, a0), vb = fmaf(ly, b1 - a1, a1);
           const float zy = fmaf(lx[j], vb - va, va);   // same operation order as the class loop: bitwise equal
-          float wt = p.cw ? __ldg(p.cw + yy) : 1.f;
+          float wt = p.cw ? __ldg(p.cw + yc) : 1.f;
           if (p.pw) wt *= __ldg(p.pw + lbase + X0 + j);
-          loss_acc += wt * (m[j] + fast_log(s[j]) - zy);
+          loss_acc = fmaf(wt, m[j] + fast_log(s[j]) - zy, loss_acc);
           coef[j] = wt;
           ycl[j] = yc;
         }
-        const bool av = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
-        n_acc += av;
-        n_correct += (av && (long long)idx[j] == yy);
+        n_acc += acc_ok[j];
+        n_correct += (acc_ok[j] && idx[j] == yc);
       }
     }
     if constexpr (GRAD) {
@@ -219,29 +234,27 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
 
   if constexpr (GRAD) {
     __syncthreads();
-    // fixed-order per-cell reduction: thread = (run of the tile, corner row), classes strided over the CTA
-    const int combos = 1 << p.logCombos;          // 2 * RT
-    const int t = tid & (combos - 1);
-    const int cr = t & 1, rl = t >> 1;
+    // fixed-order per-cell reduction: thread = run of the tile (both corner rows), classes strided over the CTA
+    const int rl = tid & (RT - 1);
     const int rr = r_first + rl;
     if (rr <= p.w) {
-      const int cstep = 256 >> p.logCombos;
-      for (int c = tid >> p.logCombos; c < C; c += cstep) {
-        float sa = 0.f, sb = 0.f;
+      const int cstep = 256 >> p.logRT;
+      for (int c = tid >> p.logRT; c < C; c += cstep) {
+        float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
         const float2* base = stage + c * 256 + rl * GPR;
         for (int ii = 0; ii < S; ++ii) {
           const float l = lam_y[ii];
           if (l < 0.f) continue;
-          const float wy = cr ? l : 1.f - l;
           const float2* row = base + ii * NG;
           float ra = 0.f, rb = 0.f;
           for (int q = 0; q < GPR; ++q) { ra += row[q].x; rb += row[q].y; }
-          sa = fmaf(wy, ra, sa);
-          sb = fmaf(wy, rb, sb);
+          s1a = fmaf(l, ra, s1a);
+          s1b = fmaf(l, rb, s1b);
+          s0a = fmaf(1.f - l, ra, s0a);
+          s0b = fmaf(1.f - l, rb, s0b);
         }
-        float2* dst = reinterpret_cast<float2*>(p.pb) +
-                      ((((size_t)n * C + c) * (p.h + 1) + b) * (p.w + 1) + rr) * 2 + cr;
-        *dst = make_float2(sa, sb);
+        float4* dst = reinterpret_cast<float4*>(p.pb) + (((size_t)n * C + c) * (p.h + 1) + b) * (p.w + 1) + rr;
+        *dst = make_float4(s0a, s0b, s1a, s1b);
       }
     }
   }
@@ -375,8 +388,9 @@ template <typename T> static int up_run(const b200seg_loss_fused_desc* d, int S,
   p.N = f->N; p.C = f->C; p.h = f->h; p.w = f->w; p.H = f->H; p.W = f->W;
   p.S = S;
   p.NG = 256 / S; p.GPR = S / 4; p.RT = p.NG / p.GPR;
-  p.logCombos = 0;
-  while ((1 << p.logCombos) < 2 * p.RT) ++p.logCombos;
+  p.logNG = 0; while ((1 << p.logNG) < p.NG) ++p.logNG;
+  p.logGPR = 0; while ((1 << p.logGPR) < p.GPR) ++p.logGPR;
+  p.logRT = 0; while ((1 << p.logRT) < p.RT) ++p.logRT;
   p.ignore_index = f->ignore_index; p.acc_has_ignore = f->acc_has_ignore; p.acc_ignore = f->acc_ignore_index;
   const bool grad = d->grad_logits != nullptr || d->defer_combine;
   if (!grad) return pick_up<T, false>(p, st);

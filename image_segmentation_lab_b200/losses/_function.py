@@ -147,7 +147,7 @@ class FusedLossFunction(torch.autograd.Function):
                 if up:
                     if lib.b200seg_loss_fused_workspace_bytes(N, Cc, h, w, H, W, fd.align_corners) > 0:
                         plan = "up_single"
-                elif needs_grad and not use_nvalid and Cc <= 512:  # register tile: <= 16 class groups x 32
+                elif needs_grad and not use_nvalid and Cc <= 32:  # one warp's register tile holds all classes
                     plan = "flat_single"
 
             loss_px = lse = grad = pb = None
@@ -156,7 +156,7 @@ class FusedLossFunction(torch.autograd.Function):
                     loss_px = torch.empty((N, H, W), dtype=torch.float32, device=dev)
                     flags |= _lib.WANT_LOSS_PX
                     fd.loss_px = loss_px.data_ptr()
-                if needs_grad:
+                if needs_grad or (spec.want_dice and Cc > 32):   # the streaming Dice kernels read lse back
                     lse = torch.empty((N, H, W), dtype=torch.float32, device=dev)
                     flags |= _lib.WANT_LSE
                     fd.lse = lse.data_ptr()
@@ -299,6 +299,10 @@ class FusedLossFunction(torch.autograd.Function):
                 acc = torch.empty(logits.shape, dtype=torch.float32, device=dev)
                 keep.append(acc)
                 bd.grad_accum = acc.data_ptr()
+            if want_dice and Cc > 32:
+                dot = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+                keep.append(dot)
+                bd.scratch_px = dot.data_ptr()
             _lib.check(lib.b200seg_loss_bwd(C.byref(bd), stream))
         return out, None, None, None
 

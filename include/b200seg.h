@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 4
+#define B200SEG_ABI_VERSION 5
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -155,6 +155,7 @@ typedef struct b200seg_loss_bwd_desc {
   const float* dice_grad_out;       /* scalar f32 (device) or NULL                             */
   void*   grad_logits;              /* (N,C,h,w) logit_dtype, fully overwritten                */
   float*  grad_accum;               /* (N,C,h,w) f32 scratch: required when (h,w)!=(H,W)       */
+  float*  scratch_px;               /* (N,H,W) f32 scratch: required for dice with C > 32      */
 } b200seg_loss_bwd_desc;
 
 /* Fused backward: d(loss)/d(logits) in one pass (softmax Jacobian, dice, resize transpose). */

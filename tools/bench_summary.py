@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Prints a compact summary of a bench.py JSON line (file argument or stdin)."""
+import json
+import sys
+
+txt = open(sys.argv[1]).read() if len(sys.argv) > 1 else sys.stdin.read()
+lines = [l for l in txt.splitlines() if l.startswith('{')]
+if not lines:
+    print(txt[-3000:])
+    sys.exit(1)
+d = json.loads(lines[-1])
+print('C2 value %.0f Mpix/s  ms/step %.4f  e2e %.0f Mpix/s  launches/step %s  n_gpus %s' % (
+    d['value'], d['ms_per_step'], d['e2e']['value'], d.get('launches_per_step'), d['n_gpus']))
+r = d.get('roofline')
+if r:
+    print('  %s: %.1f us  %.0f GB/s  frac %.3f' % (r.get('kernel'), r['ms_per_launch'] * 1e3, r['achieved'], r['frac']))
+if 'cpu_baseline' in d:
+    print('  cpu %.1f Mpix/s on %s cores; clocks %s' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores'], d.get('clocks')))
+for k, v in d.get('workloads', {}).items():
+    if isinstance(v, dict) and 'fwd' in v:
+        print('  %-28s fwd %.3f ms (%.2f)  fwd+bwd %.3f ms (%.2f)  %s' % (
+            k, v['fwd']['ms'], v['fwd']['roofline']['frac'], v['fwd_bwd']['ms'], v['fwd_bwd']['roofline']['frac'],
+            v['fwd_bwd'].get('plan', '')[:46]))
+    elif isinstance(v, dict) and 'ms' in v:
+        print('  %-28s %.3f ms  %.0f Mpix/s  frac %.2f' % (k, v['ms'], v['mpix_s'], v['roofline']['frac']))
+    else:
+        print('  ', k, v)
