@@ -19,7 +19,7 @@ WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -88,6 +88,18 @@ class LossFusedDesc(C.Structure):
     ]
 
 
+class BceDesc(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("labels", C.c_void_p), ("pixel_weight", C.c_void_p), ("pos_weight", C.c_void_p),
+        ("logit_dtype", C.c_int32), ("label_dtype", C.c_int32), ("N", C.c_int32), ("C", C.c_int32),
+        ("HW", C.c_int64), ("ignore_index", C.c_int64),
+        ("single_channel", C.c_int32), ("use_nvalid", C.c_int32),
+        ("loss_weight", C.c_float), ("grad_scale_host", C.c_float),
+        ("loss_elem", C.c_void_p), ("grad_out", C.c_void_p), ("grad_elem", C.c_void_p), ("grad_logits", C.c_void_p),
+        ("stats", C.c_void_p),
+    ]
+
+
 class Image(C.Structure):
     _fields_ = [
         ("pred", C.c_void_p), ("gt", C.c_void_p), ("n_pixels", C.c_int64),
@@ -113,8 +125,8 @@ SYMBOLS = [
     ("b200seg_confusion_chunk_pixels", _i32, []),
     ("b200seg_topk_counts", C.c_int,
      [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _i64, C.POINTER(_i32), _i32, _i32, _f, _p, _p]),
-    ("b200seg_bce_fwd", C.c_int, None),   # bound in _bind_optional (struct defined in losses/_bce.py)
-    ("b200seg_bce_bwd", C.c_int, None),
+    ("b200seg_bce_fwd", C.c_int, [C.POINTER(BceDesc), _p]),
+    ("b200seg_bce_bwd", C.c_int, [C.POINTER(BceDesc), _p]),
     ("b200seg_last_error", C.c_char_p, []),
     ("b200seg_abi_version", _i32, []),
     ("b200seg_launch_count", _i64, []),
@@ -142,8 +154,6 @@ def load():
     lib = C.CDLL(path)
     for name, restype, argtypes in SYMBOLS:
         if not hasattr(lib, name):
-            if argtypes is None:
-                continue
             raise RuntimeError("libb200seg.so does not export %s — rebuild it" % name)
         fn = getattr(lib, name)
         fn.restype = restype

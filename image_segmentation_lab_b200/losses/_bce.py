@@ -1,0 +1,140 @@
+"""Sigmoid cross-entropy with the reference's signature (models/losses/cross_entropy_loss.py:77-164) on
+csrc/loss_bce.cu: the one-hot target, the valid mask and the expanded pixel weight are formed inside the kernel."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from ._function import prep_labels
+
+_EPS = float(torch.finfo(torch.float32).eps)
+
+
+class _BceFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, label, weight, pos_weight, reduction, avg_factor, ignore_index, avg_non_ignore, single):
+        lib = _lib.load()
+        _lib.require_cuda(pred, 'pred')
+        if pred.dtype not in _lib.LOGIT_DTYPES:
+            raise TypeError('pred must be float32, bfloat16 or float16, got %s' % pred.dtype)
+        x = pred.contiguous()
+        N, Cc = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        dev = x.device
+        lab = label
+        if lab.dtype not in _lib.LABEL_DTYPES:
+            lab = lab.long()
+        lab = lab.to(dev).contiguous()
+        assert lab.numel() == N * HW, 'label must have one entry per pixel'
+        w = None
+        if weight is not None:
+            w = weight.to(device=dev, dtype=torch.float32).contiguous()
+            assert w.numel() == N * HW, 'weight must have one entry per pixel'
+        needs_grad = bool(ctx.needs_input_grad[0])
+        use_nvalid = bool(reduction == 'mean' and avg_factor is None and avg_non_ignore)
+        n_elem = max(N * Cc * HW, 1)
+        scale = 1.0
+        if reduction == 'mean':
+            if avg_factor is not None:
+                scale = 1.0 / float(torch.tensor(avg_factor + _EPS, dtype=torch.float32))
+            elif not use_nvalid:
+                scale = 1.0 / n_elem
+        with torch.cuda.device(dev):
+            stats = torch.empty(2, dtype=torch.int64, device=dev)
+            loss_elem = torch.empty(x.shape, dtype=torch.float32, device=dev) if reduction == 'none' else None
+            d = _lib.BceDesc()
+            d.logits = x.data_ptr(); d.labels = lab.data_ptr()
+            d.pixel_weight = w.data_ptr() if w is not None else None
+            d.pos_weight = pos_weight.data_ptr() if pos_weight is not None else None
+            d.logit_dtype = _lib.LOGIT_DTYPES[x.dtype]; d.label_dtype = _lib.LABEL_DTYPES[lab.dtype]
+            d.N, d.C, d.HW = N, Cc, HW
+            d.ignore_index = int(ignore_index)
+            d.single_channel = int(bool(single))
+            d.loss_weight = 1.0
+            d.loss_elem = loss_elem.data_ptr() if loss_elem is not None else None
+            d.stats = stats.data_ptr()
+            _lib.check(lib.b200seg_bce_fwd(C.byref(d), _lib.stream_ptr(dev)))
+            if reduction == 'none':
+                out = loss_elem
+            else:
+                total = stats[:1].view(torch.float64)[0]
+                if use_nvalid:
+                    denom = (stats[1].to(torch.float64) * Cc + _EPS).to(torch.float32).to(torch.float64)
+                    out = (total / denom).to(torch.float32)
+                else:
+                    out = (total * scale).to(torch.float32)
+        if needs_grad:
+            ctx.save_for_backward(x, lab, w if w is not None else stats, stats)
+            ctx.has_w = w is not None
+            ctx.pos_weight = pos_weight
+            ctx.cfg = (reduction, scale, use_nvalid, int(ignore_index), bool(single))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, lab, w, stats = ctx.saved_tensors
+        reduction, scale, use_nvalid, ignore_index, single = ctx.cfg
+        N, Cc = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        dev = x.device
+        with torch.cuda.device(dev):
+            grad = torch.empty_like(x)
+            d = _lib.BceDesc()
+            d.logits = x.data_ptr(); d.labels = lab.data_ptr()
+            d.pixel_weight = w.data_ptr() if ctx.has_w else None
+            d.pos_weight = ctx.pos_weight.data_ptr() if ctx.pos_weight is not None else None
+            d.logit_dtype = _lib.LOGIT_DTYPES[x.dtype]; d.label_dtype = _lib.LABEL_DTYPES[lab.dtype]
+            d.N, d.C, d.HW = N, Cc, HW
+            d.ignore_index = ignore_index
+            d.single_channel = int(single)
+            d.use_nvalid = int(use_nvalid)
+            d.grad_scale_host = float(scale)
+            keep = g.detach().to(torch.float32)
+            if reduction == 'none':
+                keep = keep.expand(x.shape).contiguous()
+                d.grad_elem = keep.data_ptr()
+            else:
+                keep = keep.reshape(()).contiguous()
+                d.grad_out = keep.data_ptr()
+            d.grad_logits = grad.data_ptr()
+            d.stats = stats.data_ptr()
+            _lib.check(lib.b200seg_bce_bwd(C.byref(d), _lib.stream_ptr(dev)))
+        return grad, None, None, None, None, None, None, None, None
+
+
+def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=None, class_weight=None,
+                         ignore_index=-100, avg_non_ignore=False, **kwargs):
+    """Same arguments and results as the reference (:100-164). ``pred`` (N,C,H,W) with ``label`` (N,H,W) expands
+    the label to one-hot inside the kernel; ``pred`` (N,1,H,W) treats the label (0/1) as the target (:126-134);
+    ``pred`` and ``label`` of equal shape use the label as a soft target mask as the reference does."""
+    if reduction not in ('none', 'mean', 'sum'):
+        raise ValueError('%s is not a valid value for reduction' % reduction)
+    if avg_factor is not None and reduction == 'sum':
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    single = False
+    if pred.size(1) == 1 and pred.dim() == label.dim() + 1:
+        single = True                       # the reference squeezes the channel (:133) and checks label <= 1 (:130)
+    elif pred.dim() == label.dim():
+        # element-wise targets: treat every element as its own pixel of a 1-channel prediction
+        shape = pred.shape
+        out = _BceFunction.apply(pred.reshape(-1, 1, 1), label.reshape(-1, 1), None if weight is None else weight.reshape(-1, 1),
+                                 None, reduction, avg_factor, ignore_index, avg_non_ignore, True)
+        return out.reshape(shape) if reduction == 'none' else out
+    else:
+        assert (pred.dim() == 2 and label.dim() == 1) or (pred.dim() == 4 and label.dim() == 3), \
+            'Only pred shape [N, C], label shape [N] or pred shape [N, C, H, W], label shape [N, H, W] are supported'
+    x = pred if pred.dim() >= 3 else pred.unsqueeze(-1)
+    pos_w = None
+    if class_weight is not None:
+        pos_w = torch.as_tensor(class_weight, dtype=torch.float32, device=pred.device).contiguous()
+        if single and pos_w.numel() != 1:
+            pos_w = pos_w.reshape(-1)[:1].contiguous() if pos_w.numel() == 1 else pos_w
+    out = _BceFunction.apply(x, label, weight, pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, single)
+    if reduction == 'none':
+        out = out.reshape(pred.shape)
+        if single:
+            out = out.squeeze(1)
+    if pred.dtype != torch.float32 and not torch.is_autocast_enabled():
+        out = out.to(pred.dtype)
+    return out

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 5
+#define B200SEG_ABI_VERSION 6
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -193,6 +193,30 @@ int b200seg_loss_fused_combine(const void* workspace, void* grad_logits, int32_t
 
 /* x *= *g in place (n elements of dtype); returns immediately on the device when *g == 1. */
 int b200seg_scale_inplace(void* x, int32_t dtype, int64_t n, const float* g, void* stream);
+
+/* Sigmoid cross-entropy, one-hot expansion fused in: binary_cross_entropy + _expand_onehot_labels,
+ * models/losses/cross_entropy_loss.py:77-164 (CrossEntropyLoss(use_sigmoid=True), the shipped default config).  */
+typedef struct b200seg_bce_desc {
+  const void*  logits;          /* (N,C,HW) logit_dtype                                           */
+  const void*  labels;          /* (N,HW)   label_dtype                                           */
+  const float* pixel_weight;    /* (N,HW) f32 or NULL                                             */
+  const float* pos_weight;      /* (C) f32 or NULL  (class_weight -> pos_weight, :160-161)        */
+  int32_t logit_dtype, label_dtype;
+  int32_t N, C;
+  int64_t HW;
+  int64_t ignore_index;
+  int32_t single_channel;       /* prediction was (N,1,H,W): target = label (0/1), :126-134       */
+  int32_t use_nvalid;           /* backward: divide by (n_valid_pixels*C + eps)  (avg_non_ignore) */
+  float   loss_weight;          /* forward: multiplies loss_elem                                  */
+  float   grad_scale_host;      /* backward: G = grad_scale_host * (*grad_out or 1) [/ n_valid]   */
+  float*  loss_elem;            /* forward: (N,C,HW) f32 per-element loss or NULL                 */
+  const float* grad_out;        /* backward: scalar f32 (device) or NULL                          */
+  const float* grad_elem;       /* backward: (N,C,HW) f32 upstream gradient (reduction='none')    */
+  void*   grad_logits;          /* backward: (N,C,HW) logit_dtype                                 */
+  uint64_t* stats;              /* [0] double: sum of weighted losses; [1] int64: valid pixels    */
+} b200seg_bce_desc;
+int b200seg_bce_fwd(const b200seg_bce_desc* d, void* stream);   /* zeroes stats, then accumulates     */
+int b200seg_bce_bwd(const b200seg_bce_desc* d, void* stream);   /* reads stats[1] when use_nvalid     */
 
 /* Bilinear resize, ATen semantics (torch/include/ATen/native/UpSample.h:271-312,442-476). */
 int b200seg_resize_bilinear_fwd(const void* in, void* out, int32_t dtype, int32_t NC, int32_t h, int32_t w,

@@ -54,8 +54,8 @@ def test_struct_layouts_match_c_compiler():
 #include <stddef.h>
 #include "b200seg.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu\n", sizeof(b200seg_loss_desc), sizeof(b200seg_finalize_desc), sizeof(b200seg_loss_bwd_desc),
-         sizeof(b200seg_loss_fused_desc), sizeof(b200seg_image));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(b200seg_loss_desc), sizeof(b200seg_finalize_desc), sizeof(b200seg_loss_bwd_desc),
+         sizeof(b200seg_loss_fused_desc), sizeof(b200seg_image), sizeof(b200seg_bce_desc));
   printf("%zu %zu %zu %zu\n", offsetof(b200seg_loss_desc, ignore_index), offsetof(b200seg_loss_desc, stats),
          offsetof(b200seg_loss_bwd_desc, grad_logits), offsetof(b200seg_loss_fused_desc, workspace));
   return 0;
@@ -68,9 +68,9 @@ int main(void) {
         subprocess.run([gcc, '-I', os.path.join(ROOT, 'include'), src, '-o', exe], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
     sizes = [int(x) for x in out]
-    assert sizes[:5] == [ctypes.sizeof(_lib.LossDesc), ctypes.sizeof(_lib.FinalizeDesc), ctypes.sizeof(_lib.LossBwdDesc),
-                         ctypes.sizeof(_lib.LossFusedDesc), ctypes.sizeof(_lib.Image)]
-    assert sizes[5:] == [_lib.LossDesc.ignore_index.offset, _lib.LossDesc.stats.offset,
+    assert sizes[:6] == [ctypes.sizeof(_lib.LossDesc), ctypes.sizeof(_lib.FinalizeDesc), ctypes.sizeof(_lib.LossBwdDesc),
+                         ctypes.sizeof(_lib.LossFusedDesc), ctypes.sizeof(_lib.Image), ctypes.sizeof(_lib.BceDesc)]
+    assert sizes[6:] == [_lib.LossDesc.ignore_index.offset, _lib.LossDesc.stats.offset,
                          _lib.LossBwdDesc.grad_logits.offset, _lib.LossFusedDesc.workspace.offset]
 
 
