@@ -178,6 +178,47 @@ template <typename T, int V> __device__ __forceinline__ void load_vec(const T* p
   }
 }
 
+// V consecutive fp32 values of a per-pixel map (V up to 8: two 128-bit accesses)
+template <int V> __device__ __forceinline__ void load_px_f32(const float* p, float (&o)[V]) {
+  if constexpr (V == 8) {
+    float a[4], b[4];
+    load_vec<float, 4>(p, a);
+    load_vec<float, 4>(p + 4, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[k] = a[k]; o[4 + k] = b[k]; }
+  } else {
+    load_vec<float, V>(p, o);
+  }
+}
+
+// Raw (still packed) form of V consecutive elements: loads stay in as few registers as the bytes they carry, so a
+// thread can keep more bytes in flight; convert with unpack_raw() only where the values are consumed.
+template <typename T, int V> struct RawVec {
+  static constexpr int W = (V * (int)sizeof(T) + 3) / 4;
+  uint32_t w[W];
+};
+template <typename T, int V> __device__ __forceinline__ RawVec<T, V> load_raw(const T* p) {
+  RawVec<T, V> r;
+  constexpr int B = V * (int)sizeof(T);
+  if constexpr (B == 16) { const uint4 t = ld_stream16(p); r.w[0] = t.x; r.w[1] = t.y; r.w[2] = t.z; r.w[3] = t.w; }
+  else if constexpr (B == 8) { const uint2 t = ld_stream8(p); r.w[0] = t.x; r.w[1] = t.y; }
+  else if constexpr (B == 4) { r.w[0] = ld_stream4(p); }
+  else { static_assert(B == 2, "raw vector of 2, 4, 8 or 16 bytes"); r.w[0] = ld_stream2(p); }
+  return r;
+}
+template <typename T, int V> __device__ __forceinline__ void unpack_raw(const RawVec<T, V>& r, float (&o)[V]) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) o[v] = __uint_as_float(r.w[v]);
+  } else if constexpr (V == 1) {
+    float hi;
+    unpack2<T>(r.w[0], o[0], hi);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v += 2) unpack2<T>(r.w[v / 2], o[v], o[v + 1]);
+  }
+}
+
 template <typename T, int V> __device__ __forceinline__ void store_vec(T* p, const float (&v)[V]) {
   if constexpr (sizeof(T) == 4) {
     if constexpr (V == 4) {

@@ -68,46 +68,48 @@ __global__ void __launch_bounds__(256) dice_sumsq_kernel(const DiceParams p) {
       float nl[V];
       {
         float lse[V];
-        load_vec<float, V>(p.lse + (size_t)n * HW + px0, lse);
+        load_px_f32<V>(p.lse + (size_t)n * HW + px0, lse);
 #pragma unroll
         for (int v = 0; v < V; ++v) nl[v] = -lse[v] * kLog2e;
       }
       const T* q = img + (size_t)c0 * HW + px0;
-      float za[CH][V], zb[CH][V];
-      auto load_chunk = [&](int k0, float (&z)[CH][V]) {
+      struct Chunk { RawVec<T, V> r[CH]; };
+      Chunk za, zb;
+      auto load_chunk = [&](int k0, Chunk& ck) {
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-          if (k0 + i < ncls_w) {
-            load_vec<T, V>(q, z[i]);
-          } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) z[i][v] = -1.0e30f;   // p = 0
-          }
+          if (k0 + i < ncls_w) ck.r[i] = load_raw<T, V>(q);
           q += HW;
+        }
+      };
+      auto consume = [&](int k0, const Chunk& ck, float (&a)[CH]) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          a[i] = 0.f;
+          if (k0 + i < ncls_w) {
+            float z[V];
+            unpack_raw<T, V>(ck.r[i], z);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float pr = ex2(fmaf(z[v], kLog2e, nl[v]));
+              a[i] += e2 ? pr * pr : (pr > 0.f ? __powf(pr, p.dice_exponent) : 0.f);
+            }
+          }
         }
       };
       load_chunk(0, za);
 #pragma unroll
       for (int k0 = 0; k0 < CW; k0 += 2 * CH) {
+        float a[CH];
         if (k0 + CH < CW) load_chunk(k0 + CH, zb);
+        consume(k0, za, a);
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            const float pr = ex2(fmaf(za[i][v], kLog2e, nl[v]));
-            acc[k0 + i] += e2 ? pr * pr : (pr > 0.f ? __powf(pr, p.dice_exponent) : 0.f);
-          }
-        }
+        for (int i = 0; i < CH; ++i) acc[k0 + i] += a[i];
         if (k0 + CH < CW) {
           if (k0 + 2 * CH < CW) load_chunk(k0 + 2 * CH, za);
+          consume(k0 + CH, zb, a);
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const float pr = ex2(fmaf(zb[i][v], kLog2e, nl[v]));
-              acc[k0 + CH + i] += e2 ? pr * pr : (pr > 0.f ? __powf(pr, p.dice_exponent) : 0.f);
-            }
-          }
+          for (int i = 0; i < CH; ++i) acc[k0 + CH + i] += a[i];
         }
       }
     }
@@ -157,20 +159,22 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
   load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
   const T* q = img + px0;
   for (int c0 = 0; c0 < C; c0 += CH) {
-    float z[CH][V];
+    RawVec<T, V> raw[CH];
     const int left = C - c0;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      if (i < left) load_vec<T, V>(q, z[i]);
+      if (i < left) raw[i] = load_raw<T, V>(q);
       q += HW;
     }
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       if (i < left) {
         const float b = beta_s[c0 + i];
+        float zz[V];
+        unpack_raw<T, V>(raw[i], zz);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const float pr = ex2(fmaf(z[i][v], kLog2e, nl[v]));
+          const float pr = ex2(fmaf(zz[v], kLog2e, nl[v]));
           if (e2) dot[v] = fmaf(b * pr, pr, dot[v]);
           else dot[v] += pr > 0.f ? b * __powf(pr, p.dice_exponent) : 0.f;
         }
@@ -260,21 +264,22 @@ __global__ void __launch_bounds__(256) dice_grad_kernel(const DiceParams p) {
   const T* q = img + px0;
   T* gq = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW + px0;
   for (int c0 = 0; c0 < C; c0 += CH) {
-    float z[CH][V];
+    RawVec<T, V> raw[CH];
     const int left = C - c0;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      if (i < left) load_vec<T, V>(q, z[i]);
+      if (i < left) raw[i] = load_raw<T, V>(q);
       q += HW;
     }
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       if (i < left) {
         const float b = beta_s[c0 + i];
-        float g[V];
+        float g[V], zz[V];
+        unpack_raw<T, V>(raw[i], zz);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const float pr = ex2(fmaf(z[i][v], kLog2e, nl[v]));
+          const float pr = ex2(fmaf(zz[v], kLog2e, nl[v]));
           float gd;
           if (e2) gd = b * pr;
           else gd = pr > 0.f ? b * __powf(pr, p.dice_exponent - 1.f) : 0.f;
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(256) dice_grad_kernel(const DiceParams p) {
 // ------------------------------------------------------------------------------------------------ host side
 template <typename T> static int dice_fwd_t(const DiceParams& p0, bool vec, cudaStream_t st) {
   DiceParams p = p0;
-  constexpr int VB = 8 / (int)sizeof(T);   // 8-byte loads: 256 B per warp per class row
+  constexpr int VB = 16 / (int)sizeof(T);  // 16-byte loads kept packed: 512 B per warp per class row
   constexpr int CW = 20;
   const int zb = (p.C + 8 * CW - 1) / (8 * CW);
   if (vec) {
@@ -317,10 +322,10 @@ template <typename T> static int dice_bwd_t(const DiceParams& p, bool vec, cudaS
   const size_t sm = (size_t)p.C * sizeof(float);
   if (vec) {
     dim3 grid((unsigned)((p.HW / VV + 255) / 256), p.N);
-    dice_dot_kernel<T, VV, (VV == 4 ? 8 : 4)><<<grid, 256, sm, st>>>(p);
+    dice_dot_kernel<T, VV, 8><<<grid, 256, sm, st>>>(p);
     count_launch();
     if (int e = check_launch("dice_dot_kernel")) return e;
-    dice_grad_kernel<T, VV, (VV == 4 ? 8 : 4)><<<grid, 256, sm, st>>>(p);
+    dice_grad_kernel<T, VV, 8><<<grid, 256, sm, st>>>(p);
   } else {
     dim3 grid((unsigned)((p.HW + 255) / 256), p.N);
     dice_dot_kernel<T, 1, 8><<<grid, 256, sm, st>>>(p);
@@ -346,7 +351,7 @@ int dice_stream_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   p.logits = d->logits; p.lse = d->lse; p.dice_part = d->dice_part;
   p.N = d->N; p.C = d->C; p.HW = (long long)d->H * d->W;
   p.dice_exponent = d->dice_exponent;
-  const int VB = 8 / logit_bytes(d->logit_dtype);
+  const int VB = 16 / logit_bytes(d->logit_dtype);
   const bool vec = (p.HW % VB == 0) && aligned16(d->logits) && aligned16(d->lse);
   switch (d->logit_dtype) {
     case B200SEG_F32: return dice_fwd_t<float>(p, vec, st);

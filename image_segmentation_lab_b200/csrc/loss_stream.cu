@@ -123,25 +123,34 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
     // chunk loader: CH classes x V pixels (streaming 128-bit loads; the resize-fused variant interpolates 4 taps)
     const T* cls_ptr = UP ? img : img + px0;   // running pointer over the class dimension (one 64-bit add per class)
     const long long cls_stride = UP ? hw : HW;
-    auto load_chunk = [&](int c0, float (&z)[CH][V]) {
+    // A chunk = CH classes x V pixels. Loads stay PACKED (RawVec) until they are reduced, so a bf16 thread keeps as
+    // many bytes in flight per register as an fp32 one; the resize-fused variant interpolates its 4 taps instead.
+    struct Chunk { RawVec<T, V> r[CH]; float f[UP ? CH : 1]; };
+    auto load_chunk = [&](int c0, Chunk& ck) {
       const int left = C - c0;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         if (i < left) {
-          if constexpr (UP) {
-            z[i][0] = interp<T>(cls_ptr, tp);
-          } else {
-            load_vec<T, V>(cls_ptr, z[i]);
-          }
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) z[i][v] = neg_inf();
+          if constexpr (UP) ck.f[i] = interp<T>(cls_ptr, tp);
+          else ck.r[i] = load_raw<T, V>(cls_ptr);
         }
         cls_ptr += cls_stride;
       }
     };
     // online soft-max update with one chunk (running max m, rescaled sum s, arg-max idx)
-    auto reduce_chunk = [&](int c0, const float (&z)[CH][V]) {
+    auto reduce_chunk = [&](int c0, const Chunk& ck) {
+      const int left = C - c0;
+      float z[CH][V];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (i < left) {
+          if constexpr (UP) z[i][0] = ck.f[i];
+          else unpack_raw<T, V>(ck.r[i], z[i]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) z[i][v] = neg_inf();
+        }
+      }
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         float cm = m[v];
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
       }
     };
     // double-buffered: the loads of chunk k+1 are in flight while chunk k is reduced
-    float za[CH][V], zb[CH][V];
+    Chunk za, zb;
     load_chunk(0, za);
     for (int c0 = 0; c0 < C; c0 += 2 * CH) {
       const bool has_b = c0 + CH < C;
@@ -334,20 +343,21 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
     T* gq = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW + px0;
     const T* q = img + px0;
     for (int c0 = 0; c0 < C; c0 += CH) {
-      float z[CH][V];
+      RawVec<T, V> raw[CH];
       const int left = C - c0;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        if (i < left) load_vec<T, V>(q, z[i]);
+        if (i < left) raw[i] = load_raw<T, V>(q);
         q += HW;
       }
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         if (i < left) {
-          float g[V];
+          float g[V], zz[V];
+          unpack_raw<T, V>(raw[i], zz);
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            g[v] = coef[v] * ex2(fmaf(z[i][v], kLog2e, nl[v]));
+            g[v] = coef[v] * ex2(fmaf(zz[v], kLog2e, nl[v]));
             if (c0 + i == yc[v]) g[v] -= coef[v];
           }
           store_vec<T, V>(gq, g);
@@ -436,7 +446,7 @@ template <typename T> static int launch_ce_fwd(const CeFwdParams& p, bool up, bo
     ce_fwd_kernel<T, 1, 4, true><<<grid, 256, sm, st>>>(p);
   } else if (vec) {
     dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
-    ce_fwd_kernel<T, VV, (VV == 4 ? 4 : 2), false><<<grid, 256, sm, st>>>(p);
+    ce_fwd_kernel<T, VV, 4, false><<<grid, 256, sm, st>>>(p);
   } else {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
     ce_fwd_kernel<T, 1, 8, false><<<grid, 256, sm, st>>>(p);
@@ -462,7 +472,7 @@ template <typename T> static int launch_ce_bwd(const CeBwdParams& p, bool up, bo
   }
   if (vec) {
     dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
-    ce_bwd_kernel<T, VV, (VV == 4 ? 8 : 4), false><<<grid, 256, 0, st>>>(p);
+    ce_bwd_kernel<T, VV, 8, false><<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
     ce_bwd_kernel<T, 1, 8, false><<<grid, 256, 0, st>>>(p);

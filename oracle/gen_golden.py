@@ -221,6 +221,46 @@ def build(out_dir=OUT_DIR):
     data['kat/out'] = np.array([l1(pr, tg).item(), l1(pr, tg, wt).item(), l1(pr, tg, wt, avg_factor=2).item()], dtype=np.float32)
     data['kat/none'] = l1(pr, tg, reduction='none').numpy()
 
+    # ---- sigmoid path: binary_cross_entropy + _expand_onehot_labels (cross_entropy_loss.py:77-164); appended last so
+    # that the fixtures above do not change. class_weight (pos_weight) only on 2-D predictions: on (N,C,H,W) inputs
+    # the reference's (C,) pos_weight broadcasts along W, not along the class dimension.
+    bce_cases = [
+        dict(name='bce_mean', shape=(2, 3, 8, 10), kw=dict()),
+        dict(name='bce_sum_w', shape=(2, 4, 6, 6), pixel_weight=True, kw=dict(reduction='sum')),
+        dict(name='bce_nonignore', shape=(2, 3, 8, 8), kw=dict(avg_non_ignore=True)),
+        dict(name='bce_none', shape=(1, 3, 6, 8), pixel_weight=True, kw=dict(reduction='none')),
+        dict(name='bce_single', shape=(2, 1, 8, 8), kw=dict()),
+        dict(name='bce_2d_posw', shape=(40, 5), kw=dict(class_weight=[0.5, 1.0, 2.0, 1.5, 3.0])),
+    ]
+    for case in bce_cases:
+        name, shape = case['name'], case['shape']
+        x = (torch.randn(shape, generator=g) * 2).requires_grad_(True)
+        if len(shape) == 4:
+            ncls = max(shape[1], 2)
+            y = torch.randint(0, ncls, (shape[0],) + shape[2:], generator=g)
+            y[torch.rand(y.shape, generator=g) < 0.15] = 255
+            w = torch.rand(y.shape, generator=g) + 0.5 if case.get('pixel_weight') else None
+        else:
+            y = torch.randint(0, shape[1], (shape[0],), generator=g)
+            y[::7] = 255
+            w = None
+        mod = ref.CrossEntropyLoss(use_sigmoid=True, loss_weight=0.7, **case['kw'])
+        loss = mod(x, y, weight=w, ignore_index=255)
+        if loss.dim():
+            go = torch.rand(loss.shape, generator=g)
+            (loss * go).sum().backward()
+            data[name + '/grad_out'] = go.numpy()
+        else:
+            loss.backward()
+        data[name + '/logits'] = x.detach().numpy()
+        data[name + '/labels'] = y.numpy()
+        if w is not None:
+            data[name + '/pixel_weight'] = w.numpy()
+        data[name + '/loss'] = loss.detach().numpy()
+        data[name + '/grad'] = x.grad.numpy()
+        manifest['cases'].append(dict(name=name, kind='bce', shape=shape, kw=case['kw'], loss_weight=0.7, ignore=255,
+                                      pixel_weight=bool(case.get('pixel_weight'))))
+
     os.makedirs(out_dir, exist_ok=True)
     np.savez_compressed(os.path.join(out_dir, 'hotpath_golden.npz'), **data)
     with open(os.path.join(out_dir, 'manifest.json'), 'w') as fh:

@@ -170,6 +170,43 @@ def test_golden_process_and_metrics(B, golden, capsys):
     assert torch.equal(ev2.area_totals('decode'), torch.from_numpy(data['process/areas'].astype(np.int64).sum(0)))
 
 
+def test_golden_sigmoid_bce(B, golden):
+    """CrossEntropyLoss(use_sigmoid=True): the shipped default config (configs/network/deeplabv3/*.py:30,41)."""
+    data, manifest = golden
+    for case in [c for c in manifest['cases'] if c['kind'] == 'bce']:
+        name, kw = case['name'], dict(case['kw'])
+        for dtype, ltol, gtol in ((torch.float32, LOSS_TOL, GRAD_TOL), (torch.bfloat16, HALF_TOL, 2 * HALF_TOL)):
+            x = torch.from_numpy(data[name + '/logits']).cuda().to(dtype).requires_grad_(True)
+            y = torch.from_numpy(data[name + '/labels']).cuda()
+            w = torch.from_numpy(data[name + '/pixel_weight']).cuda() if case['pixel_weight'] else None
+            mod = B.CrossEntropyLoss(use_sigmoid=True, loss_weight=case['loss_weight'], **kw)
+            loss = mod(x, y, weight=w, ignore_index=255)
+            go = torch.from_numpy(data[name + '/grad_out']).cuda() if loss.dim() else None
+            ((loss.float() * go).sum() if go is not None else loss).backward()
+            if dtype == torch.float32:
+                ref_loss, ref_grad = data[name + '/loss'], data[name + '/grad']
+            else:   # the oracle on the fp32 upcast of the same rounded logits
+                xo = x.detach().float().requires_grad_(True)
+                kwo = dict(kw)
+                if 'class_weight' in kwo:
+                    kwo['class_weight'] = xo.new_tensor(kwo['class_weight'])
+                lo = case['loss_weight'] * O.binary_cross_entropy(xo, y, w, ignore_index=255, **kwo)
+                ((lo * go).sum() if go is not None else lo).backward()
+                ref_loss, ref_grad = lo.detach(), xo.grad
+            assert loss.shape == tuple(np.shape(ref_loss)) and loss.dtype == dtype
+            assert rel_err(loss, ref_loss) <= ltol, '%s[%s] loss %.3e' % (name, dtype, rel_err(loss, ref_loss))
+            assert rel_err(x.grad, ref_grad) <= gtol, '%s[%s] grad %.3e' % (name, dtype, rel_err(x.grad, ref_grad))
+    # full Kvasir-like shape: 2 classes, 256x256 (BASELINE config 1 with the sigmoid loss), against the oracle on GPU
+    x = synth_logits((2, 2, 256, 256), 21, device='cuda').requires_grad_(True)
+    y = synth_labels((2, 256, 256), 2, 21, ignore_index=255, device='cuda')
+    loss = B.CrossEntropyLoss(use_sigmoid=True)(x, y, ignore_index=255)
+    loss.backward()
+    xo = x.detach().clone().requires_grad_(True)
+    lo = O.binary_cross_entropy(xo, y, ignore_index=255)
+    lo.backward()
+    assert rel_err(loss, lo) <= LOSS_TOL and rel_err(x.grad, xo.grad) <= GRAD_TOL
+
+
 # ------------------------------------------------------------------------------------------------ oracle, larger shapes
 def _head_case(B, shape, size, C, dtype, ce_kw, dice_kw, ac=False, ignore=255, seed=0, pixel_weight=False,
                loss_tol=LOSS_TOL, grad_tol=GRAD_TOL, single_pass=True, margin=True, loss_atol=0.0):

@@ -108,3 +108,24 @@ def test_total_area_to_metrics_nan_and_beta(golden):
             np.testing.assert_array_equal(v, data['metrics_%s/%s' % (tag, k)])
     with pytest.raises(KeyError):
         O.total_area_to_metrics(I, U, P, L, ['mAP'])
+
+
+def test_bce_cases(golden):
+    """Sigmoid path: oracle.binary_cross_entropy vs CrossEntropyLoss(use_sigmoid=True) of the reference."""
+    data, manifest = golden
+    cases = [c for c in manifest['cases'] if c['kind'] == 'bce']
+    assert len(cases) >= 6
+    for case in cases:
+        name, kw = case['name'], dict(case['kw'])
+        x = torch.from_numpy(data[name + '/logits']).requires_grad_(True)
+        y = torch.from_numpy(data[name + '/labels'])
+        w = torch.from_numpy(data[name + '/pixel_weight']) if case['pixel_weight'] else None
+        if 'class_weight' in kw:
+            kw['class_weight'] = x.new_tensor(kw['class_weight'])
+        loss = case['loss_weight'] * O.binary_cross_entropy(x, y, w, ignore_index=255, **kw)
+        if loss.dim():
+            (loss * torch.from_numpy(data[name + '/grad_out'])).sum().backward()
+        else:
+            loss.backward()
+        np.testing.assert_allclose(loss.detach().numpy(), data[name + '/loss'], err_msg=name, **RT)
+        np.testing.assert_allclose(x.grad.numpy(), data[name + '/grad'], err_msg=name, rtol=1e-5, atol=1e-8)
