@@ -224,7 +224,52 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
     const bool vec_ok = aligned16(im.pred) && aligned16(im.gt) && (!FROM_LOGITS || (im.n_pixels % V == 0));
     long long* pout = (FROM_LOGITS && p.pred_out) ? p.pred_out[img] : nullptr;
 
-    for (long long px = px_begin + (long long)threadIdx.x * V; px < px_end; px += (long long)THREADS * V) {
+    long long px_scalar_from = px_begin;
+    if constexpr (!FROM_LOGITS && PRIVATE) {
+      // Fast path (label maps: int64 predictions + float32 ground truth, the reference's dtypes): software-pipelined
+      // — the 6 x 128-bit loads of the NEXT iteration are issued before the current 8 pixels are decoded and counted.
+      if (vec_ok && p.pred_dtype == B200SEG_L_I64 && p.gt_dtype == B200SEG_L_F32) {
+        const long long span = (long long)THREADS * V;
+        const long long n_full = (px_end - px_begin) / span;       // iterations in which every thread has 8 pixels
+        const char* pb = reinterpret_cast<const char*>(im.pred);
+        const char* gb = reinterpret_cast<const char*>(im.gt);
+        unsigned int* mine = ctr.cnt + threadIdx.x;
+        uint4 pr[4], gr[2];
+        long long px = px_begin + (long long)threadIdx.x * V;
+        if (n_full > 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pr[k] = ld_stream16(pb + px * 8 + 16 * k);
+          gr[0] = ld_stream16(gb + px * 4);
+          gr[1] = ld_stream16(gb + px * 4 + 16);
+        }
+        for (long long itn = 0; itn < n_full; ++itn) {
+          uint4 pn[4], gn[2];
+          const long long pxn = px + span;
+          if (itn + 1 < n_full) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pn[k] = ld_stream16(pb + pxn * 8 + 16 * k);
+            gn[0] = ld_stream16(gb + pxn * 4);
+            gn[1] = ld_stream16(gb + pxn * 4 + 16);
+          }
+          const float gf[8] = {__uint_as_float(gr[0].x), __uint_as_float(gr[0].y), __uint_as_float(gr[0].z),
+                               __uint_as_float(gr[0].w), __uint_as_float(gr[1].x), __uint_as_float(gr[1].y),
+                               __uint_as_float(gr[1].z), __uint_as_float(gr[1].w)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ctr.update_private(mine, dpr.from_i64(pr[k].x, pr[k].y), dgt.from_f32(gf[2 * k]));
+            ctr.update_private(mine, dpr.from_i64(pr[k].z, pr[k].w), dgt.from_f32(gf[2 * k + 1]));
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pr[k] = pn[k];
+          gr[0] = gn[0];
+          gr[1] = gn[1];
+          px = pxn;
+        }
+        px_scalar_from = px_begin + n_full * span;   // the ragged remainder goes through the generic loop below
+      }
+    }
+
+    for (long long px = px_scalar_from + (long long)threadIdx.x * V; px < px_end; px += (long long)THREADS * V) {
       int gv[V], pv[V];
       const int nv = (px_end - px >= V) ? V : (int)(px_end - px);
       if (nv == V && vec_ok) {

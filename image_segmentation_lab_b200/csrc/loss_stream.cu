@@ -439,14 +439,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
 // host dispatch
 template <typename T> static int launch_ce_fwd(const CeFwdParams& p, bool up, bool vec, cudaStream_t st) {
   const long long HW = (long long)p.H * p.W;
-  constexpr int VV = 16 / (int)sizeof(T);
+  constexpr int VV = 4;   // 4 pixels per thread for every dtype: 16-byte (fp32) / 8-byte (16-bit) loads; 8 pixels of
+                          // per-thread soft-max state cost the 16-bit variant its occupancy (128 regs, 31 % of roofline)
   const size_t sm = p.dice_part ? (size_t)2 * 8 * p.C * sizeof(float) : 0;   // <= 32 KB for C <= 512
   if (up) {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
     ce_fwd_kernel<T, 1, 4, true><<<grid, 256, sm, st>>>(p);
   } else if (vec) {
     dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
-    ce_fwd_kernel<T, VV, 4, false><<<grid, 256, sm, st>>>(p);
+    ce_fwd_kernel<T, VV, (sizeof(T) == 2 ? 8 : 4), false><<<grid, 256, sm, st>>>(p);
   } else {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
     ce_fwd_kernel<T, 1, 8, false><<<grid, 256, sm, st>>>(p);
@@ -498,7 +499,7 @@ int ce_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   p.dice_ignore = d->dice_ignore_index;
   const bool up = (d->h != d->H) || (d->w != d->W);
   const long long HW = (long long)d->H * d->W;
-  const int VV = 16 / logit_bytes(d->logit_dtype);
+  const int VV = 4;
   const bool vec = !up && (HW % VV == 0) && aligned16(d->logits) && aligned16(d->labels) &&
                    (!p.pw || aligned16(p.pw)) && (!p.lse || aligned16(p.lse)) && (!p.loss_px || aligned16(p.loss_px));
   switch (d->logit_dtype) {
