@@ -19,7 +19,7 @@ WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -122,6 +122,7 @@ SYMBOLS = [
     ("b200seg_resize_nearest_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     ("b200seg_confusion_labels", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
     ("b200seg_confusion_logits", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p, _p]),
+    ("b200seg_confusion_logits_resized", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p, _p]),
     ("b200seg_confusion_chunk_pixels", _i32, []),
     ("b200seg_topk_counts", C.c_int,
      [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _i64, C.POINTER(_i32), _i32, _i32, _f, _p, _p]),

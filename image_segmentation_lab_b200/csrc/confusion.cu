@@ -352,6 +352,63 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Resize-fused variant: logits (C,h,w) are bilinearly interpolated to the ground-truth size (H,W) inside the
+// arg-max loop (decode_head.py:297-320 rescale + metrics.py:101-107 argmax), so the (1,C,H,W) rescaled logits are
+// never written. ATen's evaluation order h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11) in fp32.
+template <typename T, int THREADS, bool PRIVATE>
+__global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfParams p, const int align_corners) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Counters<THREADS, PRIVATE> ctr{reinterpret_cast<unsigned int*>(smem_raw), p.C};
+  ctr.zero();
+  __syncthreads();
+  const int C = p.C;
+  const long long per = (p.total_chunks + gridDim.x - 1) / gridDim.x;
+  long long chunk = (long long)blockIdx.x * per;
+  const long long chunk_end = (chunk + per < p.total_chunks) ? chunk + per : p.total_chunks;
+  if (chunk >= chunk_end) return;
+  int img = find_image(p.chunk_prefix, p.n_images, chunk);
+  ClassDecoder dgt;
+  dgt.init(p.gt_dtype, C, true, p.ignore);
+  const bool ac = align_corners != 0;
+  while (chunk < chunk_end) {
+    while (img + 1 < p.n_images && chunk >= p.chunk_prefix[img + 1]) ++img;
+    const b200seg_image im = p.images[img];
+    const long long img_chunk_end = p.chunk_prefix[img + 1] < chunk_end ? p.chunk_prefix[img + 1] : chunk_end;
+    const long long px_begin = (chunk - p.chunk_prefix[img]) * kChunk;
+    long long px_end = (img_chunk_end - p.chunk_prefix[img]) * kChunk;
+    if (px_end > im.n_pixels) px_end = im.n_pixels;
+    const float sh = resize_scale(im.h, im.H, ac), sw = resize_scale(im.w, im.W, ac);
+    const long long hw = (long long)im.h * im.w;
+    long long* pout = p.pred_out ? p.pred_out[img] : nullptr;
+    const T* base = reinterpret_cast<const T*>(im.pred);
+    for (long long px = px_begin + threadIdx.x; px < px_end; px += THREADS) {
+      const int gv = dgt.one(im.gt, (size_t)px);
+      const int Y = (int)(px / im.W), X = (int)(px - (long long)Y * im.W);
+      int y0, y1, x0, x1;
+      float ly, lx;
+      resize_src(sh, Y, im.h, ac, y0, y1, ly);
+      resize_src(sw, X, im.w, ac, x0, x1, lx);
+      const float h1 = ly, h0 = 1.f - ly, w1 = lx, w0 = 1.f - lx;
+      const int o00 = y0 * im.w + x0, o01 = y0 * im.w + x1, o10 = y1 * im.w + x0, o11 = y1 * im.w + x1;
+      float best = neg_inf();
+      int bi = 0;
+      const T* pl = base;
+      for (int c = 0; c < C; ++c) {
+        const float z = h0 * (w0 * to_float<T>(pl[o00]) + w1 * to_float<T>(pl[o01])) +
+                        h1 * (w0 * to_float<T>(pl[o10]) + w1 * to_float<T>(pl[o11]));
+        if (z > best) { best = z; bi = c; }   // lowest index wins ties
+        pl += hw;
+      }
+      if (pout) pout[px] = bi;
+      if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv);
+      else if (gv != kIgnored) ctr.update(bi, gv);
+    }
+    ctr.flush(p.areas + (size_t)img * 3 * C);
+    chunk = img_chunk_end;
+  }
+}
+
 // Persistent grid: exactly (SMs x resident CTAs per SM), so the static chunk partition has no tail wave.
 template <typename K> static int persistent_grid(K kernel, int threads, size_t smem, long long total_chunks, int* grid) {
   int per_sm = 0;
@@ -388,11 +445,50 @@ template <typename T, bool FROM_LOGITS> static int launch_confusion(const ConfPa
   return check_launch("confusion_kernel");
 }
 
+template <typename T> static int launch_confusion_resize(const ConfParams& p, int align_corners, cudaStream_t st) {
+  const size_t need256 = (size_t)3 * p.C * 256 * 4;
+  int grid = 1;
+  if (need256 <= 72 * 1024) {
+    auto k = confusion_resize_kernel<T, 256, true>;
+    static bool attr = false;
+    if (!attr) { B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); attr = true; }
+    if (int e = persistent_grid(k, 256, need256, p.total_chunks, &grid)) return e;
+    k<<<grid, 256, need256, st>>>(p, align_corners);
+  } else {
+    auto k = confusion_resize_kernel<T, 256, false>;
+    if (int e = persistent_grid(k, 256, (size_t)3 * p.C * 4, p.total_chunks, &grid)) return e;
+    k<<<grid, 256, (size_t)3 * p.C * 4, st>>>(p, align_corners);
+  }
+  count_launch();
+  return check_launch("confusion_resize_kernel");
+}
+
 }  // namespace b200seg
 
 using namespace b200seg;
 
 extern "C" int32_t b200seg_confusion_chunk_pixels(void) { return kChunk; }
+
+extern "C" int b200seg_confusion_logits_resized(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
+                                                int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype,
+                                                int32_t gt_dtype, int32_t C, int64_t ignore_index, int32_t align_corners,
+                                                int64_t* areas, int64_t* const* pred_out, void* stream) {
+  B200SEG_REQUIRE(chunk_pixels == kChunk, "confusion: chunk_pixels must be %d", kChunk);
+  B200SEG_REQUIRE(C >= 1 && C <= 4096, "confusion: num_classes %d out of range [1,4096]", C);
+  B200SEG_REQUIRE(n_images >= 0 && areas, "confusion: bad arguments");
+  if (n_images == 0 || total_chunks == 0) return 0;
+  B200SEG_REQUIRE(images && chunk_prefix, "confusion: NULL image table");
+  ConfParams p{images, (const long long*)chunk_prefix, n_images, total_chunks, 0, gt_dtype, C,
+               ignore_index, (long long*)areas, (long long* const*)pred_out};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (logit_dtype) {
+    case B200SEG_F32: return launch_confusion_resize<float>(p, align_corners, st);
+    case B200SEG_BF16: return launch_confusion_resize<__nv_bfloat16>(p, align_corners, st);
+    case B200SEG_F16: return launch_confusion_resize<__half>(p, align_corners, st);
+  }
+  set_error("confusion: unsupported logit dtype %d", logit_dtype);
+  return 1;
+}
 
 extern "C" int b200seg_confusion_labels(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                                         int64_t total_chunks, int32_t chunk_pixels, int32_t pred_dtype,

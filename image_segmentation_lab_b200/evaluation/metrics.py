@@ -42,13 +42,15 @@ def _common(tensors, device, allowed, fallback):
 
 
 def areas_device(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num_classes: int, ignore_index: int,
-                 from_logits: bool = False, pred_maps: Optional[list] = None) -> torch.Tensor:
+                 from_logits: bool = False, pred_maps: Optional[list] = None, align_corners: bool = False) -> torch.Tensor:
     """int64 (n_images, 3, C) device tensor [intersect, pred, label] for a list of images; no host sync.
 
     ``preds[i]`` is a label map (H_i,W_i) — or, with ``from_logits``, logits (1,C,H_i,W_i) / (C,H_i,W_i) whose
     arg-max over classes is taken in the same kernel (lowest index wins ties). ``gts[i]`` is (H_i,W_i) in
     any integer / float dtype (the reference's ``ori_gt`` is float32, core/dataset/kvasir_seg.py:37).
     ``pred_maps``: optional list that receives the int64 arg-max maps (logits mode only).
+    Logits whose spatial size differs from their ground truth are bilinearly resized to it (``align_corners``)
+    INSIDE the arg-max kernel — the rescale of decode_head.py:297-320 without materialising the (1,C,H,W) tensor.
     """
     assert len(preds) == len(gts)  # metrics.py:236
     lib = _lib.load()
@@ -66,13 +68,18 @@ def areas_device(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num
     chunk = lib.b200seg_confusion_chunk_pixels()
     table = np.zeros((n, 5), dtype=np.int64)
     prefix = np.zeros(n + 1, dtype=np.int64)
+    resized = False
     for i, (p, g) in enumerate(zip(preds_c, gts_c)):
         npx = g.numel()
         if from_logits:
             if p.dim() == 4:
                 assert p.size(0) == 1, 'each prediction must be (1,C,H,W)'
             assert p.shape[-3] == Cn, 'logits have %d classes, evaluator has %d' % (p.shape[-3], Cn)
-            assert p.shape[-2] * p.shape[-1] == npx, 'prediction / ground-truth size mismatch'
+            if tuple(p.shape[-2:]) != tuple(g.shape[-2:]):
+                assert g.dim() >= 2, 'a 2-D ground truth is needed to resize the logits to it'
+                resized = True
+            table[i, 3] = int(p.shape[-2]) | (int(p.shape[-1]) << 32)
+            table[i, 4] = int(g.shape[-2]) | (int(g.shape[-1]) << 32)
         else:
             assert p.numel() == npx, 'prediction / ground-truth size mismatch'
         table[i, 0] = p.data_ptr()
@@ -93,9 +100,14 @@ def areas_device(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num
                 ptrs = torch.tensor([m.data_ptr() for m in maps], dtype=torch.int64).to(dev, non_blocking=True)
                 pout_p = ptrs.data_ptr()
                 pred_maps.extend(maps)
-            _lib.check(lib.b200seg_confusion_logits(images_p, prefix_p, n, total_chunks, chunk, _lib.LOGIT_DTYPES[pdt],
-                                                    _lib.LABEL_DTYPES[gdt], Cn, int(ignore_index), areas.data_ptr(),
-                                                    pout_p, stream))
+            if resized:
+                _lib.check(lib.b200seg_confusion_logits_resized(
+                    images_p, prefix_p, n, total_chunks, chunk, _lib.LOGIT_DTYPES[pdt], _lib.LABEL_DTYPES[gdt], Cn,
+                    int(ignore_index), int(bool(align_corners)), areas.data_ptr(), pout_p, stream))
+            else:
+                _lib.check(lib.b200seg_confusion_logits(images_p, prefix_p, n, total_chunks, chunk, _lib.LOGIT_DTYPES[pdt],
+                                                        _lib.LABEL_DTYPES[gdt], Cn, int(ignore_index), areas.data_ptr(),
+                                                        pout_p, stream))
         else:
             _lib.check(lib.b200seg_confusion_labels(images_p, prefix_p, n, total_chunks, chunk, _lib.LABEL_DTYPES[pdt],
                                                     _lib.LABEL_DTYPES[gdt], Cn, int(ignore_index), areas.data_ptr(),
@@ -127,6 +139,7 @@ class SegEvaluator():
                  prefix: Optional[str] = None,
                  exact_totals: bool = True,
                  keep_pred_maps: bool = False,
+                 align_corners: bool = False,
                  **kwargs) -> None:
         self.epoch = epoch
         self.num_classes = num_classes
@@ -145,6 +158,7 @@ class SegEvaluator():
         self.format_only = format_only
         self.exact_totals = exact_totals
         self.keep_pred_maps = keep_pred_maps
+        self.align_corners = align_corners   # used when logits arrive at a lower resolution than the ground truth
         self._results = dict()   # key -> [[I...],[U...],[P...],[L...]] float32 CPU tensors (reference layout)
         self._pending = dict()   # key -> list of int64 (n,4,C) device tensors not yet read back
         self._exact = dict()     # key -> int64 (4,C) CPU running totals
@@ -204,7 +218,7 @@ class SegEvaluator():
             preds = [value[i] for i in range(len(value))]
             maps = [] if self.keep_pred_maps else None
             areas = areas_device(preds, list(labels_batch), self.num_classes, self.ignore_index, from_logits=True,
-                                 pred_maps=maps)
+                                 pred_maps=maps, align_corners=self.align_corners)
             if maps is not None and isinstance(value, list):
                 for i, m in enumerate(maps):
                     value[i] = m  # the reference replaces the logits by the label maps in place (:107)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 6
+#define B200SEG_ABI_VERSION 7
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -250,6 +250,13 @@ int b200seg_confusion_logits(const b200seg_image* images, const int64_t* chunk_p
                              int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype, int32_t gt_dtype,
                              int32_t C, int64_t ignore_index, int64_t* areas, int64_t* const* pred_out,
                              void* stream);
+/* Same, with the bilinear resize of low-resolution logits (C,h,w) to the ground-truth size (H,W) fused into the
+ * arg-max (decode_head.py:297-320 + metrics.py:101-107): image.h/w = logit size, image.H/W = ground-truth size,
+ * image.n_pixels = H*W. The rescaled logits are never materialised.                                            */
+int b200seg_confusion_logits_resized(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
+                                     int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype, int32_t gt_dtype,
+                                     int32_t C, int64_t ignore_index, int32_t align_corners, int64_t* areas,
+                                     int64_t* const* pred_out, void* stream);
 int32_t b200seg_confusion_chunk_pixels(void);
 
 /* top-k accuracy counts (models/losses/accuracy.py:6-61) for arbitrary k and thresh:

@@ -509,3 +509,31 @@ def test_ce_properties_full_size(B):
     assert float(g[(y == 255).unsqueeze(1).expand_as(g)].abs().max()) == 0.0
     parts = sum(ce(x[i:i + 2], y[i:i + 2], ignore_index=255) for i in range(0, 8, 2))
     assert rel_err(parts, l) <= 1e-6
+
+
+@pytest.mark.parametrize('ac', [False, True])
+def test_areas_from_lowres_logits_resize_fused(B, ac):
+    """validation rescale + arg-max + areas in one kernel — low-resolution logits against full-resolution
+    ground truth, never materialising the (1,C,H,W) rescaled logits (decode_head.py:297-320 + metrics.py:101-107)."""
+    C = 19
+    cases = [((1, C, 64, 128), (512, 1024)), ((1, C, 32, 32), (256, 256)), ((1, C, 37, 53), (111, 160)), ((1, C, 9, 7), (9, 7))]
+    logits = [synth_logits(s, 80 + i, device='cuda') for i, (s, _) in enumerate(cases)]
+    gts = [synth_labels((1,) + g, C, 80 + i, ignore_index=255)[0].float().cuda() for i, (_, g) in enumerate(cases)]
+    maps = []
+    got = B.areas_device(logits, gts, C, 255, from_logits=True, align_corners=ac, pred_maps=maps)
+    preds = [O.argmax_labels(O.resize(l, size=tuple(g.shape), mode='bilinear', align_corners=ac)) for l, g in zip(logits, gts)]
+    want = _areas_oracle_gpu(preds, gts, C, 255)
+    for i, (p_, m_) in enumerate(zip(preds, maps)):
+        mism = int((p_ != m_).sum())
+        # power-of-two ratios with 2^-6-quantised logits interpolate exactly: bit-exact; general ratios may differ from
+        # ATen by an fp32 rounding at exact class cross-overs
+        if i < 2 and not ac or i == 3:
+            assert mism == 0, (i, mism)
+        else:
+            assert mism <= max(2, int(2e-4 * p_.numel())), (i, mism)
+    assert torch.equal(got[0], want[0]) or ac
+    assert int((got - want).abs().sum()) <= 8 * sum(max(2, int(2e-4 * p_.numel())) for p_ in preds)
+    ev = B.SegEvaluator(epoch=0, num_classes=C, class_names=['c%d' % i for i in range(C)], palette=None, ignore_index=255,
+                        show_result=False, align_corners=ac)
+    ev.process(0, {'decode': [l.clone() for l in logits]}, {'ori_gt': gts})
+    assert torch.equal(ev.area_totals('decode')[[0, 2, 3]], got.sum(0).cpu())
