@@ -12,7 +12,8 @@ _EPS = float(torch.finfo(torch.float32).eps)
 
 class _BceFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, label, weight, pos_weight, reduction, avg_factor, ignore_index, avg_non_ignore, single):
+    def forward(ctx, pred, label, weight, pos_weight, reduction, avg_factor, ignore_index, avg_non_ignore, single,
+                grad_enabled=True):
         lib = _lib.load()
         _lib.require_cuda(pred, 'pred')
         if pred.dtype not in _lib.LOGIT_DTYPES:
@@ -30,7 +31,7 @@ class _BceFunction(torch.autograd.Function):
         if weight is not None:
             w = weight.to(device=dev, dtype=torch.float32).contiguous()
             assert w.numel() == N * HW, 'weight must have one entry per pixel'
-        needs_grad = bool(ctx.needs_input_grad[0])
+        needs_grad = bool(ctx.needs_input_grad[0]) and bool(grad_enabled)
         use_nvalid = bool(reduction == 'mean' and avg_factor is None and avg_non_ignore)
         n_elem = max(N * Cc * HW, 1)
         scale = 1.0
@@ -100,7 +101,7 @@ class _BceFunction(torch.autograd.Function):
             d.grad_logits = grad.data_ptr()
             d.stats = stats.data_ptr()
             _lib.check(lib.b200seg_bce_bwd(C.byref(d), _lib.stream_ptr(dev)))
-        return grad, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None
 
 
 def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=None, class_weight=None,
@@ -119,7 +120,7 @@ def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=
         # element-wise targets: treat every element as its own pixel of a 1-channel prediction
         shape = pred.shape
         out = _BceFunction.apply(pred.reshape(-1, 1, 1), label.reshape(-1, 1), None if weight is None else weight.reshape(-1, 1),
-                                 None, reduction, avg_factor, ignore_index, avg_non_ignore, True)
+                                 None, reduction, avg_factor, ignore_index, avg_non_ignore, True, torch.is_grad_enabled())
         return out.reshape(shape) if reduction == 'none' else out
     else:
         assert (pred.dim() == 2 and label.dim() == 1) or (pred.dim() == 4 and label.dim() == 3), \
@@ -130,7 +131,8 @@ def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=
         pos_w = torch.as_tensor(class_weight, dtype=torch.float32, device=pred.device).contiguous()
         if single and pos_w.numel() != 1:
             pos_w = pos_w.reshape(-1)[:1].contiguous() if pos_w.numel() == 1 else pos_w
-    out = _BceFunction.apply(x, label, weight, pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, single)
+    out = _BceFunction.apply(x, label, weight, pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, single,
+                             torch.is_grad_enabled())
     if reduction == 'none':
         out = out.reshape(pred.shape)
         if single:

@@ -72,7 +72,7 @@ class FusedLossFunction(torch.autograd.Function):
     payload of the single per-step all-reduce under data parallelism (distributed.py)."""
 
     @staticmethod
-    def forward(ctx, logits, labels, pixel_weight, spec):
+    def forward(ctx, logits, labels, pixel_weight, spec, grad_enabled=True):
         lib = _lib.load()
         _lib.require_cuda(logits, "logits")
         if logits.dtype not in _lib.LOGIT_DTYPES:
@@ -99,7 +99,7 @@ class FusedLossFunction(torch.autograd.Function):
             assert pw.dim() == 3 and tuple(pw.shape) == tuple(labels.shape), \
                 "weight must have the shape of the per-pixel loss (models/losses/utils.py:62-64)"
             pw = pw.to(device=dev, dtype=torch.float32).contiguous()
-        needs_grad = bool(ctx.needs_input_grad[0])
+        needs_grad = bool(ctx.needs_input_grad[0]) and bool(grad_enabled)   # needs_input_grad ignores no_grad()
         stream = _lib.stream_ptr(dev)
 
         with torch.cuda.device(dev):
@@ -244,7 +244,7 @@ class FusedLossFunction(torch.autograd.Function):
                 _lib.check(lib.b200seg_loss_fused_combine(
                     pb.data_ptr(), out.data_ptr(), _lib.LOGIT_DTYPES[logits.dtype], N, Cc, h, w,
                     C.c_float(ctx.ce_scale), gs.data_ptr(), int(ctx.use_nvalid), stats_p, stream))
-                return out, None, None, None
+                return out, None, None, None, None
             if ctx.plan == "flat_single":
                 if ctx.consumed:
                     raise RuntimeError("the single-pass loss graph can be back-propagated once; build the loss with "
@@ -253,7 +253,7 @@ class FusedLossFunction(torch.autograd.Function):
                 gs = scalar(g_ce)
                 _lib.check(lib.b200seg_scale_inplace(grad.data_ptr(), _lib.LOGIT_DTYPES[grad.dtype], grad.numel(),
                                                      gs.data_ptr(), stream))
-                return grad, None, None, None
+                return grad, None, None, None, None
 
             bd = _lib.LossBwdDesc()
             bd.logits = logits.data_ptr(); bd.labels = labels.data_ptr()
@@ -276,7 +276,7 @@ class FusedLossFunction(torch.autograd.Function):
             bd.flags = (_lib.WANT_CE if want_ce else 0) | (_lib.WANT_DICE if want_dice else 0)
             out = torch.empty_like(logits)
             if not (want_ce or want_dice):
-                return out.zero_(), None, None, None
+                return out.zero_(), None, None, None, None
             if want_ce:
                 bd.ce_use_nvalid = int(ctx.use_nvalid)
                 if ctx.ce_none:
@@ -304,11 +304,11 @@ class FusedLossFunction(torch.autograd.Function):
                 keep.append(dot)
                 bd.scratch_px = dot.data_ptr()
             _lib.check(lib.b200seg_loss_bwd(C.byref(bd), stream))
-        return out, None, None, None
+        return out, None, None, None, None
 
 
 def run_fused(logits, labels, pixel_weight, spec, with_log=False):
-    loss_ce, loss_dice, acc, log_vec = FusedLossFunction.apply(logits, labels, pixel_weight, spec)
+    loss_ce, loss_dice, acc, log_vec = FusedLossFunction.apply(logits, labels, pixel_weight, spec, torch.is_grad_enabled())
     if with_log:
         return loss_ce, loss_dice, acc, log_vec
     return loss_ce, loss_dice, acc
