@@ -155,8 +155,6 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
 #pragma unroll
     for (int v = 0; v < V; ++v) { nl[v] = -lse[v] * kLog2e; dot[v] = 0.f; }
   }
-  long long y[V];
-  load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
   const T* q = img + px0;
   for (int c0 = 0; c0 < C; c0 += CH) {
     RawVec<T, V> raw[CH];
@@ -181,6 +179,8 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
       }
     }
   }
+  long long y[V];   // only needed for the one-hot term: loaded after the class loop to keep 2*V registers free in it
+  load_labels<V>(p.labels, p.label_dtype, (size_t)n * HW + px0, y);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const long long yy = y[v];

@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
     const long long cls_stride = UP ? hw : HW;
     // A chunk = CH classes x V pixels. Loads stay PACKED (RawVec) until they are reduced, so a bf16 thread keeps as
     // many bytes in flight per register as an fp32 one; the resize-fused variant interpolates its 4 taps instead.
+    // Full chunks run predicate-free; the C % CH tail classes take the predicated flavour once.
     struct Chunk { RawVec<T, V> r[CH]; float f[UP ? CH : 1]; };
-    auto load_chunk = [&](int c0, Chunk& ck) {
-      const int left = C - c0;
+    auto load_chunk = [&](Chunk& ck, int left) {   // left >= CH for a full chunk
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         if (i < left) {
@@ -138,12 +138,11 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
       }
     };
     // online soft-max update with one chunk (running max m, rescaled sum s, arg-max idx)
-    auto reduce_chunk = [&](int c0, const Chunk& ck) {
-      const int left = C - c0;
+    auto reduce_chunk = [&](int c0, const Chunk& ck, int left, bool full) {
       float z[CH][V];
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        if (i < left) {
+        if (full || i < left) {
           if constexpr (UP) z[i][0] = ck.f[i];
           else unpack_raw<T, V>(ck.r[i], z[i]);
         } else {
@@ -153,29 +152,46 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
       }
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        float cm = m[v];
+        // chunk max by a select-free tree, then its (lowest) index by equality selects: no predicate chains
+        float cm = z[0][v];
+#pragma unroll
+        for (int i = 1; i < CH; ++i) cm = fmaxf(cm, z[i][v]);
+        int li = CH - 1;
+#pragma unroll
+        for (int i = CH - 2; i >= 0; --i) li = (z[i][v] == cm) ? i : li;
+        const bool up_max = cm > m[v];                       // strict '>': an earlier class keeps a tie
+        idx[v] = up_max ? c0 + li : idx[v];
+        const float nmx = up_max ? cm : m[v];
+        const float nm = -nmx * kLog2e;
+        float acc0 = s[v] * ex2(fmaf(m[v], kLog2e, nm)), acc1 = 0.f;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-          if (z[i][v] > cm) { cm = z[i][v]; idx[v] = c0 + i; }  // strict '>' keeps the lowest index
+          const float e = ex2(fmaf(z[i][v], kLog2e, nm));
+          if (i & 1) acc1 += e;
+          else acc0 += e;
         }
-        const float nm = -cm * kLog2e;
-        float acc = s[v] * ex2(fmaf(m[v], kLog2e, nm));
-#pragma unroll
-        for (int i = 0; i < CH; ++i) acc += ex2(fmaf(z[i][v], kLog2e, nm));
-        s[v] = acc;
-        m[v] = cm;
+        s[v] = acc0 + acc1;
+        m[v] = nmx;
       }
     };
-    // double-buffered: the loads of chunk k+1 are in flight while chunk k is reduced
-    Chunk za, zb;
-    load_chunk(0, za);
-    for (int c0 = 0; c0 < C; c0 += 2 * CH) {
-      const bool has_b = c0 + CH < C;
-      if (has_b) load_chunk(c0 + CH, zb);
-      reduce_chunk(c0, za);
-      if (has_b) {
-        if (c0 + 2 * CH < C) load_chunk(c0 + 2 * CH, za);
-        reduce_chunk(c0 + CH, zb);
+    // double-buffered over the full chunks: the loads of chunk k+1 are in flight while chunk k is reduced
+    {
+      const int nfull = C / CH;
+      Chunk za, zb;
+      if (nfull > 0) load_chunk(za, CH);
+      for (int k = 0; k < nfull; k += 2) {
+        const bool has_b = k + 1 < nfull;
+        if (has_b) load_chunk(zb, CH);
+        reduce_chunk(k * CH, za, CH, true);
+        if (has_b) {
+          if (k + 2 < nfull) load_chunk(za, CH);
+          reduce_chunk((k + 1) * CH, zb, CH, true);
+        }
+      }
+      const int tail = C - nfull * CH;
+      if (tail > 0) {
+        load_chunk(za, tail);
+        reduce_chunk(nfull * CH, za, tail, false);
       }
     }
 
