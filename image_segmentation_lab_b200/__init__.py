@@ -8,6 +8,7 @@ HanHan-TR/Image_Segmentation_lab as hand-written sm_100a CUDA behind the referen
     SegEvaluator                          core/evaluation/metrics.py
     fused_resize_losses, B200DecodeHeadLossMixin   models/decode_heads/decode_head.py:261-321 (fused)
     registry.install(LOSS)                registry/register.py, models/builder.py:40,262-283
+    parse_losses                          utils/train_utils.py:31-74 (one all-reduce + one D2H per step)
 
 Everything computes in libb200seg.so (include/b200seg.h); there is no CPU or PyTorch fallback.
 """
@@ -18,6 +19,7 @@ from .fused import B200DecodeHeadLossMixin, fused_resize_losses
 from .losses import (Accuracy, CrossEntropyLoss, DiceLoss, accuracy, cross_entropy, dice_loss, get_class_weight,
                      reduce_loss, weight_reduce_loss, weighted_loss)
 from .ops import Upsample, add_prefix, resize
+from .train_utils import parse_losses
 
 __version__ = '0.1.0'
 
@@ -25,5 +27,5 @@ __all__ = [
     'resize', 'Upsample', 'add_prefix', 'CrossEntropyLoss', 'cross_entropy', 'DiceLoss', 'dice_loss', 'accuracy',
     'Accuracy', 'SegEvaluator', 'areas_device', 'fused_resize_losses', 'B200DecodeHeadLossMixin', 'registry',
     'distributed', 'get_class_weight', 'reduce_loss', 'weight_reduce_loss', 'weighted_loss', 'load_library',
-    'lib_path', 'launch_count',
+    'lib_path', 'launch_count', 'parse_losses',
 ]

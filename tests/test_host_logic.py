@@ -2,6 +2,7 @@
 packed all-reduce (gloo, world_size 2), and the loud failure on non-CUDA inputs (there is no CPU fallback)."""
 import os
 import warnings
+from collections import OrderedDict
 
 import numpy as np
 import pytest
@@ -169,6 +170,9 @@ def _worker(rank, world, port, q):
         ok = ok and abs(rv[0].item() - 30.0) < 1e-12 and rv[5].item() == 256 and rc.item() == 7 and rc.dtype == torch.int64
         loss, acc = D.global_loss_scalars(rv)
         ok = ok and abs(loss.item() - 30.0 / 256) < 1e-7
+        # parse_losses: one all-reduce for every logged variable, rank-mean as the reference (train_utils.py:69-72)
+        _, lv = B.parse_losses({'loss_ce': torch.tensor(1.0 + rank), 'acc_seg': torch.tensor([10.0 * rank])})
+        ok = ok and abs(lv['loss_ce'] - 1.5) < 1e-6 and abs(lv['acc_seg'] - 5.0) < 1e-6 and abs(lv['loss'] - 1.5) < 1e-6
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -185,6 +189,24 @@ def test_packed_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_parse_losses_matches_reference_layout():
+    """utils/train_utils.py:31-74: keys containing 'loss' are summed into the graph; everything is logged as floats."""
+    a = torch.tensor(1.5, requires_grad=True)
+    b = torch.tensor([0.25, 0.75], requires_grad=True)
+    losses = OrderedDict([('decode.loss_ce', a * 2), ('decode.acc_seg', torch.tensor([87.5])),
+                          ('aux.loss_ce', [b[0] * 1.0, b[1] * 1.0]), ('_stats', torch.zeros(8))])
+    loss, log_vars = B.parse_losses(losses)
+    assert list(log_vars.keys()) == ['decode.loss_ce', 'decode.acc_seg', 'aux.loss_ce', 'loss']
+    assert abs(log_vars['loss'] - 4.0) < 1e-6 and abs(log_vars['decode.acc_seg'] - 87.5) < 1e-6
+    assert all(isinstance(v, float) for v in log_vars.values())
+    loss.backward()
+    assert float(a.grad) == 2.0 and b.grad.tolist() == [1.0, 1.0]
+    _, lazy = B.parse_losses(OrderedDict([('loss_x', torch.tensor(2.0))]), lazy=True)
+    assert isinstance(lazy['loss'], torch.Tensor) and float(lazy['loss']) == 2.0
+    with pytest.raises(TypeError):
+        B.parse_losses({'loss_bad': 1.0})
 
 
 def test_packed_allreduce_single_process_is_identity():
