@@ -47,8 +47,15 @@ struct UpParams {
   long long acc_ignore;
 };
 
+// Shared-memory layout of one CTA (floats):
+//   raw   [CPT][2][kPatchStride]   the two clamped low-res tap rows of the band (classes >= C padded very negative)
+//   vpat  [CPT][kVStride]          vertically interpolated taps V[c][row i][col k] = a + ly_i (b - a), index i*ncol + k
+//   mrow  [kVStride]               max over classes of V[.][i][k]: an upper bound of every interpolated logit
+//   stage [CPT][256] float2        (GRAD) per-thread horizontal corner sums; aliases raw
+constexpr int kVStride = 264;      // >= S * (RT + 1) for S in {4,8,16,32}: 260, 136, 80, 64
+
 template <typename T, int CPT, bool GRAD>
-__global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(const UpParams p) {
+__global__ void __launch_bounds__(256, 3) up_fused_kernel(const UpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float lam_y[32];  // cell-relative vertical weight of each row of the band (-1: row outside the image)
   const int C = p.C, S = p.S, NG = p.NG, GPR = p.GPR, RT = p.RT;
@@ -57,8 +64,12 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
   const int r_first = tile * RT;
   const int ncol = RT + 1;
 
-  float* patch = reinterpret_cast<float*>(smem_raw);                                  // [CPT][2][kPatchStride]
-  float2* stage = reinterpret_cast<float2*>(patch + CPT * 2 * kPatchStride);          // [CPT][256]
+  // raw is dead once vpat is built, so it shares its space with stage (first used after the next barrier)
+  constexpr int kUnionFloats = (GRAD && CPT * 512 > CPT * 2 * kPatchStride) ? CPT * 512 : CPT * 2 * kPatchStride;
+  float* raw = reinterpret_cast<float*>(smem_raw);
+  float2* stage = reinterpret_cast<float2*>(smem_raw);
+  float* vpat = raw + kUnionFloats;
+  float* mrow = vpat + CPT * kVStride;
 
   // ---- stage the two low-res tap rows of this band (clamped) as fp32; classes >= C are padded very negative
   {
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
           col = col < 0 ? 0 : (col > p.w - 1 ? p.w - 1 : col);
           v = to_float<T>(img[((size_t)c * p.h + (rr ? yb : ya)) * p.w + col]);
         }
-        patch[(c * 2 + rr) * kPatchStride + k] = v;
+        raw[(c * 2 + rr) * kPatchStride + k] = v;
       }
     }
     if (tid < S) {
@@ -87,6 +98,21 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
     }
   }
   __syncthreads();
+  // ---- vertical interpolation once per (row, column, class) for the whole CTA, and the per-(row, column) class max
+  for (int e = tid; e < S * ncol; e += 256) {
+    const int i = e / ncol, k = e - i * ncol;
+    const float l = lam_y[i] < 0.f ? 0.f : lam_y[i];
+    float mx = kPadLogit;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const float a = raw[(c * 2 + 0) * kPatchStride + k], bb = raw[(c * 2 + 1) * kPatchStride + k];
+      const float v = fmaf(l, bb - a, a);
+      vpat[c * kVStride + e] = v;
+      mx = fmaxf(mx, v);
+    }
+    mrow[e] = mx;
+  }
+  __syncthreads();
 
   const int i = tid >> p.logNG;  // row within the band
   const int ul = tid & (NG - 1); // group within the tile
@@ -96,7 +122,6 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
   const int r = u >> p.logGPR;
   const bool row_ok = (Y >= 0 && Y < p.H);
   const bool any_ok = row_ok && r <= p.w && X0 + 3 >= 0 && X0 < p.W;
-  const float ly = row_ok ? lam_y[i] : 0.f;
 
   float loss_acc = 0.f;
   int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
@@ -141,39 +166,44 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
       }
     }
 
-    float e[CPT][4];
-    float m[4];
+    // ---- pass 1: interpolated logits, arg-max, and sum of exponentials against the reference M >= every logit of
+    // these 4 pixels (class max of the two tap columns: a logit is a convex combination of its taps)
+    const float* pv = vpat + i * ncol + (r - r_first);
+    const float M = fmaxf(mrow[i * ncol + (r - r_first)], mrow[i * ncol + (r - r_first) + 1]);
+    const float nM = -M * kLog2e;
+    float m[4], s[4];
     int idx[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { m[j] = neg_inf(); idx[j] = 0; }
-    const float* pc = patch + (r - r_first);
+    for (int j = 0; j < 4; ++j) { m[j] = neg_inf(); idx[j] = 0; s[j] = 0.f; }
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-      const float a0 = pc[(c * 2 + 0) * kPatchStride], a1 = pc[(c * 2 + 0) * kPatchStride + 1];
-      const float b0 = pc[(c * 2 + 1) * kPatchStride], b1 = pc[(c * 2 + 1) * kPatchStride + 1];
-      const float va = fmaf(ly, b0 - a0, a0);
-      const float vb = fmaf(ly, b1 - a1, a1);
+      const float va = pv[c * kVStride], vb = pv[c * kVStride + 1];
       const float d = vb - va;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float z = fmaf(lx[j], d, va);
-        e[c][j] = z;
         if (z > m[j]) { m[j] = z; idx[j] = c; }   // strict '>' keeps the lowest index
+        s[j] += ex2(fmaf(z, kLog2e, nM));
       }
     }
-    float s[4];
+    // re-reference the sums to each pixel's own max (s >= 1 afterwards). If a pixel sits more than ~80 below the tile
+    // bound its sum underflowed: redo that (rare) pixel exactly against its own max.
+    bool redo = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float nm = -m[j] * kLog2e;
-      float acc0 = 0.f, acc1 = 0.f;   // two chains: more ILP for the 4 warps per scheduler
+    for (int j = 0; j < 4; ++j) redo |= !(s[j] > 1e-30f);
+    if (redo) {
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        e[c][j] = ex2(fmaf(e[c][j], kLog2e, nm));
-        if (c & 1) acc1 += e[c][j];
-        else acc0 += e[c][j];
+      for (int j = 0; j < 4; ++j) s[j] = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float va = pv[c * kVStride], vb = pv[c * kVStride + 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += ex2((fmaf(lx[j], vb - va, va) - m[j]) * kLog2e);
       }
-      s[j] = acc0 + acc1;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] *= ex2((M - m[j]) * kLog2e);
     }
+
     float coef[4];
     int ycl[4];
 #pragma unroll
@@ -185,10 +215,8 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
         n_bad += (yc == -1);
         n_valid += (yc != -2);
         if (yc >= 0) {
-          const float* py = pc + yc * (2 * kPatchStride);
-          const float a0 = py[0], a1 = py[1], b0 = py[kPatchStride], b1 = py[kPatchStride + 1];
-          const float va = fmaf(ly, b0 - a0, a0), vb = fmaf(ly, b1 - a1, a1);
-          const float zy = fmaf(lx[j], vb - va, va);   // same operation order as the class loop: bitwise equal
+          const float va = pv[yc * kVStride], vb = pv[yc * kVStride + 1];
+          const float zy = fmaf(lx[j], vb - va, va);   // same operations as the class loop: bitwise equal
           float wt = p.cw ? __ldg(p.cw + yc) : 1.f;
           if (p.pw) wt *= __ldg(p.pw + lbase + X0 + j);
           loss_acc = fmaf(wt, m[j] + fast_log(s[j]) - zy, loss_acc);
@@ -200,16 +228,19 @@ __global__ void __launch_bounds__(256, (CPT <= 20 ? 2 : 1)) up_fused_kernel(cons
       }
     }
     if constexpr (GRAD) {
-      float rj[4];
+      // ---- pass 2: the exponentials are recomputed (not kept: 80 registers), now against each pixel's own max
+      float rj[4], nm[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rj[j] = coef[j] * fast_rcp(s[j]);
+      for (int j = 0; j < 4; ++j) { rj[j] = coef[j] * fast_rcp(s[j]); nm[j] = -m[j] * kLog2e; }
       float2* st = stage + tid;   // i * NG + ul == tid
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
+        const float va = pv[c * kVStride], vb = pv[c * kVStride + 1];
+        const float d = vb - va;
         float gs = 0.f, gb = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float g = rj[j] * e[c][j];
+          const float g = rj[j] * ex2(fmaf(fmaf(lx[j], d, va), kLog2e, nm[j]));
           gs += g;
           gb = fmaf(lx[j], g, gb);
         }
@@ -314,8 +345,8 @@ long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {
 }
 
 template <typename T, int CPT, bool GRAD> static int launch_up(const UpParams& p, cudaStream_t st) {
-  size_t smem = (size_t)CPT * 2 * kPatchStride * 4;
-  if (GRAD) smem += (size_t)CPT * 256 * sizeof(float2);
+  const size_t uni = (GRAD && CPT * 512 > CPT * 2 * kPatchStride) ? (size_t)CPT * 512 : (size_t)CPT * 2 * kPatchStride;
+  const size_t smem = (uni + (size_t)CPT * kVStride + kVStride) * 4;
   auto k = up_fused_kernel<T, CPT, GRAD>;
   static bool attr = false;
   if (!attr) {
