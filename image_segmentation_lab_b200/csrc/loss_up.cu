@@ -27,6 +27,10 @@ namespace b200seg {
 
 constexpr int kPatchStride = 68;   // floats per patch row (>= runs per tile + 1 = 65 at S = 4)
 constexpr float kPadLogit = -1.0e30f;
+#ifndef B200SEG_UP_MINBLOCKS
+#define B200SEG_UP_MINBLOCKS 4
+#endif
+constexpr int kUpMinBlocks = B200SEG_UP_MINBLOCKS;   // resident CTAs per SM the S >= 8 variant is compiled for
 
 struct UpParams {
   const void* logits;
@@ -52,10 +56,11 @@ struct UpParams {
 //   vpat  [CPT][kVStride]          vertically interpolated taps V[c][row i][col k] = a + ly_i (b - a), index i*ncol + k
 //   mrow  [kVStride]               max over classes of V[.][i][k]: an upper bound of every interpolated logit
 //   stage [CPT][256] float2        (GRAD) per-thread horizontal corner sums; aliases raw
-constexpr int kVStride = 264;      // >= S * (RT + 1) for S in {4,8,16,32}: 260, 136, 80, 64
+// VS = floats per class of vpat: >= S * (RT + 1), i.e. 260 at S = 4 and 136 / 80 / 64 at S = 8 / 16 / 32
 
-template <typename T, int CPT, bool GRAD>
-__global__ void __launch_bounds__(256, 3) up_fused_kernel(const UpParams p) {
+template <typename T, int CPT, bool GRAD, int VS, int MINB>
+__global__ void __launch_bounds__(256, MINB) up_fused_kernel(const UpParams p) {
+  constexpr int kVStride = VS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float lam_y[32];  // cell-relative vertical weight of each row of the band (-1: row outside the image)
   const int C = p.C, S = p.S, NG = p.NG, GPR = p.GPR, RT = p.RT;
@@ -344,10 +349,12 @@ long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {
   return (long long)N * C * (h + 1) * (w + 1) * 4 * (long long)sizeof(float);
 }
 
-template <typename T, int CPT, bool GRAD> static int launch_up(const UpParams& p, cudaStream_t st) {
+template <typename T, int CPT, bool GRAD, int VS> static int launch_up_vs(const UpParams& p, cudaStream_t st) {
+  constexpr int kVStride = VS;
+  constexpr int MINB = (VS <= 136 && CPT <= 24) ? kUpMinBlocks : 3;
   const size_t uni = (GRAD && CPT * 512 > CPT * 2 * kPatchStride) ? (size_t)CPT * 512 : (size_t)CPT * 2 * kPatchStride;
   const size_t smem = (uni + (size_t)CPT * kVStride + kVStride) * 4;
-  auto k = up_fused_kernel<T, CPT, GRAD>;
+  auto k = up_fused_kernel<T, CPT, GRAD, VS, MINB>;
   static bool attr = false;
   if (!attr) {
     B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -358,6 +365,10 @@ template <typename T, int CPT, bool GRAD> static int launch_up(const UpParams& p
   k<<<grid, 256, smem, st>>>(p);
   count_launch();
   return check_launch("up_fused_kernel");
+}
+
+template <typename T, int CPT, bool GRAD> static int launch_up(const UpParams& p, cudaStream_t st) {
+  return p.S == 4 ? launch_up_vs<T, CPT, GRAD, 264>(p, st) : launch_up_vs<T, CPT, GRAD, 136>(p, st);
 }
 
 template <typename T, bool GRAD> static int pick_up(const UpParams& p, cudaStream_t st) {
