@@ -261,6 +261,26 @@ def build(out_dir=OUT_DIR):
         manifest['cases'].append(dict(name=name, kind='bce', shape=shape, kw=case['kw'], loss_weight=0.7, ignore=255,
                                       pixel_weight=bool(case.get('pixel_weight'))))
 
+    # ---- TverskyLoss (models/losses/tversky_loss.py:24-148); appended last
+    tv_cases = [
+        dict(name='tversky_basic', shape=(2, 4, 8, 8), kw=dict()),
+        dict(name='tversky_weighted', shape=(3, 5, 6, 10), kw=dict(class_weight=[0.5, 1, 1.5, 2, 2.5], loss_weight=2.0, smooth=0.5,
+                                                                   alpha=0.4, beta=0.6)),
+        dict(name='tversky_ignore_in_range', shape=(2, 4, 8, 8), kw=dict(ignore_index=1), ignore=1, ignore_frac=0.0),
+        dict(name='tversky_c40', shape=(2, 40, 4, 8), kw=dict()),
+    ]
+    for case in tv_cases:
+        name, shape = case['name'], case['shape']
+        x = (torch.randn(shape, generator=g) * 2).requires_grad_(True)
+        y = _labels(g, shape[0], shape[2], shape[3], shape[1], case.get('ignore', 255), case.get('ignore_frac', 0.1))
+        loss = ref.TverskyLoss(**case['kw'])(x, y)
+        loss.backward()
+        data[name + '/logits'] = x.detach().numpy()
+        data[name + '/labels'] = y.numpy()
+        data[name + '/loss'] = loss.detach().numpy()
+        data[name + '/grad'] = x.grad.numpy()
+        manifest['cases'].append(dict(name=name, kind='tversky', shape=shape, kw=case['kw']))
+
     os.makedirs(out_dir, exist_ok=True)
     np.savez_compressed(os.path.join(out_dir, 'hotpath_golden.npz'), **data)
     with open(os.path.join(out_dir, 'manifest.json'), 'w') as fh:

@@ -78,6 +78,7 @@ def load():
         lutils = _load('models.losses.utils', 'models/losses/utils.py')
         ce = _load('_ref_cross_entropy_loss', 'models/losses/cross_entropy_loss.py')
         dice = _load('_ref_dice_loss', 'models/losses/dice_loss.py')
+        tv = _load('_ref_tversky_loss', 'models/losses/tversky_loss.py')
         acc = _load('_ref_accuracy', 'models/losses/accuracy.py')
         met = _load('_ref_metrics', 'core/evaluation/metrics.py')
     finally:
@@ -90,7 +91,7 @@ def load():
         resize=ops.resize, Upsample=ops.Upsample, add_prefix=ops.add_prefix,
         reduce_loss=lutils.reduce_loss, weight_reduce_loss=lutils.weight_reduce_loss, weighted_loss=lutils.weighted_loss,
         cross_entropy=ce.cross_entropy, binary_cross_entropy=ce.binary_cross_entropy, CrossEntropyLoss=ce.CrossEntropyLoss,
-        DiceLoss=dice.DiceLoss, accuracy=acc.accuracy, Accuracy=acc.Accuracy, SegEvaluator=met.SegEvaluator)
+        DiceLoss=dice.DiceLoss, TverskyLoss=tv.TverskyLoss, accuracy=acc.accuracy, Accuracy=acc.Accuracy, SegEvaluator=met.SegEvaluator)
     _CACHE = ns
     return ns
 

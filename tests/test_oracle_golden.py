@@ -129,3 +129,18 @@ def test_bce_cases(golden):
             loss.backward()
         np.testing.assert_allclose(loss.detach().numpy(), data[name + '/loss'], err_msg=name, **RT)
         np.testing.assert_allclose(x.grad.numpy(), data[name + '/grad'], err_msg=name, rtol=1e-5, atol=1e-8)
+
+
+def test_tversky_cases(golden):
+    """TverskyLoss (models/losses/tversky_loss.py:24-148): oracle.tversky_loss_module vs the reference's fixtures."""
+    data, manifest = golden
+    cases = [c for c in manifest['cases'] if c['kind'] == 'tversky']
+    assert len(cases) >= 4
+    for case in cases:
+        name = case['name']
+        x = torch.from_numpy(data[name + '/logits']).requires_grad_(True)
+        y = torch.from_numpy(data[name + '/labels'])
+        loss = O.tversky_loss_module(x, y, **case['kw'])
+        loss.backward()
+        np.testing.assert_allclose(loss.detach().numpy(), data[name + '/loss'], err_msg=name, **RT)
+        np.testing.assert_allclose(x.grad.numpy(), data[name + '/grad'], err_msg=name, rtol=1e-5, atol=1e-8)
