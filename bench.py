@@ -13,7 +13,7 @@ one all-reduce of the 8-double statistics vector per step on a side stream.
                 timed with CUDA events on the launching stream, max over ranks.
   e2e           the same step through the public API with HOST inputs: pinned H2D of logits + labels every step,
                 fused_resize_losses + backward, D2H read of the loss.
-  roofline      the dominant kernel (up_fused_kernel) timed alone with CUDA events: algorithmic bytes / time vs the
+  roofline      the dominant kernel (up_cell_kernel) timed alone with CUDA events: algorithmic bytes / time vs the
                 measured HBM copy peak (MEASURED_PEAKS.json).
   cpu_baseline  the oracle (the reference's ATen chain restated, oracle/oracle.py) on the host cores, bounded sample.
   workloads     extra single-GPU results for BASELINE configs 3, 4 and 5 (HBM-bound shapes), each with its roofline.
@@ -399,7 +399,7 @@ def b200_main(args):
 
 
 def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind):
-    """up_fused_kernel alone: b200seg_loss_fused_fwdbwd(defer_combine=1) = one 64-byte memset + the kernel."""
+    """up_cell_kernel alone: b200seg_loss_fused_fwdbwd(defer_combine=1) launches exactly that kernel."""
     import ctypes as C
     dev = xs[0].device
     R = len(xs)
@@ -437,16 +437,16 @@ def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
     traffic, warp_inst = None, None
     try:   # DRAM bytes / executed warp instructions per launch of the same kernel and shape, from the committed ncu capture
         with open(os.path.join(ROOT, 'profiles', 'traffic_r1.json')) as fh:
-            k = json.load(fh)['kernels']['up_fused_kernel<float, 20, 1>']
+            k = json.load(fh)['kernels']['up_cell_kernel<float, 5, 1, 64, 6, 0>']
         traffic, warp_inst = k['dram_bytes'], k['warp_inst']
     except Exception:
         pass
-    out = {'bound': 'hbm', 'kernel': 'up_fused_kernel<float,20,true>', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-           'frac': achieved / peak, 'traffic': traffic, 'peak_kind': peak_kind, 'ms_per_launch': ms,
+    out = {'bound': 'hbm', 'kernel': 'up_cell_kernel<float,CPT=5,GRAD,64 threads,int64 labels>', 'achieved': achieved, 'peak': peak,
+           'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_kind': peak_kind, 'ms_per_launch': ms,
            'algorithmic_bytes_per_launch': algo,
-           'note': 'instruction-issue bound (C exps + ~25 C FP32/ALU instructions per output pixel), not HBM: the only '
-                   'full-resolution tensor touched is the label map; see DESIGN.md. The HBM-bound kernels of the path are '
-                   'reported under workloads'}
+           'note': 'not HBM bound: with the logits at 1/8 resolution the only full-resolution tensor touched is the label map '
+                   '(33.6 of the 43.5 MB), while every output pixel owes C exponentials (MUFU) and ~11 issue slots per class; '
+                   'see issue_roofline and DESIGN.md. The HBM-bound kernels of the path are reported under workloads'}
     if warp_inst:
         sm_clock = 1.965e9
         issue_peak = 148 * 4 * sm_clock          # warp instructions / s: 4 schedulers x 148 SMs at clocks.max.sm

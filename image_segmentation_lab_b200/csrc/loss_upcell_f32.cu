@@ -1,0 +1,6 @@
+// Resize-fused cell-owner CE kernels, float logits (see loss_upcell.cuh); one translation unit per dtype to compile in parallel.
+#include "loss_upcell.cuh"
+
+namespace b200seg {
+template int upcell_run<float>(const b200seg_loss_desc*, float*, int, bool, cudaStream_t);
+}

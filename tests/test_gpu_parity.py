@@ -249,6 +249,23 @@ def test_config2_variants(B):
     _head_case(B, (2, 19, 64, 128), (512, 1024), 19, torch.bfloat16, {}, None, loss_tol=HALF_TOL, grad_tol=2 * HALF_TOL)
 
 
+
+def test_resize_fused_extreme_logits_and_small_shapes(B):
+    """Resize-fused single pass: steep logits (a pixel's classes all far below its row's upper bound -> the exact
+    per-pixel-max redo path), every label dtype's edge handling on tiny and odd low-res extents, S in {4, 8, 16, 32}."""
+    for S, (h, w), C, n in ((8, (5, 7), 19, 2), (4, (3, 9), 5, 3), (16, (2, 3), 21, 2), (32, (1, 2), 32, 1), (8, (1, 1), 3, 2),
+                             (8, (9, 4), 2, 2), (4, (6, 6), 13, 1)):
+        for scale in (1.0, 60.0):
+            g = torch.Generator().manual_seed(S * 100 + C)
+            x = (torch.randn((n, C, h, w), generator=g) * 3.0 * scale).cuda()
+            labels = synth_labels((n, h * S, w * S), C, S + C, ignore_index=255, block=3, device='cuda')
+            case = dict(kind='ce', size=(h * S, w * S), ac=False, ignore=255, kw=dict(class_weight=[0.5 + 0.1 * i for i in range(C)]))
+            out = loss_case_cuda(case, x, labels, None)
+            ref = loss_case_oracle(case, x, labels, None)
+            _check(out, ref, 'S%d C%d %dx%d x%g' % (S, C, h, w, scale), loss_tol=2e-5 if scale > 1 else LOSS_TOL, acc_tol=0.05,
+                   loss_atol=0.0)
+
+
 def test_config3_ade20k_shape(B):
     """BASELINE config 3 (batch reduced to 2 for the oracle's 150-iteration Python loop): 150 classes, 512x512, bf16,
     class-weighted CE + Dice(loss_weight=3)."""
