@@ -16,10 +16,11 @@ _LIB = None
 F32, BF16, F16 = 0, 1, 2
 L_U8, L_I16, L_I32, L_I64, L_F32, L_F64 = 0, 1, 2, 3, 4, 5
 WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
+MODE_DICE, MODE_TVERSKY = 0, 1
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -38,7 +39,7 @@ class LossDesc(C.Structure):
         ("N", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("align_corners", C.c_int32), ("flags", C.c_int32),
         ("ignore_index", C.c_int64),
-        ("acc_has_ignore", C.c_int32), ("reserved0", C.c_int32),
+        ("acc_has_ignore", C.c_int32), ("dice_mode", C.c_int32),
         ("acc_ignore_index", C.c_int64),
         ("dice_ignore_index", C.c_int64),
         ("dice_exponent", C.c_float), ("reserved1", C.c_float),
@@ -60,6 +61,7 @@ class FinalizeDesc(C.Structure):
         ("dice_smooth", C.c_float), ("dice_reduction", C.c_int32),
         ("dice_ignore_index", C.c_int64),
         ("out", C.c_void_p), ("dice_coef", C.c_void_p), ("log_vec", C.c_void_p),
+        ("dice_mode", C.c_int32), ("tversky_alpha", C.c_float), ("tversky_beta", C.c_float), ("reserved0", C.c_int32),
     ]
 
 
@@ -73,7 +75,7 @@ class LossBwdDesc(C.Structure):
         ("ignore_index", C.c_int64), ("dice_ignore_index", C.c_int64),
         ("dice_exponent", C.c_float), ("ce_scale_host", C.c_float),
         ("ce_grad_out", C.c_void_p), ("ce_grad_px", C.c_void_p), ("stats", C.c_void_p),
-        ("ce_use_nvalid", C.c_int32), ("reserved0", C.c_int32),
+        ("ce_use_nvalid", C.c_int32), ("dice_mode", C.c_int32),
         ("dice_coef", C.c_void_p), ("dice_grad_out", C.c_void_p),
         ("grad_logits", C.c_void_p), ("grad_accum", C.c_void_p), ("scratch_px", C.c_void_p),
     ]

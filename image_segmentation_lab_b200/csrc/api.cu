@@ -115,7 +115,15 @@ extern "C" int b200seg_loss_fwd(const b200seg_loss_desc* d, void* stream) {
   if (d->N == 0) return 0;
   B200SEG_REQUIRE(d->logits && d->labels, "loss_fwd: NULL logits/labels");
   // Dice: <= 32 classes fit one warp's register tile (single read); more classes take the streaming kernels
-  if (d->flags & B200SEG_WANT_DICE) return d->C <= 32 ? tile_fwd_dispatch(d, st) : dice_stream_fwd_dispatch(d, st);
+  if (d->flags & B200SEG_WANT_DICE) {
+    if (d->dice_mode == B200SEG_MODE_TVERSKY) {   // masked sums, exponent 1: the streaming kernels for every C
+      B200SEG_REQUIRE(d->dice_exponent == 1.f, "loss_fwd: Tversky mode needs dice_exponent == 1");
+      B200SEG_REQUIRE(d->h == d->H && d->w == d->W, "loss_fwd: Tversky needs logits at label resolution (resize first)");
+      return dice_stream_fwd_dispatch(d, st);
+    }
+    B200SEG_REQUIRE(d->dice_mode == B200SEG_MODE_DICE, "loss_fwd: unknown dice_mode %d", d->dice_mode);
+    return d->C <= 32 ? tile_fwd_dispatch(d, st) : dice_stream_fwd_dispatch(d, st);
+  }
   return ce_fwd_dispatch(d, st);
 }
 
@@ -135,7 +143,10 @@ extern "C" int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream) {
   B200SEG_REQUIRE(d->logits && d->labels && d->lse && d->grad_logits, "loss_bwd: NULL tensor");
   B200SEG_REQUIRE(!d->ce_use_nvalid || d->stats, "loss_bwd: ce_use_nvalid without stats");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->flags & B200SEG_WANT_DICE) return d->C <= 32 ? tile_bwd_dispatch(d, st) : dice_stream_bwd_dispatch(d, st);
+  if (d->flags & B200SEG_WANT_DICE) {
+    if (d->dice_mode == B200SEG_MODE_TVERSKY) return dice_stream_bwd_dispatch(d, st);
+    return d->C <= 32 ? tile_bwd_dispatch(d, st) : dice_stream_bwd_dispatch(d, st);
+  }
   B200SEG_REQUIRE(d->flags & B200SEG_WANT_CE, "loss_bwd: nothing requested");
   return ce_bwd_dispatch(d, st);
 }

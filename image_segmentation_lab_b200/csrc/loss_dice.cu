@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) dice_sumsq_kernel(const DiceParams p) {
   const long long HW = p.HW;
   const int c0 = (blockIdx.z * 8 + warp) * CW;          // first class of this warp
   const int ncls_w = C - c0 < CW ? C - c0 : CW;         // may be <= 0
-  const bool e2 = (p.dice_exponent == 2.f);
+  const bool e2 = (p.dice_exponent == 2.f), e1 = (p.dice_exponent == 1.f);
   const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * HW;
 
   float acc[CW];
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) dice_sumsq_kernel(const DiceParams p) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
               const float pr = ex2(fmaf(z[v], kLog2e, nl[v]));
-              a[i] += e2 ? pr * pr : (pr > 0.f ? __powf(pr, p.dice_exponent) : 0.f);
+              a[i] += e2 ? pr * pr : (e1 ? pr : (pr > 0.f ? __powf(pr, p.dice_exponent) : 0.f));
             }
           }
         }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
   __syncthreads();
   const long long px0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (px0 >= HW) return;
-  const bool e2 = (p.dice_exponent == 2.f);
+  const bool e2 = (p.dice_exponent == 2.f), e1 = (p.dice_exponent == 1.f);
   const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * HW;
   float nl[V], dot[V];
   {
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
         for (int v = 0; v < V; ++v) {
           const float pr = ex2(fmaf(zz[v], kLog2e, nl[v]));
           if (e2) dot[v] = fmaf(b * pr, pr, dot[v]);
+          else if (e1) dot[v] = fmaf(b, pr, dot[v]);
           else dot[v] += pr > 0.f ? b * __powf(pr, p.dice_exponent) : 0.f;
         }
       }
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) dice_grad_kernel(const DiceParams p) {
   __syncthreads();
   const long long px0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (px0 >= HW) return;
-  const bool e2 = (p.dice_exponent == 2.f);
+  const bool e2 = (p.dice_exponent == 2.f), e1 = (p.dice_exponent == 1.f);
   const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;
   float Gce = 0.f;
   if (want_ce) {
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(256) dice_grad_kernel(const DiceParams p) {
           const float pr = ex2(fmaf(zz[v], kLog2e, nl[v]));
           float gd;
           if (e2) gd = b * pr;
+          else if (e1) gd = b;
           else gd = pr > 0.f ? b * __powf(pr, p.dice_exponent - 1.f) : 0.f;
           float gv = pr * (gd + sub[v]);
           if (c0 + i == ycl[v]) gv -= fmaf(pr, da[v], kk[v]);

@@ -36,6 +36,7 @@ struct CeFwdParams {
   float sh, sw;
   double* dice_part;        // (N,C,3) or NULL: also accumulate the one-hot Dice sums [sum p_y*valid, -, count]
   long long dice_ignore;
+  int tversky;              // B200SEG_MODE_TVERSKY: count only valid pixels, store lse = +inf for ignored ones
 };
 
 template <int V> __device__ __forceinline__ void load_f32(const float* p, float (&o)[V]) {
@@ -222,8 +223,9 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
           l = wt * (lse[v] - zy) * pwv[v];
         }
         if (dice) {
-          ycl[v] = (int)ycc;
-          pyv[v] = (yy != p.dice_ignore) ? ex2((zy - lse[v]) * kLog2e) : 0.f;   // valid_mask
+          const bool dv = (yy != p.dice_ignore);                                 // valid_mask
+          ycl[v] = (p.tversky && !dv) ? -1 : (int)ycc;                           // Tversky counts sum t*v, Dice sum t
+          pyv[v] = dv ? ex2((zy - lse[v]) * kLog2e) : 0.f;
         }
       }
       lpx[v] = l * p.lw;
@@ -231,6 +233,10 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
       const bool av = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
       n_acc += av;
       n_correct += (av && (long long)idx[v] == yy);
+    }
+    if (p.tversky) {   // every later pass forms p = exp(z - lse): +inf masks the ignored pixels out of all of them
+#pragma unroll
+      for (int v = 0; v < V; ++v) lse[v] = (y[v] == p.dice_ignore) ? __int_as_float(0x7f800000) : lse[v];
     }
     if (p.lse) store_f32<V>(p.lse + (size_t)n * HW + px0, lse);
     if (p.loss_px) store_f32<V>(p.loss_px + (size_t)n * HW + px0, lpx);
@@ -434,6 +440,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
     const double A = d.dice_part[(size_t)i * 3 + 0], B = d.dice_part[(size_t)i * 3 + 1], T = d.dice_part[(size_t)i * 3 + 2];
     const double cwv = d.dice_class_weight ? (double)d.dice_class_weight[c] : 1.0;
     const bool skip = ((long long)c == d.dice_ignore_index);
+    if (d.dice_mode == B200SEG_MODE_TVERSKY) {
+      // tversky_loss.py:52-68: TP = A, FP = B - A, FN = T - A; 1 - (TP + s) / (TP + a FP + b FN + s)
+      const double ta = (double)d.tversky_alpha, tb = (double)d.tversky_beta, sm = (double)d.dice_smooth;
+      const double num = A + sm;
+      const double den = (1.0 - ta - tb) * A + ta * B + tb * T + sm;
+      if (!skip) part += cwv * (1.0 - num / den);
+      if (d.dice_coef) {   // alpha = -dL/dA, beta = dL/dB (exponent 1)
+        d.dice_coef[(size_t)i * 2 + 0] = skip ? 0.f : (float)(K * cwv * (1.0 / den - num * (1.0 - ta - tb) / (den * den)));
+        d.dice_coef[(size_t)i * 2 + 1] = skip ? 0.f : (float)(K * cwv * num * ta / (den * den));
+      }
+      continue;
+    }
     const double num = 2.0 * A + (double)d.dice_smooth;
     const double den = B + T + (double)d.dice_smooth;
     if (!skip) part += cwv * (1.0 - num / den);
@@ -513,6 +531,7 @@ int ce_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   p.sw = resize_scale(d->w, d->W, d->align_corners != 0);
   p.dice_part = (d->flags & B200SEG_WANT_DICE) ? d->dice_part : nullptr;
   p.dice_ignore = d->dice_ignore_index;
+  p.tversky = (d->flags & B200SEG_WANT_DICE) && d->dice_mode == B200SEG_MODE_TVERSKY;
   const bool up = (d->h != d->H) || (d->w != d->W);
   const long long HW = (long long)d->H * d->W;
   const int VV = 4;

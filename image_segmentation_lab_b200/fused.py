@@ -12,6 +12,7 @@ from .losses._function import LossSpec, run_fused
 from .losses.accuracy import accuracy
 from .losses.cross_entropy_loss import CrossEntropyLoss, _match_dtype
 from .losses.dice_loss import DiceLoss
+from .losses.tversky_loss import TverskyLoss
 from .ops import resize
 
 
@@ -27,6 +28,7 @@ def _merge_spec(ce, dice, device, seg_weight, ignore_index, align_corners, want_
         spec.want_dice = True
         spec.dice_reduction, spec.dice_class_weight, spec.dice_loss_weight = s.dice_reduction, s.dice_class_weight, s.dice_loss_weight
         spec.dice_ignore_index, spec.dice_smooth, spec.dice_exponent = s.dice_ignore_index, s.dice_smooth, s.dice_exponent
+        spec.dice_mode, spec.tversky_alpha, spec.tversky_beta = s.dice_mode, s.tversky_alpha, s.tversky_beta
     return spec
 
 
@@ -35,7 +37,7 @@ def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False
     """{loss_name: loss, ..., 'acc_seg': (1,) tensor} for low- or full-resolution ``seg_logit``.
 
     ``losses_decode`` is a loss module or a list / ModuleList of them (this package's CrossEntropyLoss and
-    DiceLoss are fused into a single kernel launch; any other nn.Module loss is called on the materialised
+    DiceLoss / TverskyLoss are fused into a single kernel launch; any other nn.Module loss is called on the materialised
     resize). Same-named losses are summed, as decode_head.py:283-293 does. ``return_stats`` adds the float64
     statistics vector of the fused launch under '_stats' (see distributed.py).
     """
@@ -51,6 +53,10 @@ def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False
         if type(m) is CrossEntropyLoss and not m.use_sigmoid and fused_ce is None and m.reduction != 'none':
             fused_ce = m
         elif type(m) is DiceLoss and fused_dice is None:
+            fused_dice = m
+        elif type(m) is TverskyLoss and fused_dice is None and (fused_ce is None or m.ignore_index == ignore_index):
+            # Tversky masks its ignored pixels through the saved lse; it shares the launch with CE only when both ignore
+            # the same label, otherwise it runs as its own (still fused forward/backward) call below
             fused_dice = m
         else:
             others.append(m)

@@ -43,6 +43,10 @@ class LossSpec:
     dice_smooth: float = 1.0
     dice_exponent: float = 2.0
     dice_avg_factor: Optional[float] = None
+    # tversky (models/losses/tversky_loss.py:24-148) shares the dice slot: masked sums, exponent 1
+    dice_mode: str = "dice"
+    tversky_alpha: float = 0.3
+    tversky_beta: float = 0.7
     # accuracy (models/losses/accuracy.py:6-61, top-1)
     want_acc: bool = False
     acc_ignore_index: Optional[int] = None
@@ -135,7 +139,10 @@ class FusedLossFunction(torch.autograd.Function):
             fd.acc_has_ignore = int(spec.acc_ignore_index is not None)
             fd.acc_ignore_index = _none_int(spec.acc_ignore_index, 0)
             fd.dice_ignore_index = _none_int(spec.dice_ignore_index, -(2 ** 62))
-            fd.dice_exponent = float(spec.dice_exponent)
+            tversky = spec.want_dice and spec.dice_mode == "tversky"
+            stream_dice = spec.want_dice and (Cc > 32 or tversky)   # the streaming Dice kernels read lse back
+            fd.dice_exponent = 1.0 if tversky else float(spec.dice_exponent)
+            fd.dice_mode = _lib.MODE_TVERSKY if tversky else _lib.MODE_DICE
             fd.ce_loss_weight = float(spec.ce_loss_weight)
             fd.stats = stats_p
             fd.dice_part = part_p if spec.want_dice else None
@@ -156,7 +163,7 @@ class FusedLossFunction(torch.autograd.Function):
                     loss_px = torch.empty((N, H, W), dtype=torch.float32, device=dev)
                     flags |= _lib.WANT_LOSS_PX
                     fd.loss_px = loss_px.data_ptr()
-                if needs_grad or (spec.want_dice and Cc > 32):   # the streaming Dice kernels read lse back
+                if needs_grad or stream_dice:
                     lse = torch.empty((N, H, W), dtype=torch.float32, device=dev)
                     flags |= _lib.WANT_LSE
                     fd.lse = lse.data_ptr()
@@ -196,6 +203,9 @@ class FusedLossFunction(torch.autograd.Function):
             fin.dice_smooth = float(spec.dice_smooth)
             fin.dice_reduction = _lib.REDUCTIONS[spec.dice_reduction]
             fin.dice_ignore_index = fd.dice_ignore_index
+            fin.dice_mode = fd.dice_mode
+            fin.tversky_alpha = float(spec.tversky_alpha)
+            fin.tversky_beta = float(spec.tversky_beta)
             fin.out = out_p
             fin.dice_coef = coef_p if (spec.want_dice and needs_grad) else None
             fin.log_vec = log_p
@@ -265,7 +275,9 @@ class FusedLossFunction(torch.autograd.Function):
             bd.align_corners = int(bool(spec.align_corners))
             bd.ignore_index = int(spec.ce_ignore_index)
             bd.dice_ignore_index = _none_int(spec.dice_ignore_index, -(2 ** 62))
-            bd.dice_exponent = float(spec.dice_exponent)
+            tversky = spec.want_dice and spec.dice_mode == "tversky"
+            bd.dice_exponent = 1.0 if tversky else float(spec.dice_exponent)
+            bd.dice_mode = _lib.MODE_TVERSKY if tversky else _lib.MODE_DICE
             bd.stats = stats_p
             keep = []
             want_ce = spec.want_ce and g_ce is not None
@@ -299,7 +311,7 @@ class FusedLossFunction(torch.autograd.Function):
                 acc = torch.empty(logits.shape, dtype=torch.float32, device=dev)
                 keep.append(acc)
                 bd.grad_accum = acc.data_ptr()
-            if want_dice and Cc > 32:
+            if want_dice and (Cc > 32 or tversky):
                 dot = torch.empty((N, H, W), dtype=torch.float32, device=dev)
                 keep.append(dot)
                 bd.scratch_px = dot.data_ptr()

@@ -12,6 +12,7 @@
  *                                      cross_entropy       models/losses/cross_entropy_loss.py:23-74
  *                                      weight_reduce_loss  models/losses/utils.py:48-80
  *                                      DiceLoss.forward    models/losses/dice_loss.py:103-134 (+ :23-58)
+ *                                      TverskyLoss.forward models/losses/tversky_loss.py:112-134 (+ :24-68)
  *                                      accuracy (top-1)    models/losses/accuracy.py:6-61
  *   b200seg_loss_fused_fwdbwd        the same chain plus its autograd backward in one pass
  *   b200seg_confusion_labels         SegEvaluator.intersect_and_union core/evaluation/metrics.py:210-270
@@ -35,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 7
+#define B200SEG_ABI_VERSION 8
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -69,6 +70,13 @@ enum { B200SEG_LOG_CE_SUM = 0, B200SEG_LOG_N_VALID = 1, B200SEG_LOG_N_CORRECT = 
        B200SEG_LOG_N_BAD = 4, B200SEG_LOG_N_PIXELS = 5, B200SEG_LOG_DICE_SUM = 6, B200SEG_LOG_N_IMAGES = 7,
        B200SEG_LOG_WORDS = 8 };
 
+/* which overlap loss the B200SEG_WANT_DICE sums serve (dice_mode)
+ *   DICE   : [sum p*t*v, sum p^e (unmasked), sum t (unmasked, labels clamped)]   models/losses/dice_loss.py:48-58
+ *   TVERSKY: [TP = sum p*t*v, sum p*v, sum t*v] (all masked by v = label != ignore_index; exponent must be 1):
+ *            FP = sum p*v - TP, FN = sum t*v - TP                                models/losses/tversky_loss.py:52-68
+ *            the forward stores lse = +inf for ignored pixels, which masks them in every later pass            */
+enum { B200SEG_MODE_DICE = 0, B200SEG_MODE_TVERSKY = 1 };
+
 /* reductions (models/losses/utils.py:28-80) */
 enum { B200SEG_RED_NONE = 0, B200SEG_RED_MEAN = 1, B200SEG_RED_SUM = 2 };
 
@@ -84,7 +92,7 @@ typedef struct b200seg_loss_desc {
   int32_t flags;                /* B200SEG_WANT_*                                              */
   int64_t ignore_index;         /* CE ignore_index                                             */
   int32_t acc_has_ignore;       /* accuracy(ignore_index=None) -> 0                            */
-  int32_t reserved0;
+  int32_t dice_mode;            /* B200SEG_MODE_DICE / _TVERSKY                                */
   int64_t acc_ignore_index;
   /* ---- dice (models/losses/dice_loss.py) ---- */
   int64_t dice_ignore_index;
@@ -124,6 +132,10 @@ typedef struct b200seg_finalize_desc {
   double* log_vec;                  /* B200SEG_LOG_WORDS doubles or NULL: the additive quantities of
                                      * this call as float64 (exact below 2^53), i.e. the payload of the
                                      * single per-step all-reduce across data-parallel ranks           */
+  int32_t dice_mode;                /* B200SEG_MODE_*                                          */
+  float   tversky_alpha;            /* weight of the false positives (tversky_loss.py:66)      */
+  float   tversky_beta;             /* weight of the false negatives                           */
+  int32_t reserved0;
 } b200seg_finalize_desc;
 
 /* One tiny launch: statistics -> loss_ce, loss_dice, acc_seg scalars (+ dice backward table). */
@@ -150,7 +162,7 @@ typedef struct b200seg_loss_bwd_desc {
   const float*    ce_grad_px;       /* (N,H,W) f32 or NULL                                     */
   const uint64_t* stats;            /* for n_valid when ce_use_nvalid                          */
   int32_t ce_use_nvalid;
-  int32_t reserved0;
+  int32_t dice_mode;                /* B200SEG_MODE_*                                          */
   const float* dice_coef;           /* (N,C,2) from finalize                                   */
   const float* dice_grad_out;       /* scalar f32 (device) or NULL                             */
   void*   grad_logits;              /* (N,C,h,w) logit_dtype, fully overwritten                */

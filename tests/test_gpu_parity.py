@@ -266,6 +266,50 @@ def test_resize_fused_extreme_logits_and_small_shapes(B):
                    loss_atol=0.0)
 
 
+
+def test_tversky_golden_and_oracle(B, golden):
+    """TverskyLoss (models/losses/tversky_loss.py:24-148): the reference's fixtures in fp32, the oracle on larger shapes
+    (C below and above 32, bf16), and the launch shared with CrossEntropyLoss through fused_resize_losses."""
+    data, manifest = golden
+    cases = [c for c in manifest['cases'] if c['kind'] == 'tversky']
+    assert len(cases) >= 4
+    for case in cases:
+        name = case['name']
+        x = torch.from_numpy(data[name + '/logits']).cuda().requires_grad_(True)
+        y = torch.from_numpy(data[name + '/labels']).cuda()
+        loss = B.TverskyLoss(**case['kw'])(x, y, weight=None, ignore_index=255)   # call-site kwargs are swallowed
+        loss.backward()
+        assert rel_err(loss, data[name + '/loss']) <= LOSS_TOL, '%s loss %.3e' % (name, rel_err(loss, data[name + '/loss']))
+        assert rel_err(x.grad, data[name + '/grad']) <= GRAD_TOL, '%s grad %.3e' % (name, rel_err(x.grad, data[name + '/grad']))
+    for shape, C, dtype, kw in (((4, 19, 96, 160), 19, torch.float32, dict(alpha=0.4, beta=0.6, smooth=0.5)),
+                                ((2, 150, 64, 64), 150, torch.float32, dict(class_weight=torch.linspace(0.5, 1.5, 150).tolist())),
+                                ((2, 21, 128, 128), 21, torch.bfloat16, dict(loss_weight=2.0)),
+                                ((3, 7, 37, 53), 7, torch.float32, dict(ignore_index=3))):   # odd extent, in-range ignore
+        x = synth_logits(shape, 31, dtype=dtype, device='cuda').requires_grad_(True)
+        y = synth_labels((shape[0],) + shape[2:], C, 31, ignore_index=255, block=8, device='cuda')
+        loss = B.TverskyLoss(**kw)(x, y)
+        loss.backward()
+        xo = x.detach().float().requires_grad_(True)
+        lo = O.tversky_loss_module(xo, y, **kw)
+        lo.backward()
+        tol = (LOSS_TOL, GRAD_TOL) if dtype == torch.float32 else (HALF_TOL, 2 * HALF_TOL)
+        assert rel_err(loss, lo) <= tol[0], '%s loss %.3e' % (shape, rel_err(loss, lo))
+        assert rel_err(x.grad, xo.grad) <= tol[1], '%s grad %.3e' % (shape, rel_err(x.grad, xo.grad))
+    # decode-head call: CE + Tversky on low-resolution logits, one fused launch set
+    x = synth_logits((2, 19, 32, 64), 5, device='cuda').requires_grad_(True)
+    y = synth_labels((2, 128, 256), 19, 5, ignore_index=255, block=8, device='cuda').unsqueeze(1)
+    out = B.fused_resize_losses(x, y, [B.CrossEntropyLoss(), B.TverskyLoss(loss_weight=0.5)], ignore_index=255)
+    assert list(out.keys()) == ['loss_ce', 'loss_tversky', 'acc_seg']
+    (out['loss_ce'] + out['loss_tversky']).backward()
+    xo = x.detach().clone().requires_grad_(True)
+    full = O.resize(xo, size=(128, 256), mode='bilinear', align_corners=False)
+    ref_ce = O.cross_entropy_loss_module(full, y.squeeze(1), ignore_index=255)
+    ref_tv = O.tversky_loss_module(full, y.squeeze(1), loss_weight=0.5)
+    (ref_ce + ref_tv).backward()
+    assert rel_err(out['loss_ce'], ref_ce) <= LOSS_TOL and rel_err(out['loss_tversky'], ref_tv) <= LOSS_TOL
+    assert rel_err(x.grad, xo.grad) <= GRAD_TOL
+
+
 def test_config3_ade20k_shape(B):
     """BASELINE config 3 (batch reduced to 2 for the oracle's 150-iteration Python loop): 150 classes, 512x512, bf16,
     class-weighted CE + Dice(loss_weight=3)."""

@@ -76,7 +76,8 @@ def test_registry_install_and_build():
 
     installed = B.registry.install(FakeLoss, override=True)
     assert FakeLoss.get('CrossEntropyLoss') is B.CrossEntropyLoss and FakeLoss.get('B200DiceLoss') is B.DiceLoss
-    assert set(installed) == {'CrossEntropyLoss', 'DiceLoss', 'B200CrossEntropyLoss', 'B200DiceLoss'}
+    assert set(installed) == {'CrossEntropyLoss', 'DiceLoss', 'TverskyLoss', 'B200CrossEntropyLoss', 'B200DiceLoss',
+                              'B200TverskyLoss'}
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         m = B.registry.build_loss(dict(type='CrossEntropyLoss', loss_weight=0.4, class_weight=[1.0, 2.0]))
