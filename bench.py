@@ -296,62 +296,55 @@ def b200_main(args):
     ms_step = ms_total / K
     value = world * px_step / (ms_step * 1e-3) / 1e6
 
-    # ---- e2e: host inputs, H2D + step + D2H every step, through the public API
-    xh = [make_logits((N, Cc, h, w), seed0 + 77 + i).pin_memory() for i in range(2)]
-    yh = [make_labels((N, H, Wd), Cc, seed0 + 77 + i, ign).unsqueeze(1).pin_memory() for i in range(2)]
-    xd = torch.empty((N, Cc, h, w), device=dev).requires_grad_(True)
-    yd = torch.empty((N, 1, H, Wd), dtype=torch.int64, device=dev)
-    host_loss = []
-
-    def e2e_step(k):
-        with torch.no_grad():
-            xd.copy_(xh[k & 1], non_blocking=True)
-        yd.copy_(yh[k & 1], non_blocking=True)
-        xd.grad = None
-        r = B.fused_resize_losses(xd, yd, ce, align_corners=False, ignore_index=ign)
-        r['loss_ce'].backward()
-        host_loss.append(r['loss_ce'].item())  # D2H read of the step's result (synchronises, as parse_losses does)
-
+    # ---- e2e: host inputs, H2D + step + D2H every step, through the public API. The copies of step k+1 are issued on a
+    # copy stream before step k's kernels (double-buffered device inputs), as a DataLoader with pin_memory +
+    # non_blocking copies does; every step still ends with the D2H read of its loss (parse_losses' .item()).
     e2e_steps = max(10, min(K, 50))
-    for k in range(3):
-        e2e_step(k)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * px_step * e2e_steps / float(t.item()) / 1e6
-    h2d = xh[0].numel() * 4 + yh[0].numel() * 8
+
+    def e2e_run(label_dtype):
+        xh = [make_logits((N, Cc, h, w), seed0 + 77 + i).pin_memory() for i in range(2)]
+        yh = [make_labels((N, H, Wd), Cc, seed0 + 77 + i, ign).unsqueeze(1).to(label_dtype).pin_memory() for i in range(2)]
+        xd = [torch.empty((N, Cc, h, w), device=dev).requires_grad_(True) for _ in range(2)]
+        yd = [torch.empty((N, 1, H, Wd), dtype=label_dtype, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        arrived = [torch.cuda.Event() for _ in range(2)]
+        host_loss = []
+
+        def issue_copy(k):
+            j = k & 1
+            with torch.cuda.stream(copy_stream):
+                with torch.no_grad():
+                    xd[j].copy_(xh[j], non_blocking=True)
+                yd[j].copy_(yh[j], non_blocking=True)
+                arrived[j].record(copy_stream)
+
+        def run(steps):
+            issue_copy(0)
+            for k in range(steps):
+                j = k & 1
+                if k + 1 < steps:
+                    issue_copy(k + 1)      # buffer (k+1)&1 was released by the .item() of step k-1
+                torch.cuda.current_stream().wait_event(arrived[j])
+                xd[j].grad = None
+                r = B.fused_resize_losses(xd[j], yd[j], ce, align_corners=False, ignore_index=ign)
+                r['loss_ce'].backward()
+                host_loss.append(r['loss_ce'].item())  # D2H read of the step's result (synchronises, as parse_losses does)
+
+        run(4)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(e2e_steps)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * px_step * e2e_steps / float(tt.item()) / 1e6, xh[0].numel() * 4 + yh[0].numel() * yh[0].element_size()
+
+    e2e_value, h2d = e2e_run(torch.int64)
     # same loop with the label maps kept uint8 on the host (the kernels read u8 directly): 8x fewer label bytes over PCIe
-    yh8 = [t_.to(torch.uint8).pin_memory() for t_ in yh]
-    yd8 = torch.empty((N, 1, H, Wd), dtype=torch.uint8, device=dev)
-
-    def e2e_step_u8(k):
-        with torch.no_grad():
-            xd.copy_(xh[k & 1], non_blocking=True)
-        yd8.copy_(yh8[k & 1], non_blocking=True)
-        xd.grad = None
-        r = B.fused_resize_losses(xd, yd8, ce, align_corners=False, ignore_index=ign)
-        r['loss_ce'].backward()
-        host_loss.append(r['loss_ce'].item())
-
-    for k in range(3):
-        e2e_step_u8(k)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step_u8(k)
-    torch.cuda.synchronize()
-    t8 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t8, op=dist.ReduceOp.MAX)
-    e2e_u8_value = world * px_step * e2e_steps / float(t8.item()) / 1e6
+    e2e_u8_value, h2d_u8 = e2e_run(torch.uint8)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- dominant kernel alone (C ABI, CUDA events on the launching stream)
@@ -371,6 +364,11 @@ def b200_main(args):
                     'sample': 'full C2 batch (8 images), 6 timed steps of resize + CE fwd/bwd + accuracy on the host CPU '
                               '(torch %s, os.cpu_count()=%s), %.0f ms/step' % (torch.__version__, os.cpu_count(), ms_cpu)}
 
+    if world > 1 and not args.no_extras:
+        sharded = c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind)
+        if rank == 0:
+            extras['C5i_miou_label_maps_sharded'] = sharded
+
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': K, 'warmup': W,
@@ -381,8 +379,9 @@ def b200_main(args):
                 if world > 1 else 'none (single GPU)'),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                    'steps': e2e_steps, 'note': 'pinned host logits+int64 labels copied every step; PCIe-bound',
-                    'uint8_labels': {'value': e2e_u8_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': xh[0].numel() * 4 + yh[0].numel(),
+                    'steps': e2e_steps, 'note': 'pinned host logits + int64 labels copied every step on a copy stream (double-'
+                                                'buffered, overlapping the previous step), loss read back every step; PCIe-bound',
+                    'uint8_labels': {'value': e2e_u8_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d_u8,
                                      'note': 'same step with the label maps kept uint8 on the host (read directly by the kernels)'}},
             'gpu_launches': int(launches_per_step * K),
             'launches_per_step': int(launches_per_step),
@@ -453,6 +452,48 @@ def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
         out['issue_roofline'] = {'bound': 'issue', 'achieved': warp_inst / (ms * 1e-3), 'peak': issue_peak, 'unit': 'warp-inst/s',
                                  'frac': warp_inst / (ms * 1e-3) / issue_peak, 'warp_inst_per_launch': warp_inst}
     return out
+
+
+def c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind):
+    """BASELINE config 5 across ranks: the 500-image sweep sharded by image (ceil split), one launch per rank for its
+    image list, then ONE packed all-reduce of the (3, C) int64 area totals. Timed with CUDA events between barriers,
+    max over ranks; pixels counted over all 500 images."""
+    Cn, n_img = 19, 500
+    lo, hi = D.shard_range(n_img, rank, world)
+    g = torch.Generator(device=dev).manual_seed(555 + rank)
+    gts = [make_labels((1, 1024, 2048), Cn, 500 + i, 255, device=dev)[0].float() for i in range(4)]
+    pred_base = [torch.randint(0, Cn, (1024, 2048), generator=g, device=dev) for _ in range(8)]
+    preds = [pred_base[i % 8].clone() for i in range(lo, hi)]
+    gt_all = [gts[i % 4].clone() for i in range(lo, hi)]
+
+    def sweep():
+        areas = B.areas_device(preds, gt_all, Cn, 255)
+        return D.all_reduce_areas({'areas': areas.sum(0)})['areas']
+
+    for _ in range(2):
+        tot = sweep()
+    torch.cuda.synchronize()
+    dist.barrier()
+    iters = 5
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for _ in range(iters):
+        tot = sweep()
+    e_ev.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([s_ev.elapsed_time(e_ev) / iters], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    px = n_img * 1024 * 2048
+    label_px = int(tot[2].sum().item())       # all-reduced label-area total: every non-ignored pixel of all 500 images
+    a = px * 12 / (ms * 1e-3) / 1e9
+    return {'images': n_img, 'images_per_rank': hi - lo, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3, 'n_gpus': world,
+            'roofline': {'bound': 'hbm', 'achieved': a, 'peak': peak * world, 'unit': 'GB/s', 'frac': a / (peak * world),
+                         'peak_kind': peak_kind},
+            'all_reduced_label_pixels': label_px,
+            'note': 'sharded by image over the ranks, one b200seg_confusion_labels launch per rank + one packed all-reduce of '
+                    'the area totals per sweep'}
 
 
 def extra_workloads(B, _lib, dev, peak, peak_kind):

@@ -79,6 +79,7 @@ class FusedLossFunction(torch.autograd.Function):
     def forward(ctx, logits, labels, pixel_weight, spec, grad_enabled=True):
         lib = _lib.load()
         _lib.require_cuda(logits, "logits")
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None in backward(), not as zero-filled tensors
         if logits.dtype not in _lib.LOGIT_DTYPES:
             raise TypeError("logits must be float32, bfloat16 or float16, got %s" % logits.dtype)
         if logits.dim() != 4:
