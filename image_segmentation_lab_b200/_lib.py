@@ -20,7 +20,7 @@ MODE_DICE, MODE_TVERSKY = 0, 1
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 8
+ABI_VERSION = 9
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -116,6 +116,7 @@ SYMBOLS = [
     ("b200seg_loss_finalize", C.c_int, [C.POINTER(FinalizeDesc), _p]),
     ("b200seg_loss_bwd", C.c_int, [C.POINTER(LossBwdDesc), _p]),
     ("b200seg_loss_fused_workspace_bytes", _i64, [_i32] * 7),
+    ("b200seg_loss_flat_single_ok", _i32, [_p, _p, _i32, _i32, _i32, _i64, _i32]),
     ("b200seg_loss_fused_fwdbwd", C.c_int, [C.POINTER(LossFusedDesc), _p]),
     ("b200seg_loss_fused_combine", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _f, _p, _i32, _p, _p]),
     ("b200seg_scale_inplace", C.c_int, [_p, _i32, _i64, _p, _p]),

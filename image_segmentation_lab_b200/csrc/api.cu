@@ -40,6 +40,8 @@ long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac);
 int up_combine_dispatch(const void* ws, void* grad, int dtype, int N, int C, int h, int w, float scale_host,
                         const float* grad_out, int use_nvalid, const uint64_t* stats, cudaStream_t st);
 int scale_inplace_dispatch(void* x, int dtype, long long n, const float* g, cudaStream_t st);
+bool bulk_supported(const void* logits, const void* labels, const void* grad, int logit_dtype, int label_dtype, int C,
+                    long long HW, bool has_pixel_weight);
 
 static int check_shape(const char* who, int N, int C, int h, int w, int H, int W, int ldt, int ydt) {
   B200SEG_REQUIRE(N >= 0 && C >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1, "%s: bad shape N=%d C=%d h=%d w=%d H=%d W=%d",
@@ -154,6 +156,12 @@ extern "C" int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream) {
 extern "C" int64_t b200seg_loss_fused_workspace_bytes(int32_t N, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W,
                                                       int32_t align_corners) {
   return up_fused_workspace(N, C, h, w, H, W, align_corners);
+}
+
+extern "C" int32_t b200seg_loss_flat_single_ok(const void* logits, const void* labels, int32_t logit_dtype, int32_t label_dtype,
+                                               int32_t C, int64_t HW, int32_t has_pixel_weight) {
+  if (C <= 32) return 1;   // register-tile kernel
+  return bulk_supported(logits, labels, logits, logit_dtype, label_dtype, C, HW, has_pixel_weight != 0) ? 1 : 0;
 }
 
 extern "C" int b200seg_loss_fused_fwdbwd(const b200seg_loss_fused_desc* d, void* stream) {

@@ -24,11 +24,21 @@ static int rt_by_dtype(int dtype, const RtParams& p, int kind, bool vec, cudaStr
   return 1;
 }
 
+bool bulk_supported(const void* logits, const void* labels, const void* grad, int logit_dtype, int label_dtype, int C,
+                    long long HW, bool has_pixel_weight);
+int bulk_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st);
+
 int flat_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st) {
   const b200seg_loss_desc* f = &d->fwd;
   B200SEG_REQUIRE(d->grad_logits != nullptr, "loss_fused: grad_logits is NULL");
   B200SEG_REQUIRE(!d->use_nvalid, "loss_fused: avg_non_ignore needs the two-pass path at label resolution");
-  B200SEG_REQUIRE(f->C <= 32, "loss_fused: the label-resolution single pass holds at most 32 classes (got %d)", f->C);
+  // 16-byte tileable problems take the bulk-copy pipeline (any C whose tile fits shared memory); the rest the
+  // register-tile kernel (C <= 32)
+  if (bulk_supported(f->logits, f->labels, d->grad_logits, f->logit_dtype, f->label_dtype, f->C, (long long)f->H * f->W,
+                     f->pixel_weight != nullptr))
+    return bulk_fused_dispatch(d, st);
+  B200SEG_REQUIRE(f->C <= 32, "loss_fused: the label-resolution single pass holds at most 32 classes unless the problem is "
+                  "16-byte tileable (got %d; query b200seg_loss_flat_single_ok first)", f->C);
   RtParams p = {};
   p.logits = f->logits; p.labels = f->labels; p.pw = f->pixel_weight; p.cw = f->ce_class_weight;
   p.ce_grad_out = d->grad_out; p.stats = reinterpret_cast<unsigned long long*>(f->stats); p.grad = d->grad_logits;

@@ -37,8 +37,8 @@ __device__ __forceinline__ void cta_named_barrier(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-template <typename T, int V, int CPT, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParams p) {
+template <typename T, int V, int CPT, int MODE, bool SPLIT, int MINB = 4>
+__global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_kernel(const RtParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   static_assert(CPT <= 32, "one lane per class in the flush");
   constexpr int PXW = 32 * V;
@@ -87,12 +87,15 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParam
     const bool owner = SPLIT ? ((tile % G) == g) : true;   // the warp doing this tile's per-pixel work
     float z[CPT][V];
     {
-      // running pointer over the class dimension: one 64-bit add per class instead of a 64-bit multiply-add
-      const T* q = img + (size_t)c0 * HW + px0;
-      const int ncls = active ? c1 - c0 : 0;
+      // running pointer over the class dimension: one 64-bit add per class instead of a 64-bit multiply-add. The host
+      // picks the smallest CPT >= C, so classes below kSure always exist and carry no predicate; lanes past the end of
+      // the image read the tile's first pixel again (their results are masked by `active`).
+      constexpr int kSure = SPLIT ? 0 : (V == 2 ? (CPT == 32 ? 24 : (CPT >= 8 ? CPT - 4 : 0)) : (CPT == 32 ? 8 : 0));
+      const T* q = img + (size_t)c0 * HW + (active ? px0 : 0);
+      const int ncls = c1 - c0;
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
-        if (i < ncls) {
+        if (i < kSure || i < ncls) {
           load_vec<T, V>(q, z[i]);
         } else {
 #pragma unroll
@@ -115,11 +118,11 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParam
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       float lm = z[0][v];
-      int li = c0;
 #pragma unroll
-      for (int i = 1; i < CPT; ++i) {
-        if (z[i][v] > lm) { lm = z[i][v]; li = c0 + i; }   // strict '>': lowest index wins
-      }
+      for (int i = 1; i < CPT; ++i) lm = fmaxf(lm, z[i][v]);           // FMNMX3 tree
+      int li = c0 + CPT - 1;
+#pragma unroll
+      for (int i = CPT - 2; i >= 0; --i) li = (z[i][v] == lm) ? c0 + i : li;   // lowest index among the maxima
       const float nm = -lm * kLog2e;
       float ls = 0.f;
 #pragma unroll
@@ -200,21 +203,28 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_fwd_kernel(const RtParam
         for (int v = 0; v < V; ++v) { kg[v] = kk[v] * Gs; rr[v] = kg[v] * f[v]; }
         T* gq = gimg + (size_t)c0 * HW + px0;
         const int ncls = c1 - c0;
-        int yl[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) yl[v] = yc[v] - c0;
+        constexpr int kSureG = SPLIT ? 0 : (V == 2 ? (CPT == 32 ? 24 : (CPT >= 8 ? CPT - 4 : 0)) : (CPT == 32 ? 8 : 0));
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-          if (i < ncls) {
+          if (i < kSureG || i < ncls) {
             float gr[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              gr[v] = rr[v] * z[i][v];
-              if (i == yl[v]) gr[v] -= kg[v];
-            }
+            for (int v = 0; v < V; ++v) gr[v] = rr[v] * z[i][v];
             store_vec<T, V>(gq, gr);
           }
           gq += HW;
+        }
+        // one-hot term: instead of a compare per element, the label's class is re-stored by the same thread (program
+        // order) with k * (p_y - 1); p_y is recomputed from the label's logit with the operations of the class loop
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int yl = yc[v] - c0;
+          if (yc[v] >= 0 && yl >= 0 && yl < ncls) {
+            const float zy = to_float<T>(img[(size_t)yc[v] * HW + px0 + v]);
+            static_assert(!SPLIT, "the one-hot patch assumes the local max is the pixel's max");
+            const float ey = ex2(fmaf(zy, kLog2e, -m[v] * kLog2e));
+            gimg[(size_t)yc[v] * HW + px0 + v] = from_float<T>(rr[v] * ey - kg[v]);
+          }
         }
       }
     }
@@ -488,7 +498,16 @@ template <typename T, int V, int CPT, int MODE> static int launch_rt_fwd(RtParam
   if (gx < 1) gx = 1;
   dim3 grid(gx, p.N);
   B200SEG_REQUIRE(!split, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
-  rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
+  if constexpr (CPT == 24 && MODE == MODE_GRAD && V == 2 && sizeof(T) == 4) {   // A/B: resident CTAs per SM (register cap)
+    static int mb = -1;
+    if (mb < 0) { const char* e = getenv("B200SEG_RT_MINB"); mb = e ? atoi(e) : 4; }
+    if (mb == 2) rt_fwd_kernel<T, V, CPT, MODE, false, 2><<<grid, threads, smem, st>>>(p);
+    else if (mb == 3) rt_fwd_kernel<T, V, CPT, MODE, false, 3><<<grid, threads, smem, st>>>(p);
+    else if (mb == 5) rt_fwd_kernel<T, V, CPT, MODE, false, 5><<<grid, threads, smem, st>>>(p);
+    else rt_fwd_kernel<T, V, CPT, MODE, false, 4><<<grid, threads, smem, st>>>(p);
+  } else {
+    rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
+  }
   count_launch();
   return check_launch("rt_fwd_kernel");
 }

@@ -155,8 +155,9 @@ class FusedLossFunction(torch.autograd.Function):
                 if up:
                     if lib.b200seg_loss_fused_workspace_bytes(N, Cc, h, w, H, W, fd.align_corners) > 0:
                         plan = "up_single"
-                elif needs_grad and not use_nvalid and Cc <= 32:  # one warp's register tile holds all classes
-                    plan = "flat_single"
+                elif needs_grad and not use_nvalid and lib.b200seg_loss_flat_single_ok(
+                        logits_c.data_ptr(), labels.data_ptr(), fd.logit_dtype, fd.label_dtype, Cc, H * W, int(pw is not None)):
+                    plan = "flat_single"   # bulk-copy pipeline (any C whose tile fits shared memory) or register tile (C <= 32)
 
             loss_px = lse = grad = pb = None
             if plan == "two_pass":
