@@ -310,6 +310,32 @@ def test_tversky_golden_and_oracle(B, golden):
     assert rel_err(x.grad, xo.grad) <= GRAD_TOL
 
 
+
+def test_bulk_pipeline_single_pass_shapes(B):
+    """Label-resolution single-pass CE (cp.async.bulk pipeline, csrc/loss_bulk.cu): many classes, 16-bit logits, partial
+    last tiles (H*W not a multiple of the 256-pixel tile), uint8 / int32 labels, class weights, more tiles than CTAs."""
+    cw150 = torch.linspace(0.5, 1.5, 150).tolist()
+    for shape, C, dtype, ldt, kw in (((2, 150, 64, 96), 150, torch.float32, torch.int64, dict(class_weight=cw150)),
+                                     ((2, 150, 48, 40), 150, torch.bfloat16, torch.uint8, {}),
+                                     ((3, 33, 20, 12), 33, torch.float32, torch.int32, {}),        # 240 px: one partial tile
+                                     ((1, 21, 36, 52), 21, torch.float16, torch.int64, {}),        # 1872 px = 7 tiles + 80 px
+                                     ((4, 100, 160, 160), 100, torch.float32, torch.uint8, dict(loss_weight=0.4)),
+                                     ((2, 260, 32, 32), 260, torch.bfloat16, torch.int64, {})):    # near the 16-bit class limit
+        x = synth_logits(shape, 77, dtype=dtype, device='cuda').requires_grad_(True)
+        y = synth_labels((shape[0],) + shape[2:], C, 77, ignore_index=255, block=4, device='cuda').to(ldt)
+        ce = B.CrossEntropyLoss(**kw)
+        out = B.fused_resize_losses(x, y.unsqueeze(1), ce, ignore_index=255)
+        out['loss_ce'].backward()
+        xo = x.detach().float().requires_grad_(True)
+        ref = O.cross_entropy_loss_module(xo, y.long(), ignore_index=255, **kw)
+        ref.backward()
+        acc = O.accuracy(xo.detach(), y.long(), ignore_index=255)
+        lt, gt = (LOSS_TOL, GRAD_TOL) if dtype == torch.float32 else (HALF_TOL, 2 * HALF_TOL)
+        assert rel_err(out['loss_ce'], ref) <= lt, '%s loss %.3e' % (shape, rel_err(out['loss_ce'], ref))
+        assert rel_err(x.grad, xo.grad) <= gt, '%s grad %.3e' % (shape, rel_err(x.grad, xo.grad))
+        assert abs(float(out['acc_seg']) - float(acc)) <= (1e-3 if dtype == torch.float32 else 0.5)
+
+
 def test_config3_ade20k_shape(B):
     """BASELINE config 3 (batch reduced to 2 for the oracle's 150-iteration Python loop): 150 classes, 512x512, bf16,
     class-weighted CE + Dice(loss_weight=3)."""

@@ -15,6 +15,18 @@ peak, _ = bench.hbm_peak()
 shape = (32, 21, 512, 512)
 xs = [bench.make_logits(shape, 300 + i, device=dev).requires_grad_(True) for i in range(2)]
 ys = [bench.make_labels((32, 512, 512), 21, 300 + i, 255, device=dev).unsqueeze(1) for i in range(2)]
+ce0 = B.CrossEntropyLoss()
+
+
+def fwd_only(i):
+    with torch.no_grad():
+        B.fused_resize_losses(xs[i & 1], ys[i & 1], ce0, ignore_index=255)
+
+
+for i in range(3):
+    fwd_only(i)
+ms = bench.timed_events(fwd_only, 20)
+print('C4 fwd (no grad): %.3f ms  frac %.2f' % (ms, (32 * 21 * 512 * 512 * 4 + 32 * 512 * 512 * 8) / (ms * 1e-3) / 1e9 / peak))
 for single in (True, False):
     ce = B.CrossEntropyLoss()
     ce.single_pass = single
