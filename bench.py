@@ -546,7 +546,9 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
                  [B.CrossEntropyLoss(class_weight=cw), B.DiceLoss(loss_weight=3.0)], iters=10,
                  plan='ce_fwd_kernel(+one-hot dice sums) + dice_sumsq_kernel + finalize; dice_dot_kernel + dice_grad_kernel')
     bench_losses('C4_voc_fp32_ce', (32, 21, 512, 512), torch.float32, B.CrossEntropyLoss(), iters=20, single=True,
-                 plan='flat_fused_kernel: forward+backward in one pass')
+                 plan='ce_bulk_kernel (cp.async.bulk load warp / consumers / store warp): forward+backward in one pass')
+    bench_losses('C3_ade20k_bf16_ce_only', (16, 150, 512, 512), torch.bfloat16, B.CrossEntropyLoss(class_weight=cw), iters=10,
+                 plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
     ce2 = B.CrossEntropyLoss()
     ce2.single_pass = False
     bench_losses('C4_voc_fp32_ce_two_pass', (32, 21, 512, 512), torch.float32, ce2, iters=10,

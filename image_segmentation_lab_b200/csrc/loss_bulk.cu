@@ -3,7 +3,7 @@
 // Replaces F.cross_entropy (models/losses/cross_entropy_loss.py:56-61), weight_reduce_loss (models/losses/utils.py:48-80),
 // the top-1 accuracy (models/losses/accuracy.py:41-60) and their autograd backward — at least six passes over the
 // (N,C,H,W) logits in ATen — with ONE read and ONE write of them (the algorithmic minimum for a gradient of the same
-// shape), for any class count whose tile fits shared memory (fp32: C <= 134, 16-bit: C <= 269).
+// shape), for class counts whose tile leaves room for two CTAs x three stages per SM (fp32: C <= 34, 16-bit: C <= 69).
 //
 // Structure. A persistent CTA walks tiles of 256 pixels x C classes. A producer warp issues one `cp.async.bulk`
 // (global -> shared, completion on an mbarrier) per class row of the tile plus one for the label row, 3-4 stages ahead;
@@ -266,7 +266,9 @@ bool bulk_supported(const void* logits, const void* labels, const void* grad, in
   if (has_pixel_weight || C < 1 || HW < 1) return false;
   if (!aligned16(logits) || !aligned16(labels) || !aligned16(grad)) return false;
   if ((HW * elem) % 16 || (HW * lb) % 16) return false;
-  return 3 * bulk_stage_bytes(C, elem) <= 200 * 1024;
+  // two resident CTAs x three stages must fit: with fewer consumer warps per SM the kernel turns consumer bound (measured:
+  // bf16 C = 150 with 128-pixel tiles and one CTA per SM ran at 0.21 of the roofline, the two-pass kernels at 0.56)
+  return 6 * bulk_stage_bytes(C, elem) <= 220 * 1024;   // fp32: C <= 34, 16-bit: C <= 69
 }
 
 template <typename T> static int bulk_launch(BulkParams p, cudaStream_t st) {

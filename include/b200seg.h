@@ -173,9 +173,9 @@ typedef struct b200seg_loss_bwd_desc {
 /* Fused backward: d(loss)/d(logits) in one pass (softmax Jacobian, dice, resize transpose). */
 int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream);
 
-/* 1 if b200seg_loss_fused_fwdbwd can run a label-resolution problem (h == H, w == W) in a single pass: C <= 32, or any
- * C whose 128-pixel tile fits shared memory when the tensors are 16-byte tileable (aligned pointers, H*W*elem % 16 == 0,
- * no per-pixel weight). grad_logits is assumed to be aligned like logits. */
+/* 1 if b200seg_loss_fused_fwdbwd can run a label-resolution problem (h == H, w == W) in a single pass: C <= 32 (register
+ * tile), or up to 34 (fp32) / 69 (16-bit) classes on the bulk-copy pipeline when the tensors are 16-byte tileable (aligned
+ * pointers, H*W*elem % 16 == 0, no per-pixel weight). grad_logits is assumed to be aligned like logits. */
 int32_t b200seg_loss_flat_single_ok(const void* logits, const void* labels, int32_t logit_dtype, int32_t label_dtype,
                                     int32_t C, int64_t HW, int32_t has_pixel_weight);
 
