@@ -14,8 +14,6 @@
 // of the copy roofline because a thread had to hold its own loads.
 //
 // Bound: HBM. Algorithmic bytes per launch: 2*N*C*H*W*s + N*H*W*L.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace b200seg {
@@ -275,9 +273,6 @@ template <typename T> static int bulk_launch(BulkParams p, cudaStream_t st) {
   const size_t stage = bulk_stage_bytes(p.C, (int)sizeof(T));
   int stages = (int)((200 * 1024) / stage);
   if (stages > kBulkMaxStages) stages = kBulkMaxStages;
-  static int env_stages = -1;
-  if (env_stages < 0) { const char* e = getenv("B200SEG_BULK_STAGES"); env_stages = e ? atoi(e) : 0; }
-  if (env_stages >= 2 && env_stages <= stages) stages = env_stages;
   p.stages = stages;
   p.stage_bytes = (int)stage;
   const size_t smem = stage * stages;

@@ -10,13 +10,11 @@
 //
 // Both Dice (sum_px softmax(z)_c^e for every class) and the single-pass CE gradient need the NORMALISED probability
 // of every (pixel, class) element, so the exponentials must be kept until the per-pixel sum is known. A thread keeps
-// CPT classes x V pixels in registers. If C <= CPT one warp owns all classes of its 32*V pixels and there is no
-// inter-warp traffic at all (SPLIT=false, 4 independent warps per CTA). Otherwise the class dimension is split over
-// G warps (SPLIT=true, CTA = G warps): each warp soft-maxes its own classes against its LOCAL max, the G (max, sum,
-// argmax) partials of a pixel are exchanged through double-buffered shared memory with ONE named barrier per tile
-// and combined online (s = sum_g s_g * 2^((m_g - m) log2e)). Per-pixel work (label, CE term, accuracy, one-hot Dice
-// sums) rotates over the G warps tile by tile. Per-class Dice sums live in per-thread registers across all tiles a
-// CTA visits: one shuffle tree per class per CTA lifetime. One MUFU.EX2 per element.
+// CPT >= C classes x V pixels in registers: one warp owns all classes of its 32*V pixels, so there is no inter-warp
+// traffic at all (4 independent warps per CTA). Per-class Dice sums live in per-thread registers across all tiles a
+// CTA visits: one shuffle tree per class per CTA lifetime. One MUFU.EX2 per element. More than 32 classes take the
+// streaming kernels (loss_dice.cu); a class-split variant of this file (warps exchanging partial max / sum through
+// shared memory) was measured at 9 % of the roofline and removed.
 //
 // Roofline: HBM. Algorithmic bytes: forward el*s + px*L (+4 px for lse); backward / single pass 2*el*s + px*L.
 #pragma once
@@ -33,33 +31,23 @@ enum { MODE_GRAD = 0, MODE_DICE = 1 };
 #include "loss_rt_params.cuh"
 namespace b200seg {
 
-__device__ __forceinline__ void cta_named_barrier(int nthreads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
-
-template <typename T, int V, int CPT, int MODE, bool SPLIT, int MINB = 4>
-__global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_kernel(const RtParams p) {
+// 4 resident CTAs per SM (register cap 128): measured 0.59 / 0.65 / 0.73 of the roofline at 2 / 3 / 4 CTAs, 0.54 at 5 (spills)
+template <typename T, int V, int CPT, int MODE>
+__global__ void __launch_bounds__(128, 4) rt_fwd_kernel(const RtParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   static_assert(CPT <= 32, "one lane per class in the flush");
   constexpr int PXW = 32 * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C;
-  const int G = SPLIT ? p.G : 1;
-  const int g = SPLIT ? warp : 0;
-  const int NPG = SPLIT ? 1 : 4;           // pixel groups per CTA
-  const int pgw = SPLIT ? 0 : warp;
-  const int c0 = g * p.cpg;
-  const int c1 = (c0 + p.cpg < C) ? c0 + p.cpg : C;
+  constexpr int NPG = 4;                   // pixel groups (warps) per CTA
+  const int pgw = warp;
+  constexpr int c0 = 0;
+  const int c1 = C;
   const int n = blockIdx.y;
   const long long HW = p.HW;
 
-  // shared memory: SPLIT exchange buffers (x2 parity), per-warp one-hot Dice bins
-  float* xm = reinterpret_cast<float*>(smem_raw);             // [2][G][PXW]
-  float* xs = xm + (SPLIT ? 2 * G * PXW : 0);                 // [2][G][PXW]
-  int* xi = reinterpret_cast<int*>(xs + (SPLIT ? 2 * G * PXW : 0));   // [2][G][PXW]
-  float* xk = reinterpret_cast<float*>(xi + (SPLIT ? 2 * G * PXW : 0));  // [2][PXW]   (MODE_GRAD)
-  int* xy = reinterpret_cast<int*>(xk + (SPLIT ? 2 * PXW : 0));        // [2][PXW]   (MODE_GRAD)
-  float* A_s = reinterpret_cast<float*>(xy + (SPLIT ? 2 * PXW : 0));   // [warps][C] (MODE_DICE)
+  // shared memory: per-warp one-hot Dice bins
+  float* A_s = reinterpret_cast<float*>(smem_raw);   // [warps][C] (MODE_DICE)
   const int nwarps = blockDim.x >> 5;
   float* T_s = A_s + (MODE == MODE_DICE ? nwarps * C : 0);
   if constexpr (MODE == MODE_DICE) {
@@ -80,17 +68,16 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_ke
   float loss_acc = 0.f;
   int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
 
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long px0 = ((long long)tile * NPG + pgw) * PXW + (long long)lane * V;
     const bool active = px0 < HW;
-    const bool owner = SPLIT ? ((tile % G) == g) : true;   // the warp doing this tile's per-pixel work
+    constexpr bool owner = true;
     float z[CPT][V];
     {
       // running pointer over the class dimension: one 64-bit add per class instead of a 64-bit multiply-add. The host
       // picks the smallest CPT >= C, so classes below kSure always exist and carry no predicate; lanes past the end of
       // the image read the tile's first pixel again (their results are masked by `active`).
-      constexpr int kSure = SPLIT ? 0 : (V == 2 ? (CPT == 32 ? 24 : (CPT >= 8 ? CPT - 4 : 0)) : (CPT == 32 ? 8 : 0));
+      constexpr int kSure = V == 2 ? (CPT == 32 ? 24 : (CPT >= 8 ? CPT - 4 : 0)) : (CPT == 32 ? 8 : 0);
       const T* q = img + (size_t)c0 * HW + (active ? px0 : 0);
       const int ncls = c1 - c0;
 #pragma unroll
@@ -143,38 +130,8 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_ke
       yc[v] = valid ? (int)yy : -1;
     }
     float f[V];
-    if constexpr (SPLIT) {
-      const int par = it & 1;
-      float* bm = xm + par * G * PXW;
-      float* bs = xs + par * G * PXW;
-      int* bi = xi + par * G * PXW;
-      const int slot = g * PXW + lane * V;
 #pragma unroll
-      for (int v = 0; v < V; ++v) { bm[slot + v] = m[v]; bs[slot + v] = s[v]; bi[slot + v] = idx[v]; }
-      if (MODE == MODE_GRAD && owner) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) { xk[par * PXW + lane * V + v] = kk[v]; xy[par * PXW + lane * V + v] = yc[v]; }
-      }
-      cta_named_barrier(32 * G);
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float gm = bm[lane * V + v];
-        int gi = bi[lane * V + v];
-        for (int gg = 1; gg < G; ++gg) {
-          const float t = bm[gg * PXW + lane * V + v];
-          if (t > gm) { gm = t; gi = bi[gg * PXW + lane * V + v]; }
-        }
-        float gsum = 0.f;
-        for (int gg = 0; gg < G; ++gg)
-          gsum = fmaf(bs[gg * PXW + lane * V + v], ex2((bm[gg * PXW + lane * V + v] - gm) * kLog2e), gsum);
-        f[v] = ex2((m[v] - gm) * kLog2e) * fast_rcp(gsum);
-        m[v] = gm; s[v] = gsum; idx[v] = gi;
-        if constexpr (MODE == MODE_GRAD) { kk[v] = xk[par * PXW + lane * V + v]; yc[v] = xy[par * PXW + lane * V + v]; }
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < V; ++v) f[v] = fast_rcp(s[v]);
-    }
+    for (int v = 0; v < V; ++v) f[v] = fast_rcp(s[v]);
 
     if (active) {
       if constexpr (MODE == MODE_DICE) {
@@ -203,7 +160,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_ke
         for (int v = 0; v < V; ++v) { kg[v] = kk[v] * Gs; rr[v] = kg[v] * f[v]; }
         T* gq = gimg + (size_t)c0 * HW + px0;
         const int ncls = c1 - c0;
-        constexpr int kSureG = SPLIT ? 0 : (V == 2 ? (CPT == 32 ? 24 : (CPT >= 8 ? CPT - 4 : 0)) : (CPT == 32 ? 8 : 0));
+        constexpr int kSureG = V == 2 ? (CPT == 32 ? 24 : (CPT >= 8 ? CPT - 4 : 0)) : (CPT == 32 ? 8 : 0);
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           if (i < kSureG || i < ncls) {
@@ -221,7 +178,6 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_ke
           const int yl = yc[v] - c0;
           if (yc[v] >= 0 && yl >= 0 && yl < ncls) {
             const float zy = to_float<T>(img[(size_t)yc[v] * HW + px0 + v]);
-            static_assert(!SPLIT, "the one-hot patch assumes the local max is the pixel's max");
             const float ey = ex2(fmaf(zy, kLog2e, -m[v] * kLog2e));
             gimg[(size_t)yc[v] * HW + px0 + v] = from_float<T>(rr[v] * ey - kg[v]);
           }
@@ -308,25 +264,17 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128, SPLIT ? 1 : MINB) rt_fwd_ke
 
 // ------------------------------------------------------------------------------------------------
 // Backward: grad_z_j = p_j * (g_j - sum_c p_c g_c) [dice, g = dL/dp]  +  k * (p_j - onehot_j) [CE]
-template <typename T, int V, int CPT, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const RtParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+template <typename T, int V, int CPT>
+__global__ void __launch_bounds__(128) rt_dice_bwd_kernel(const RtParams p) {
   constexpr int PXW = 32 * V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C;
-  const int G = SPLIT ? p.G : 1;
-  const int g = SPLIT ? warp : 0;
-  const int NPG = SPLIT ? 1 : 4;
-  const int pgw = SPLIT ? 0 : warp;
-  const int c0 = g * p.cpg;
-  const int c1 = (c0 + p.cpg < C) ? c0 + p.cpg : C;
+  constexpr int NPG = 4;
+  const int pgw = warp;
+  constexpr int c0 = 0;
+  const int c1 = C;
   const int n = blockIdx.y;
   const long long HW = p.HW;
-
-  float* xd = reinterpret_cast<float*>(smem_raw);     // [2][G][PXW] partial dots
-  float* xk = xd + 2 * G * PXW;                        // [2][PXW] CE coefficient
-  float* xa = xk + 2 * PXW;                            // [2][PXW] dice one-hot coefficient
-  int* xy = reinterpret_cast<int*>(xa + 2 * PXW);      // [2][PXW] clamped label
 
   const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;
   const bool e2 = (p.dice_exponent == 2.f);
@@ -348,11 +296,10 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const Rt
   const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * HW;
   T* gimg = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW;
 
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long px0 = ((long long)tile * NPG + pgw) * PXW + (long long)lane * V;
     const bool active = px0 < HW;
-    const bool owner = SPLIT ? ((tile % G) == g) : true;
+    constexpr bool owner = true;
     float z[CPT][V];
     {
       // running pointer over the class dimension: one 64-bit add per class instead of a 64-bit multiply-add
@@ -421,30 +368,8 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 128) rt_dice_bwd_kernel(const Rt
       }
     }
     float sub[V];
-    if constexpr (SPLIT) {
-      const int par = it & 1;
-      float* bd = xd + par * G * PXW;
-      const int ps = par * PXW + lane * V;
 #pragma unroll
-      for (int v = 0; v < V; ++v) bd[g * PXW + lane * V + v] = dotp[v];
-      if (owner) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) { xk[ps + v] = kk[v]; xa[ps + v] = da[v]; xy[ps + v] = yc[v]; }
-      }
-      cta_named_barrier(32 * G);
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float t = 0.f;
-        for (int gg = 0; gg < G; ++gg) t += bd[gg * PXW + lane * V + v];
-        kk[v] = xk[ps + v];
-        da[v] = xa[ps + v];
-        yc[v] = xy[ps + v];
-        sub[v] = kk[v] - t;   // grad = p * (gd + k - dot)
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < V; ++v) sub[v] = kk[v] - dotp[v];
-    }
+    for (int v = 0; v < V; ++v) sub[v] = kk[v] - dotp[v];   // grad = p * (gd + k - dot)
     if (active) {
       T* gq = gimg + (size_t)c0 * HW + px0;
       const int ncls = c1 - c0;
@@ -482,57 +407,36 @@ static int resident_ctas(int threads, int regs_hint) {
 }
 
 template <typename T, int V, int CPT, int MODE> static int launch_rt_fwd(RtParams p, cudaStream_t st) {
-  const bool split = p.C > CPT;
-  p.G = split ? (p.C + CPT - 1) / CPT : 1;
-  p.cpg = (p.C + p.G - 1) / p.G;
-  const int npg = split ? 1 : 4;
-  const long long per_tile = (long long)npg * 32 * V;
+  B200SEG_REQUIRE(p.C <= CPT, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
+  const long long per_tile = 4LL * 32 * V;   // 4 warps x 32 lanes x V pixels
   p.tiles = (int)((p.HW + per_tile - 1) / per_tile);
-  const int threads = split ? 32 * p.G : 128;
-  const int nwarps = threads / 32;
-  size_t smem = 0;
-  if (split) smem += (size_t)(3 * 2 * p.G + 2 * 2) * 32 * V * 4;
-  if (MODE == MODE_DICE) smem += (size_t)2 * nwarps * p.C * 4;
-  int gx = (kSMs * resident_ctas(threads, 128) * (split ? 1 : 2) + p.N - 1) / p.N;
+  const int threads = 128;
+  const size_t smem = MODE == MODE_DICE ? (size_t)2 * (threads / 32) * p.C * 4 : 0;
+  int gx = (kSMs * resident_ctas(threads, 128) * 2 + p.N - 1) / p.N;
   if (gx > p.tiles) gx = p.tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, p.N);
-  B200SEG_REQUIRE(!split, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
-  if constexpr (CPT == 24 && MODE == MODE_GRAD && V == 2 && sizeof(T) == 4) {   // A/B: resident CTAs per SM (register cap)
-    static int mb = -1;
-    if (mb < 0) { const char* e = getenv("B200SEG_RT_MINB"); mb = e ? atoi(e) : 4; }
-    if (mb == 2) rt_fwd_kernel<T, V, CPT, MODE, false, 2><<<grid, threads, smem, st>>>(p);
-    else if (mb == 3) rt_fwd_kernel<T, V, CPT, MODE, false, 3><<<grid, threads, smem, st>>>(p);
-    else if (mb == 5) rt_fwd_kernel<T, V, CPT, MODE, false, 5><<<grid, threads, smem, st>>>(p);
-    else rt_fwd_kernel<T, V, CPT, MODE, false, 4><<<grid, threads, smem, st>>>(p);
-  } else {
-    rt_fwd_kernel<T, V, CPT, MODE, false><<<grid, threads, smem, st>>>(p);
-  }
+  rt_fwd_kernel<T, V, CPT, MODE><<<grid, threads, smem, st>>>(p);
   count_launch();
   return check_launch("rt_fwd_kernel");
 }
 
 template <typename T, int V, int CPT> static int launch_rt_bwd(RtParams p, cudaStream_t st) {
-  const bool split = p.C > CPT;
-  p.G = split ? (p.C + CPT - 1) / CPT : 1;
-  p.cpg = (p.C + p.G - 1) / p.G;
-  const int npg = split ? 1 : 4;
-  const long long per_tile = (long long)npg * 32 * V;
+  B200SEG_REQUIRE(p.C <= CPT, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
+  const long long per_tile = 4LL * 32 * V;
   p.tiles = (int)((p.HW + per_tile - 1) / per_tile);
-  const int threads = split ? 32 * p.G : 128;
-  const size_t smem = split ? (size_t)(2 * p.G + 3 * 2) * 32 * V * 4 : 0;
-  int gx = (kSMs * resident_ctas(threads, 128) * (split ? 1 : 2) + p.N - 1) / p.N;
+  const int threads = 128;
+  int gx = (kSMs * resident_ctas(threads, 128) * 2 + p.N - 1) / p.N;
   if (gx > p.tiles) gx = p.tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, p.N);
-  B200SEG_REQUIRE(!split, "register-tile kernels hold at most %d classes per warp (got %d)", CPT, p.C);
-  rt_dice_bwd_kernel<T, V, CPT, false><<<grid, threads, smem, st>>>(p);
+  rt_dice_bwd_kernel<T, V, CPT><<<grid, threads, 0, st>>>(p);
   count_launch();
   return check_launch("rt_dice_bwd_kernel");
 }
 
-// classes per thread: the smallest instantiation that holds all C classes in one warp; above 32 classes the class
-// dimension is split over up to 16 warps of <= 32 classes. The scalar (V=1) fallback for odd H*W only has 8 / 32.
+// classes per thread: the smallest instantiation that holds all C <= 32 classes in one warp. The scalar (V=1) fallback
+// for odd H*W only has 8 / 32.
 static int pick_cpt(int C, int V) {
   if (V == 1) return C <= 8 ? 8 : 32;
   if (C <= 32) return C <= 4 ? 4 : (C <= 8 ? 8 : (C <= 12 ? 12 : (C <= 16 ? 16 : (C <= 20 ? 20 : (C <= 24 ? 24 : 32)))));

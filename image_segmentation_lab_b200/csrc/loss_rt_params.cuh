@@ -30,6 +30,6 @@ struct RtParams {
   long long dice_ignore;
   float dice_exponent;
   float lw;
-  int G, cpg, tiles;
+  int tiles;
 };
 }  // namespace b200seg

@@ -29,8 +29,6 @@
 // Bound: instruction issue / MUFU (C exponentials per output pixel); HBM traffic is the label map only.
 // Algorithmic bytes per launch: 2*N*C*h*w*s + N*H*W*L.
 #pragma once
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace b200seg {
@@ -471,10 +469,6 @@ static inline int pick_row_groups(long long cells, int S) {
   int rgv = 1;
   const long long want = (long long)kSMs * 4 * 128 * 3;   // >= 3 rounds of resident CTAs
   while (rgv < 8 && rgv * 2 <= S / 2 && cells * 4 * rgv < want) rgv *= 2;
-  if (const char* e = getenv("B200SEG_UPCELL_RG")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8) rgv = v <= S ? v : rgv;
-  }
   return rgv;
 }
 
