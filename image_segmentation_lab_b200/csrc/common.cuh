@@ -383,6 +383,19 @@ __device__ __forceinline__ void cta_flush_stats(float loss, int n_valid, int n_c
   }
 }
 
+// One-hot Dice sums of one pixel per lane into this warp's class bins: lanes holding the same class are found with one
+// MATCH.ANY, their p_y are added with one integer REDUX in Q23 fixed point (p_y <= 1, 32 lanes: no overflow; rounding
+// 6e-8 per term, unbiased), and the group's lowest lane does the two shared-memory updates. cls < 0 = nothing to add.
+__device__ __forceinline__ void onehot_bins_add(float* A_w, float* T_w, int cls, float pyv, int lane) {
+  const unsigned peers = __match_any_sync(0xffffffffu, cls);
+  const unsigned tot = __reduce_add_sync(peers, (unsigned)__float2int_rn(pyv * 8388608.f));
+  if (cls >= 0 && lane == __ffs(peers) - 1) {
+    A_w[cls] += (float)tot * (1.f / 8388608.f);
+    T_w[cls] += (float)__popc(peers);
+  }
+  __syncwarp();
+}
+
 // lg2.approx / rcp.approx: 1 MUFU each (max rel. error 2^-22 / 1 ulp) — used once per pixel
 __device__ __forceinline__ float fast_log(float x) { return __log2f(x) * 0.6931471805599453f; }
 __device__ __forceinline__ float fast_rcp(float x) {

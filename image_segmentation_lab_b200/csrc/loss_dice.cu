@@ -285,13 +285,27 @@ __global__ void __launch_bounds__(256) dice_grad_kernel(const DiceParams p) {
           if (e2) gd = b * pr;
           else if (e1) gd = b;
           else gd = pr > 0.f ? b * __powf(pr, p.dice_exponent - 1.f) : 0.f;
-          float gv = pr * (gd + sub[v]);
-          if (c0 + i == ycl[v]) gv -= fmaf(pr, da[v], kk[v]);
-          g[v] = gv;
+          g[v] = pr * (gd + sub[v]);
         }
         store_vec<T, V>(gq, g);
       }
       gq += HW;
+    }
+  }
+  // one-hot terms: instead of a compare per element, the label's class is re-stored by the same thread (program order)
+  // with its extra -(p_y alpha_y + k); p_y is recomputed from the label's logit with the operations of the class loop
+  T* gimg = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if (da[v] != 0.f || kk[v] != 0.f) {
+      const int yc = ycl[v];
+      const float pr = ex2(fmaf(to_float<T>(img[(size_t)yc * HW + px0 + v]), kLog2e, nl[v]));
+      const float b = beta_s[yc];
+      float gd;
+      if (e2) gd = b * pr;
+      else if (e1) gd = b;
+      else gd = pr > 0.f ? b * __powf(pr, p.dice_exponent - 1.f) : 0.f;
+      gimg[(size_t)yc * HW + px0 + v] = from_float<T>(pr * (gd + sub[v]) - fmaf(pr, da[v], kk[v]));
     }
   }
 }

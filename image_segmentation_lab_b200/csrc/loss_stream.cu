@@ -249,20 +249,7 @@ __global__ void __launch_bounds__(256, (V == 8 ? 2 : 3)) ce_fwd_kernel(const CeF
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int cls = ycl[v];
-      unsigned rem = __ballot_sync(0xffffffffu, cls >= 0);
-      while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int lc = __shfl_sync(0xffffffffu, cls, leader);
-        const bool mine = (cls == lc);
-        const float sum = warp_sum(mine ? pyv[v] : 0.f);
-        const unsigned mm = __ballot_sync(0xffffffffu, mine);
-        if (lane == leader) {
-          A_s[warp * C + lc] += sum;
-          T_s[warp * C + lc] += (float)__popc(mm);
-        }
-        rem &= ~mm;
-      }
+      onehot_bins_add(A_s + warp * C, T_s + warp * C, ycl[v], pyv[v], lane);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {

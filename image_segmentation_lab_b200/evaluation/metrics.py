@@ -33,6 +33,8 @@ def _common(tensors, device, allowed, fallback):
     dt = dts.pop() if len(dts) == 1 else None
     if dt is None or dt not in allowed:
         dt = fallback
+    if all(t.dtype == dt and t.device == device and t.is_contiguous() for t in tensors):
+        return tensors, dt            # the usual case: nothing to convert, no per-tensor dispatch
     out = []
     for t in tensors:
         if t.device != device or t.dtype != dt:
@@ -66,12 +68,16 @@ def areas_device(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num
     else:
         preds_c, pdt = _common(list(preds), dev, _lib.LABEL_DTYPES, torch.int64)
     chunk = lib.b200seg_confusion_chunk_pixels()
+    # per-image table {pred*, gt*, n_pixels, (h,w) of the logits, (H,W) of the ground truth} and the chunk prefix sum,
+    # built with a few vectorised passes (a 500-image sweep must not be bound by this loop)
     table = np.zeros((n, 5), dtype=np.int64)
-    prefix = np.zeros(n + 1, dtype=np.int64)
+    table[:, 0] = np.fromiter((p.data_ptr() for p in preds_c), dtype=np.int64, count=n)
+    table[:, 1] = np.fromiter((g.data_ptr() for g in gts_c), dtype=np.int64, count=n)
+    npx = np.fromiter((g.numel() for g in gts_c), dtype=np.int64, count=n)
+    table[:, 2] = npx
     resized = False
-    for i, (p, g) in enumerate(zip(preds_c, gts_c)):
-        npx = g.numel()
-        if from_logits:
+    if from_logits:
+        for i, (p, g) in enumerate(zip(preds_c, gts_c)):
             if p.dim() == 4:
                 assert p.size(0) == 1, 'each prediction must be (1,C,H,W)'
             assert p.shape[-3] == Cn, 'logits have %d classes, evaluator has %d' % (p.shape[-3], Cn)
@@ -80,12 +86,11 @@ def areas_device(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num
                 resized = True
             table[i, 3] = int(p.shape[-2]) | (int(p.shape[-1]) << 32)
             table[i, 4] = int(g.shape[-2]) | (int(g.shape[-1]) << 32)
-        else:
-            assert p.numel() == npx, 'prediction / ground-truth size mismatch'
-        table[i, 0] = p.data_ptr()
-        table[i, 1] = g.data_ptr()
-        table[i, 2] = npx
-        prefix[i + 1] = prefix[i] + (npx + chunk - 1) // chunk
+    else:
+        pnum = np.fromiter((p.numel() for p in preds_c), dtype=np.int64, count=n)
+        assert (pnum == npx).all(), 'prediction / ground-truth size mismatch'
+    prefix = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum((npx + chunk - 1) // chunk, out=prefix[1:])
     total_chunks = int(prefix[n])
     with torch.cuda.device(dev):
         meta = torch.from_numpy(np.concatenate([table.reshape(-1), prefix])).to(dev, non_blocking=True)
