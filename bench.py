@@ -211,6 +211,7 @@ def b200_main(args):
     else:
         raise RuntimeError('bench.py needs a CUDA device: the B200 path has no CPU fallback')
     dev = torch.device('cuda', local)
+    numa_bound = D.bind_to_gpu_numa_node(local) if world > 1 else False   # before any pinned allocation
     lib = B.load_library()
     peak, peak_kind = hbm_peak()
     K, W = args.steps, max(args.warmup, 3)
@@ -375,7 +376,9 @@ def b200_main(args):
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': dict(workload_config(), l2='ring of %d input sets (%.0f MB) > 126 MB L2; one CUDA graph per set' % (
-                R, R * (xs[0].numel() * 4 + ys[0].numel() * 8) / 1e6), collective='1 all_reduce(8 doubles)/step on a side stream'
+                R, R * (xs[0].numel() * 4 + ys[0].numel() * 8) / 1e6),
+                cpu_affinity='GPU-local NUMA node (NVML)' if numa_bound else 'inherited',
+                collective='1 all_reduce(8 doubles)/step on a side stream'
                 if world > 1 else 'none (single GPU)'),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,

@@ -36,6 +36,30 @@ def init_from_env(backend: Optional[str] = None, device: Optional[torch.device] 
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that pinned host buffers allocated afterwards
+    (first touch) and the copy threads sit on the GPU's NUMA node: with one process per GPU all ranks otherwise share one
+    socket's memory path for their host-to-device traffic. Returns False (and changes nothing) when NVML or
+    sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous ceil split: rank r owns [r*ceil(n/w), min(n, (r+1)*ceil(n/w)))."""
     per = (n_items + world - 1) // world
