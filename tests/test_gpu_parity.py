@@ -336,6 +336,56 @@ def test_bulk_pipeline_single_pass_shapes(B):
         assert abs(float(out['acc_seg']) - float(acc)) <= (1e-3 if dtype == torch.float32 else 0.5)
 
 
+
+def test_cabi_output_buffers_have_no_out_of_bounds_writes(B):
+    """Every output / workspace buffer of the single-pass entries sits between canary words (compute-sanitizer is not
+    available on the GPU pool): resize-fused cell kernel + combine, and the bulk-copy pipeline with a partial last tile."""
+    import ctypes as C
+    from image_segmentation_lab_b200 import _lib
+    lib = B.load_library()
+    dev = torch.device('cuda', 0)
+    stream = _lib.stream_ptr(dev)
+    G = 4096                                    # guard floats on each side (16 KB: keeps the interior 16-byte aligned)
+
+    def guarded(n_floats, dtype=torch.float32):
+        buf = torch.full((n_floats + 2 * G,), 12345.0, dtype=torch.float32, device=dev)
+        return buf, buf[G:G + n_floats]
+
+    def check(buf, n_floats, what):
+        assert bool((buf[:G] == 12345.0).all()) and bool((buf[G + n_floats:] == 12345.0).all()), what + ': guard overwritten'
+
+    for (N, Cc, h, w, S) in ((2, 19, 9, 13, 8), (1, 5, 3, 2, 16), (3, 21, 6, 5, 4), (2, 21, 40, 52, 1), (1, 33, 20, 12, 1)):
+        H, W = h * S, w * S
+        x = synth_logits((N, Cc, h, w), 5, device='cuda')
+        y = synth_labels((N, H, W), Cc, 5, ignore_index=255, block=3, device='cuda')
+        gbuf, grad = guarded(N * Cc * h * w)
+        sbuf, stats = guarded(16)
+        nbytes = lib.b200seg_loss_fused_workspace_bytes(N, Cc, h, w, H, W, 0) if S > 1 else 0
+        wbuf, ws = guarded(max(nbytes // 4, 4))
+        fu = _lib.LossFusedDesc()
+        fd = fu.fwd
+        fd.logits = x.data_ptr(); fd.labels = y.data_ptr()
+        fd.logit_dtype = _lib.F32; fd.label_dtype = _lib.L_I64
+        fd.N, fd.C, fd.h, fd.w, fd.H, fd.W = N, Cc, h, w, H, W
+        fd.flags = _lib.WANT_CE | _lib.WANT_ACC
+        fd.ignore_index = 255; fd.acc_has_ignore = 1; fd.acc_ignore_index = 255
+        fd.dice_exponent = 2.0; fd.ce_loss_weight = 1.0
+        fd.stats = stats.data_ptr()
+        fu.grad_scale_host = 1.0 / (N * H * W)
+        fu.grad_logits = grad.data_ptr()
+        fu.workspace = ws.data_ptr() if S > 1 else None
+        _lib.check(lib.b200seg_loss_fused_fwdbwd(C.byref(fu), stream))
+        torch.cuda.synchronize()
+        check(gbuf, N * Cc * h * w, 'grad S=%d' % S)
+        check(sbuf, 16, 'stats S=%d' % S)
+        check(wbuf, max(nbytes // 4, 4), 'workspace S=%d' % S)
+        # and the result is the oracle's gradient
+        xo = x.clone().requires_grad_(True)
+        full = O.resize(xo, size=(H, W), mode='bilinear', align_corners=False) if S > 1 else xo
+        O.cross_entropy_loss_module(full, y, ignore_index=255).backward()
+        assert rel_err(grad.view(N, Cc, h, w), xo.grad) <= GRAD_TOL
+
+
 def test_config3_ade20k_shape(B):
     """BASELINE config 3 (batch reduced to 2 for the oracle's 150-iteration Python loop): 150 classes, 512x512, bf16,
     class-weighted CE + Dice(loss_weight=3)."""
