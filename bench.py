@@ -332,20 +332,23 @@ def b200_main(args):
                 host_loss.append(r['loss_ce'].item())  # D2H read of the step's result (synchronises, as parse_losses does)
 
         run(4)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run(e2e_steps)
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return world * px_step * e2e_steps / float(tt.item()) / 1e6, xh[0].numel() * 4 + yh[0].numel() * yh[0].element_size()
+        vals = []
+        for _ in range(3):      # host-timed and PCIe-bound: three repeats, the median is reported (all three are kept)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run(e2e_steps)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            vals.append(world * px_step * e2e_steps / float(tt.item()) / 1e6)
+        return sorted(vals)[1], xh[0].numel() * 4 + yh[0].numel() * yh[0].element_size(), vals
 
-    e2e_value, h2d = e2e_run(torch.int64)
+    e2e_value, h2d, e2e_runs = e2e_run(torch.int64)
     # same loop with the label maps kept uint8 on the host (the kernels read u8 directly): 8x fewer label bytes over PCIe
-    e2e_u8_value, h2d_u8 = e2e_run(torch.uint8)
+    e2e_u8_value, h2d_u8, _ = e2e_run(torch.uint8)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- dominant kernel alone (C ABI, CUDA events on the launching stream)
@@ -382,8 +385,9 @@ def b200_main(args):
                 if world > 1 else 'none (single GPU)'),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                    'steps': e2e_steps, 'note': 'pinned host logits + int64 labels copied every step on a copy stream (double-'
-                                                'buffered, overlapping the previous step), loss read back every step; PCIe-bound',
+                    'steps': e2e_steps, 'repeats_mpix_s': [round(v, 1) for v in e2e_runs], 'note': 'pinned host logits + int64 labels copied every step on a copy stream (double-'
+                                                'buffered, overlapping the previous step), loss read back every step; PCIe-bound (38.5 MB at the '
+                                                'measured 54 GB/s pinned H2D rate = 0.71 ms/step = 5.9 Gpix/s); median of 3 repeats',
                     'uint8_labels': {'value': e2e_u8_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d_u8,
                                      'note': 'same step with the label maps kept uint8 on the host (read directly by the kernels)'}},
             'gpu_launches': int(launches_per_step * K),
