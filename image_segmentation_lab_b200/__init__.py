@@ -5,6 +5,7 @@ HanHan-TR/Image_Segmentation_lab as hand-written sm_100a CUDA behind the referen
     CrossEntropyLoss, cross_entropy       models/losses/cross_entropy_loss.py
     DiceLoss                              models/losses/dice_loss.py
     TverskyLoss                           models/losses/tversky_loss.py
+    LovaszLoss                            models/losses/lovasz_loss.py
     accuracy, Accuracy                    models/losses/accuracy.py
     SegEvaluator                          core/evaluation/metrics.py
     fused_resize_losses, B200DecodeHeadLossMixin   models/decode_heads/decode_head.py:261-321 (fused)
@@ -17,7 +18,7 @@ from . import distributed, registry
 from ._lib import launch_count, lib_path, load as load_library
 from .evaluation import SegEvaluator, areas_device
 from .fused import B200DecodeHeadLossMixin, fused_resize_losses
-from .losses import (Accuracy, CrossEntropyLoss, DiceLoss, TverskyLoss, accuracy, cross_entropy, dice_loss, get_class_weight,
+from .losses import (Accuracy, CrossEntropyLoss, DiceLoss, LovaszLoss, TverskyLoss, accuracy, cross_entropy, dice_loss, get_class_weight,
                      reduce_loss, weight_reduce_loss, weighted_loss)
 from .ops import Upsample, add_prefix, resize
 from .train_utils import parse_losses
@@ -25,7 +26,7 @@ from .train_utils import parse_losses
 __version__ = '0.1.0'
 
 __all__ = [
-    'resize', 'Upsample', 'add_prefix', 'CrossEntropyLoss', 'cross_entropy', 'DiceLoss', 'dice_loss', 'TverskyLoss', 'accuracy',
+    'resize', 'Upsample', 'add_prefix', 'CrossEntropyLoss', 'cross_entropy', 'DiceLoss', 'dice_loss', 'TverskyLoss', 'LovaszLoss', 'accuracy',
     'Accuracy', 'SegEvaluator', 'areas_device', 'fused_resize_losses', 'B200DecodeHeadLossMixin', 'registry',
     'distributed', 'get_class_weight', 'reduce_loss', 'weight_reduce_loss', 'weighted_loss', 'load_library',
     'lib_path', 'launch_count', 'parse_losses',

@@ -20,7 +20,7 @@ MODE_DICE, MODE_TVERSKY = 0, 1
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -102,6 +102,30 @@ class BceDesc(C.Structure):
     ]
 
 
+class LovaszDesc(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("labels", C.c_void_p), ("lse", C.c_void_p), ("class_weight", C.c_void_p),
+        ("logit_dtype", C.c_int32), ("label_dtype", C.c_int32), ("N", C.c_int32), ("C", C.c_int32),
+        ("HW", C.c_int64), ("ignore_index", C.c_int64),
+        ("has_ignore", C.c_int32), ("binary", C.c_int32), ("per_image", C.c_int32), ("only_present", C.c_int32),
+        ("classes_host", C.POINTER(C.c_int32)), ("n_classes", C.c_int32), ("reduction", C.c_int32),
+        ("has_avg_factor", C.c_int32), ("loss_weight", C.c_float),
+        ("avg_factor", C.c_double),
+        ("lab16", C.c_void_p), ("G", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("seg_stats", C.c_void_p), ("out", C.c_void_p), ("coef", C.c_void_p),
+    ]
+
+
+class LovaszBwdDesc(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("lse", C.c_void_p), ("lab16", C.c_void_p), ("G", C.c_void_p), ("coef", C.c_void_p),
+        ("grad_out", C.c_void_p), ("grad_logits", C.c_void_p),
+        ("logit_dtype", C.c_int32), ("N", C.c_int32), ("C", C.c_int32),
+        ("binary", C.c_int32), ("per_image", C.c_int32), ("grad_per_group", C.c_int32),
+        ("HW", C.c_int64),
+    ]
+
+
 class Image(C.Structure):
     _fields_ = [
         ("pred", C.c_void_p), ("gt", C.c_void_p), ("n_pixels", C.c_int64),
@@ -131,6 +155,9 @@ SYMBOLS = [
      [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _i64, C.POINTER(_i32), _i32, _i32, _f, _p, _p]),
     ("b200seg_bce_fwd", C.c_int, [C.POINTER(BceDesc), _p]),
     ("b200seg_bce_bwd", C.c_int, [C.POINTER(BceDesc), _p]),
+    ("b200seg_lovasz_workspace_bytes", _i64, [_i64, _i32]),
+    ("b200seg_lovasz_fwd", C.c_int, [C.POINTER(LovaszDesc), _p]),
+    ("b200seg_lovasz_bwd", C.c_int, [C.POINTER(LovaszBwdDesc), _p]),
     ("b200seg_last_error", C.c_char_p, []),
     ("b200seg_abi_version", _i32, []),
     ("b200seg_launch_count", _i64, []),

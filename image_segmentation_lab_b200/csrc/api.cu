@@ -40,6 +40,9 @@ long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac);
 int up_combine_dispatch(const void* ws, void* grad, int dtype, int N, int C, int h, int w, float scale_host,
                         const float* grad_out, int use_nvalid, const uint64_t* stats, cudaStream_t st);
 int scale_inplace_dispatch(void* x, int dtype, long long n, const float* g, cudaStream_t st);
+int lovasz_fwd_dispatch(const b200seg_lovasz_desc* d, cudaStream_t st);
+int lovasz_bwd_dispatch(const b200seg_lovasz_bwd_desc* d, cudaStream_t st);
+long long lovasz_workspace_bytes(long long seg_len, int pairs);
 bool bulk_supported(const void* logits, const void* labels, const void* grad, int logit_dtype, int label_dtype, int C,
                     long long HW, bool has_pixel_weight);
 
@@ -192,6 +195,51 @@ extern "C" int b200seg_scale_inplace(void* x, int32_t dtype, int64_t n, const fl
   B200SEG_REQUIRE(x && g && n >= 0, "scale_inplace: bad arguments");
   if (n == 0) return 0;
   return scale_inplace_dispatch(x, dtype, n, g, (cudaStream_t)stream);
+}
+
+extern "C" int64_t b200seg_lovasz_workspace_bytes(int64_t seg_len, int32_t pairs) {
+  return lovasz_workspace_bytes(seg_len, pairs);
+}
+
+extern "C" int b200seg_lovasz_fwd(const b200seg_lovasz_desc* d, void* stream) {
+  B200SEG_REQUIRE(d != nullptr, "lovasz_fwd: NULL descriptor");
+  B200SEG_REQUIRE(d->N >= 0 && d->N <= 65535 && d->C >= 1 && d->HW >= 0, "lovasz_fwd: bad shape N=%d C=%d HW=%lld", d->N, d->C,
+                  (long long)d->HW);
+  B200SEG_REQUIRE(d->logit_dtype == B200SEG_F32 || d->logit_dtype == B200SEG_BF16 || d->logit_dtype == B200SEG_F16,
+                  "lovasz_fwd: unsupported logit dtype %d", d->logit_dtype);
+  B200SEG_REQUIRE(d->label_dtype >= B200SEG_L_U8 && d->label_dtype <= B200SEG_L_F64, "lovasz_fwd: unsupported label dtype %d",
+                  d->label_dtype);
+  B200SEG_REQUIRE(!d->binary || d->C == 1, "lovasz_fwd: the binary hinge takes single-channel logits (C=%d)", d->C);
+  B200SEG_REQUIRE(d->binary || d->C <= 32766, "lovasz_fwd: at most 32766 classes");
+  B200SEG_REQUIRE(d->reduction >= B200SEG_RED_NONE && d->reduction <= B200SEG_RED_SUM, "lovasz_fwd: bad reduction %d", d->reduction);
+  B200SEG_REQUIRE(!(d->per_image && d->has_avg_factor && d->reduction == B200SEG_RED_SUM),
+                  "avg_factor can not be used with reduction=\"sum\"");   // models/losses/utils.py:78-79
+  B200SEG_REQUIRE(d->seg_stats && d->out, "lovasz_fwd: NULL seg_stats / out");
+  const long long seg_len = (long long)(d->per_image ? 1 : d->N) * d->HW;
+  B200SEG_REQUIRE(seg_len < 2147483647LL, "lovasz_fwd: segment of %lld pixels exceeds 2^31-1", seg_len);
+  if (d->N > 0 && d->HW > 0) {
+    B200SEG_REQUIRE(d->logits && d->labels && d->lab16 && d->workspace, "lovasz_fwd: NULL tensor");
+    B200SEG_REQUIRE(d->binary || d->lse, "lovasz_fwd: the multi-class loss needs the per-pixel log-sum-exp");
+    B200SEG_REQUIRE((reinterpret_cast<uintptr_t>(d->workspace) & 255u) == 0, "lovasz_fwd: workspace must be 256-byte aligned");
+    if (!d->binary && d->classes_host) {
+      B200SEG_REQUIRE(d->n_classes >= 1, "lovasz_fwd: empty class list");
+      for (int j = 0; j < d->n_classes; ++j)
+        B200SEG_REQUIRE(d->classes_host[j] >= 0 && d->classes_host[j] < d->C, "lovasz_fwd: class %d outside [0,%d)",
+                        d->classes_host[j], d->C);
+    }
+  }
+  return lovasz_fwd_dispatch(d, (cudaStream_t)stream);
+}
+
+extern "C" int b200seg_lovasz_bwd(const b200seg_lovasz_bwd_desc* d, void* stream) {
+  B200SEG_REQUIRE(d != nullptr, "lovasz_bwd: NULL descriptor");
+  B200SEG_REQUIRE(d->N >= 0 && d->N <= 65535 && d->C >= 1 && d->HW >= 0, "lovasz_bwd: bad shape");
+  B200SEG_REQUIRE(d->logit_dtype == B200SEG_F32 || d->logit_dtype == B200SEG_BF16 || d->logit_dtype == B200SEG_F16,
+                  "lovasz_bwd: unsupported logit dtype %d", d->logit_dtype);
+  if (d->N == 0 || d->HW == 0) return 0;
+  B200SEG_REQUIRE(d->logits && d->lab16 && d->G && d->coef && d->grad_logits, "lovasz_bwd: NULL tensor");
+  B200SEG_REQUIRE(d->binary || d->lse, "lovasz_bwd: NULL lse");
+  return lovasz_bwd_dispatch(d, (cudaStream_t)stream);
 }
 
 extern "C" int b200seg_topk_counts(const void* logits, const void* labels, int32_t logit_dtype, int32_t label_dtype,

@@ -5,15 +5,15 @@ The reference selects losses by name: ``loss_decode=dict(type='CrossEntropyLoss'
 refuses duplicate keys (register.py:15-18), so a drop-in either registers under new names or
 overwrites the class-level ``_storage`` entry. Both are offered.
 """
-from .losses import CrossEntropyLoss, DiceLoss, TverskyLoss
+from .losses import CrossEntropyLoss, DiceLoss, LovaszLoss, TverskyLoss
 
-B200_LOSSES = {'CrossEntropyLoss': CrossEntropyLoss, 'DiceLoss': DiceLoss, 'TverskyLoss': TverskyLoss}
+B200_LOSSES = {'CrossEntropyLoss': CrossEntropyLoss, 'DiceLoss': DiceLoss, 'TverskyLoss': TverskyLoss, 'LovaszLoss': LovaszLoss}
 
 
 def install(loss_registry, override=True, prefix='B200'):
     """Make the fused losses reachable through the reference's ``LOSS`` registry.
 
-    override=True : ``LOSS._storage['CrossEntropyLoss'|'DiceLoss'|'TverskyLoss']`` now build this package's classes, so existing
+    override=True : ``LOSS._storage['CrossEntropyLoss'|'DiceLoss'|'TverskyLoss'|'LovaszLoss']`` now build this package's classes, so existing
                     network configs run on the fused kernels unchanged.
     always        : also registers ``B200CrossEntropyLoss`` / ``B200DiceLoss`` for configs that opt in by name.
     Returns the dict of names installed.

@@ -15,6 +15,8 @@
  *                                      TverskyLoss.forward models/losses/tversky_loss.py:112-134 (+ :24-68)
  *                                      accuracy (top-1)    models/losses/accuracy.py:6-61
  *   b200seg_loss_fused_fwdbwd        the same chain plus its autograd backward in one pass
+ *   b200seg_lovasz_fwd / _bwd        LovaszLoss.forward models/losses/lovasz_loss.py:272-298 (+ lovasz_grad :26-39,
+ *                                    lovasz_softmax(_flat) :135-231, lovasz_hinge(_flat) :69-132) and its autograd backward
  *   b200seg_confusion_labels         SegEvaluator.intersect_and_union core/evaluation/metrics.py:210-270
  *   b200seg_confusion_logits         SegEvaluator.process argmax :101-107 + intersect_and_union
  *
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 9
+#define B200SEG_ABI_VERSION 10
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -235,6 +237,58 @@ typedef struct b200seg_bce_desc {
 } b200seg_bce_desc;
 int b200seg_bce_fwd(const b200seg_bce_desc* d, void* stream);   /* zeroes stats, then accumulates     */
 int b200seg_bce_bwd(const b200seg_bce_desc* d, void* stream);   /* reads stats[1] when use_nvalid     */
+
+/* Lovasz-Softmax ('multi_class') and Lovasz hinge ('binary') losses, models/losses/lovasz_loss.py:26-298.
+ * One SEGMENT per (image group, class): the whole batch, or one image when per_image. Per segment: sort keys from the
+ * logits row and the per-pixel log-sum-exp, a device radix sort (descending errors), a scan of the foreground bits in
+ * sorted order, the Jaccard increments in closed form, loss_c = sum e_i g_i and dloss_c/dp_c scattered into G.      */
+typedef struct b200seg_lovasz_desc {
+  const void*  logits;          /* multi-class: (N,C,HW) RAW logits (the soft-max of :281-282 is fused in);
+                                 * binary: (N,HW) logits (C must be 1)                                              */
+  const void*  labels;          /* (N,HW) label_dtype                                                               */
+  const float* lse;             /* (N,HW) f32 per-pixel log-sum-exp of the logits (b200seg_loss_fwd with
+                                 * B200SEG_WANT_LSE); unused (may be NULL) for binary                                */
+  const float* class_weight;    /* (C) f32 or NULL (:165-166); ignored for binary (a placeholder there, :103-104)   */
+  int32_t logit_dtype, label_dtype;
+  int32_t N, C;
+  int64_t HW;
+  int64_t ignore_index;
+  int32_t has_ignore;           /* ignore_index=None -> 0 (:44-45, :61-62)                                          */
+  int32_t binary;               /* loss_type == 'binary'                                                            */
+  int32_t per_image;            /* :119-126, :217-226                                                               */
+  int32_t only_present;         /* classes == 'present' (:153-154); 0 for 'all' or an explicit list                 */
+  const int32_t* classes_host;  /* HOST array of class ids to average (classes=[...]) or NULL = every class         */
+  int32_t n_classes;
+  int32_t reduction;            /* B200SEG_RED_* — used only when per_image (weight_reduce_loss over the images)    */
+  int32_t has_avg_factor;
+  float   loss_weight;
+  double  avg_factor;
+  int16_t* lab16;               /* out (N,HW): compact class ids (-1 ignored), kept for the backward                */
+  float*   G;                   /* out: multi-class (N,C,HW) f32, binary (N,HW) f32: dloss_seg/dp (resp. /dz), unscaled;
+                                 * NULL = forward only (the sort then moves keys only)                              */
+  void*    workspace;           /* b200seg_lovasz_workspace_bytes(segment length, pairs) bytes, 256-byte aligned    */
+  int64_t  workspace_bytes;
+  double*  seg_stats;           /* (n_groups, C or 1, 2) doubles [loss, #foreground + 1], zeroed by the call        */
+  float*   out;                 /* per_image && reduction none: n_groups floats; else 1 float (loss_weight applied) */
+  float*   coef;                /* (n_groups, C or 1) f32: d out / d loss_seg, for the backward; or NULL            */
+} b200seg_lovasz_desc;
+/* seg_len = HW (per_image) or N*HW; pairs = 1 when G != NULL or binary. Needs a CUDA device (queries the sort). */
+int64_t b200seg_lovasz_workspace_bytes(int64_t seg_len, int32_t pairs);
+int b200seg_lovasz_fwd(const b200seg_lovasz_desc* d, void* stream);
+
+typedef struct b200seg_lovasz_bwd_desc {
+  const void*    logits;
+  const float*   lse;           /* multi-class only */
+  const int16_t* lab16;
+  const float*   G;
+  const float*   coef;
+  const float*   grad_out;      /* device f32: scalar, or one per image group when grad_per_group; NULL = 1         */
+  void*          grad_logits;   /* same shape and dtype as logits, fully overwritten (0 on ignored pixels)          */
+  int32_t logit_dtype, N, C;
+  int32_t binary, per_image, grad_per_group;
+  int64_t HW;
+} b200seg_lovasz_bwd_desc;
+int b200seg_lovasz_bwd(const b200seg_lovasz_bwd_desc* d, void* stream);
 
 /* Bilinear resize, ATen semantics (torch/include/ATen/native/UpSample.h:271-312,442-476). */
 int b200seg_resize_bilinear_fwd(const void* in, void* out, int32_t dtype, int32_t NC, int32_t h, int32_t w,

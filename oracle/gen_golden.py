@@ -281,6 +281,76 @@ def build(out_dir=OUT_DIR):
         data[name + '/grad'] = x.grad.numpy()
         manifest['cases'].append(dict(name=name, kind='tversky', shape=shape, kw=case['kw']))
 
+    # ---- LovaszLoss (models/losses/lovasz_loss.py:26-312); appended last. Small segments: the reference's fp32 Jaccard
+    # differences are accurate here (their absolute noise of ~6e-8 is far below increments of ~1/100), and no two errors
+    # of a segment are closer than 1e-6 (checked below), so the sorted order — hence the gradient — is well defined.
+    lov_cases = [
+        dict(name='lovasz_present', shape=(2, 5, 8, 12), kw=dict(reduction='none')),
+        dict(name='lovasz_all_weighted', shape=(2, 5, 8, 12), kw=dict(reduction='none', classes='all', loss_weight=2.0,
+                                                                      class_weight=[0.5, 1.0, 1.5, 2.0, 0.25])),
+        dict(name='lovasz_absent_class', shape=(2, 6, 8, 8), max_label=4, kw=dict(reduction='none')),
+        dict(name='lovasz_all_absent_class', shape=(2, 6, 8, 8), max_label=4, kw=dict(reduction='none', classes='all')),
+        dict(name='lovasz_list', shape=(2, 5, 8, 12), kw=dict(reduction='none', classes=[1, 3])),
+        dict(name='lovasz_per_image_mean', shape=(3, 4, 8, 8), kw=dict(per_image=True, reduction='mean')),
+        dict(name='lovasz_per_image_sum', shape=(3, 4, 8, 8), kw=dict(per_image=True, reduction='sum', class_weight=[1, 2, 3, 4.0])),
+        dict(name='lovasz_per_image_none', shape=(3, 4, 8, 8), kw=dict(per_image=True, reduction='none')),
+        dict(name='lovasz_per_image_avg', shape=(3, 4, 8, 8), avg_factor=2.5, kw=dict(per_image=True, reduction='mean')),
+        dict(name='lovasz_c40', shape=(1, 40, 12, 16), kw=dict(reduction='none')),
+        dict(name='lovasz_no_ignore', shape=(2, 3, 6, 10), ignore=None, kw=dict(reduction='none')),
+        dict(name='lovasz_hinge', shape=(2, 1, 8, 12), kw=dict(loss_type='binary', reduction='none')),
+        dict(name='lovasz_hinge_per_image', shape=(3, 1, 8, 8), kw=dict(loss_type='binary', per_image=True, reduction='mean',
+                                                                        loss_weight=0.5)),
+    ]
+    def _lovasz_gap(x, y, shape, ign, binary, per_image):
+        with torch.no_grad():
+            if binary:
+                err = [(1 - x[:, 0] * (2. * y.float() - 1))[y != 255]] if not per_image else \
+                    [(1 - x[i, 0] * (2. * y[i].float() - 1))[y[i] != 255] for i in range(shape[0])]
+            else:
+                p = torch.softmax(x, 1)
+                groups = [slice(i, i + 1) for i in range(shape[0])] if per_image else [slice(0, shape[0])]
+                err = []
+                for sl in groups:
+                    keep = (y[sl] != ign) if ign is not None else torch.ones_like(y[sl], dtype=torch.bool)
+                    for c in range(shape[1]):
+                        err.append(((y[sl] == c).float() - p[sl, c]).abs()[keep])
+            # margin of every adjacent pair of sorted errors over what two fp32 soft-max implementations can differ by
+            # (3e-6 relative, plus two ulps of 1.0 for errors of the form 1 - p): > 1 means the order is unambiguous
+            worst = float('inf')
+            for e in err:
+                if e.numel() > 1:
+                    v = torch.sort(e.abs()).values
+                    tol = 3e-6 * v[1:] + 2.4e-7 * (v[1:] > 0.5)
+                    worst = min(worst, float(((v[1:] - v[:-1]) / tol).min()))
+            return worst
+
+    for case in lov_cases:
+        name, shape = case['name'], case['shape']
+        binary = case['kw'].get('loss_type') == 'binary'
+        ign = case.get('ignore', 255)
+        ncls = 2 if binary else case.get('max_label', shape[1])
+        for _ in range(50):   # redraw until the sorted errors of every segment are separated (near-ties are common)
+            x = (torch.randn(shape, generator=g) * 2).requires_grad_(True)
+            y = _labels(g, shape[0], shape[2], shape[3], ncls, ign, 0.1)
+            gap = _lovasz_gap(x, y, shape, ign, binary, bool(case['kw'].get('per_image')))
+            if gap > 1.0:
+                break
+        mod = ref.LovaszLoss(**case['kw'])
+        loss = mod(x, y, avg_factor=case.get('avg_factor'), ignore_index=ign)
+        if loss.dim():
+            go = torch.rand(loss.shape, generator=g)
+            (loss * go).sum().backward()
+            data[name + '/grad_out'] = go.numpy()
+        else:
+            loss.backward()
+        assert gap > 1.0, (name, gap)
+        data[name + '/logits'] = x.detach().numpy()
+        data[name + '/labels'] = y.numpy()
+        data[name + '/loss'] = loss.detach().numpy()
+        data[name + '/grad'] = x.grad.numpy()
+        manifest['cases'].append(dict(name=name, kind='lovasz', shape=shape, kw=case['kw'], ignore=ign,
+                                      avg_factor=case.get('avg_factor'), order_margin=gap))
+
     os.makedirs(out_dir, exist_ok=True)
     np.savez_compressed(os.path.join(out_dir, 'hotpath_golden.npz'), **data)
     with open(os.path.join(out_dir, 'manifest.json'), 'w') as fh:

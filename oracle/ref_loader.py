@@ -60,7 +60,7 @@ def load():
         def get_string(self):
             return '\n'.join('%s: %s' % (k, v) for k, v in self.cols)
 
-    sys.modules['mmcv'] = _stub('mmcv')
+    sys.modules['mmcv'] = _stub('mmcv', is_list_of=lambda seq, t: isinstance(seq, list) and all(isinstance(x, t) for x in seq))
     sys.modules['prettytable'] = _stub('prettytable', PrettyTable=_PrettyTable)
     models = _stub('models')
     models.__path__ = []
@@ -79,6 +79,7 @@ def load():
         ce = _load('_ref_cross_entropy_loss', 'models/losses/cross_entropy_loss.py')
         dice = _load('_ref_dice_loss', 'models/losses/dice_loss.py')
         tv = _load('_ref_tversky_loss', 'models/losses/tversky_loss.py')
+        lov = _load('_ref_lovasz_loss', 'models/losses/lovasz_loss.py')
         acc = _load('_ref_accuracy', 'models/losses/accuracy.py')
         met = _load('_ref_metrics', 'core/evaluation/metrics.py')
     finally:
@@ -91,7 +92,7 @@ def load():
         resize=ops.resize, Upsample=ops.Upsample, add_prefix=ops.add_prefix,
         reduce_loss=lutils.reduce_loss, weight_reduce_loss=lutils.weight_reduce_loss, weighted_loss=lutils.weighted_loss,
         cross_entropy=ce.cross_entropy, binary_cross_entropy=ce.binary_cross_entropy, CrossEntropyLoss=ce.CrossEntropyLoss,
-        DiceLoss=dice.DiceLoss, TverskyLoss=tv.TverskyLoss, accuracy=acc.accuracy, Accuracy=acc.Accuracy, SegEvaluator=met.SegEvaluator)
+        DiceLoss=dice.DiceLoss, TverskyLoss=tv.TverskyLoss, LovaszLoss=lov.LovaszLoss, lovasz_grad=lov.lovasz_grad, accuracy=acc.accuracy, Accuracy=acc.Accuracy, SegEvaluator=met.SegEvaluator)
     _CACHE = ns
     return ns
 

@@ -58,6 +58,8 @@ int main(void) {
          sizeof(b200seg_loss_fused_desc), sizeof(b200seg_image), sizeof(b200seg_bce_desc));
   printf("%zu %zu %zu %zu\n", offsetof(b200seg_loss_desc, ignore_index), offsetof(b200seg_loss_desc, stats),
          offsetof(b200seg_loss_bwd_desc, grad_logits), offsetof(b200seg_loss_fused_desc, workspace));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(b200seg_lovasz_desc), sizeof(b200seg_lovasz_bwd_desc), offsetof(b200seg_lovasz_desc, avg_factor),
+         offsetof(b200seg_lovasz_desc, coef), offsetof(b200seg_lovasz_bwd_desc, HW));
   return 0;
 }
 '''
@@ -70,8 +72,10 @@ int main(void) {
     sizes = [int(x) for x in out]
     assert sizes[:6] == [ctypes.sizeof(_lib.LossDesc), ctypes.sizeof(_lib.FinalizeDesc), ctypes.sizeof(_lib.LossBwdDesc),
                          ctypes.sizeof(_lib.LossFusedDesc), ctypes.sizeof(_lib.Image), ctypes.sizeof(_lib.BceDesc)]
-    assert sizes[6:] == [_lib.LossDesc.ignore_index.offset, _lib.LossDesc.stats.offset,
-                         _lib.LossBwdDesc.grad_logits.offset, _lib.LossFusedDesc.workspace.offset]
+    assert sizes[6:10] == [_lib.LossDesc.ignore_index.offset, _lib.LossDesc.stats.offset,
+                           _lib.LossBwdDesc.grad_logits.offset, _lib.LossFusedDesc.workspace.offset]
+    assert sizes[10:] == [ctypes.sizeof(_lib.LovaszDesc), ctypes.sizeof(_lib.LovaszBwdDesc), _lib.LovaszDesc.avg_factor.offset,
+                          _lib.LovaszDesc.coef.offset, _lib.LovaszBwdDesc.HW.offset]
 
 
 def test_validation_errors_without_gpu():
@@ -84,6 +88,13 @@ def test_validation_errors_without_gpu():
     assert 'bad shape' in _lib.last_error()
     f = _lib.FinalizeDesc()
     assert lib.b200seg_loss_finalize(ctypes.byref(f), None) != 0
+    lv = _lib.LovaszDesc()
+    lv.N, lv.C, lv.HW, lv.binary = 2, 3, 16, 1
+    assert lib.b200seg_lovasz_fwd(ctypes.byref(lv), None) != 0
+    assert 'single-channel' in _lib.last_error()
+    lv.binary, lv.per_image, lv.has_avg_factor, lv.reduction = 0, 1, 1, _lib.RED_SUM
+    assert lib.b200seg_lovasz_fwd(ctypes.byref(lv), None) != 0
+    assert 'avg_factor can not be used' in _lib.last_error()
     assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 0) == 8 * 19 * 65 * 129 * 16
     assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 1) == 0   # align_corners -> general path
     assert lib.b200seg_loss_fused_workspace_bytes(8, 150, 64, 64, 512, 512, 0) == 0    # C > 32 -> composite path

@@ -76,14 +76,16 @@ def test_registry_install_and_build():
 
     installed = B.registry.install(FakeLoss, override=True)
     assert FakeLoss.get('CrossEntropyLoss') is B.CrossEntropyLoss and FakeLoss.get('B200DiceLoss') is B.DiceLoss
-    assert set(installed) == {'CrossEntropyLoss', 'DiceLoss', 'TverskyLoss', 'B200CrossEntropyLoss', 'B200DiceLoss',
-                              'B200TverskyLoss'}
+    assert set(installed) == {'CrossEntropyLoss', 'DiceLoss', 'TverskyLoss', 'LovaszLoss', 'B200CrossEntropyLoss', 'B200DiceLoss',
+                              'B200TverskyLoss', 'B200LovaszLoss'}
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         m = B.registry.build_loss(dict(type='CrossEntropyLoss', loss_weight=0.4, class_weight=[1.0, 2.0]))
     assert isinstance(m, B.CrossEntropyLoss) and m.loss_weight == 0.4
     with pytest.raises(KeyError):
-        B.registry.build_loss(dict(type='LovaszLoss'))
+        B.registry.build_loss(dict(type='FocalLoss'))
+    with pytest.raises(AssertionError):
+        B.registry.build_loss(dict(type='LovaszLoss'))   # per_image=False needs reduction='none' (lovasz_loss.py:271-273)
     with pytest.raises(TypeError):
         B.registry.build_loss('CrossEntropyLoss')
 

@@ -74,3 +74,21 @@ def test_argmax_matches_process(ref):
     g = torch.Generator().manual_seed(11)
     l = torch.randn((1, 7, 12, 9), generator=g)
     assert torch.equal(O.argmax_labels(l), torch.nn.functional.softmax(l, dim=1).argmax(dim=1).squeeze(0))
+
+
+@pytest.mark.parametrize('kw', [dict(reduction='none'), dict(reduction='none', classes='all', class_weight=[.5, 1, 1.5, 2, .25]),
+                                dict(reduction='none', classes=[0, 2]), dict(per_image=True), dict(per_image=True, reduction='sum'),
+                                dict(loss_type='binary', reduction='none'), dict(loss_type='binary', per_image=True)])
+def test_lovasz_bitwise(ref, kw):
+    g = torch.Generator().manual_seed(9)
+    binary = kw.get('loss_type') == 'binary'
+    x = (torch.randn((3, 1 if binary else 5, 7, 9), generator=g) * 2)
+    y = torch.randint(0, 2 if binary else 5, (3, 7, 9), generator=g)
+    y[torch.rand(y.shape, generator=g) < 0.15] = 255
+    xr = x.clone().requires_grad_(True)
+    a = ref.LovaszLoss(**kw)(xr, y, ignore_index=255)
+    a.sum().backward()
+    xo = x.clone().requires_grad_(True)
+    b = O.lovasz_loss_module(xo, y, ignore_index=255, **kw)
+    b.sum().backward()
+    assert torch.equal(a, b) and torch.equal(xr.grad, xo.grad)
