@@ -49,7 +49,9 @@ template <typename T, int V, int CW, int CH>
 __global__ void __launch_bounds__(256) dice_sumsq_kernel(const DiceParams p) {
   static_assert(CW % CH == 0 && CW <= 32, "class window");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.y;
+  // images and tiles are walked in REVERSE launch order: this kernel follows ce_fwd_kernel, which leaves the last
+  // ~100 MB it read (the tail of the batch) in the 126 MB L2
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int C = p.C;
   const long long HW = p.HW;
   const int c0 = (blockIdx.z * 8 + warp) * CW;          // first class of this warp
@@ -62,7 +64,8 @@ __global__ void __launch_bounds__(256) dice_sumsq_kernel(const DiceParams p) {
   for (int i = 0; i < CW; ++i) acc[i] = 0.f;
 
   if (ncls_w > 0) {
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      const int tile = p.tiles - 1 - t;
       const long long px0 = ((long long)tile * 32 + lane) * V;
       if (px0 >= HW) continue;
       float nl[V];
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
   if (px0 >= HW) return;
   const bool e2 = (p.dice_exponent == 2.f), e1 = (p.dice_exponent == 1.f);
   const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * HW;
-  float nl[V], dot[V];
+  float nl[V], nl2[V], dot[V];
   {
     float lse[V];
     if constexpr (V == 8) {
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
       load_vec<float, V>(p.lse + (size_t)n * HW + px0, lse);
     }
 #pragma unroll
-    for (int v = 0; v < V; ++v) { nl[v] = -lse[v] * kLog2e; dot[v] = 0.f; }
+    for (int v = 0; v < V; ++v) { nl[v] = -lse[v] * kLog2e; nl2[v] = 2.f * nl[v]; dot[v] = 0.f; }
   }
   const T* q = img + px0;
   for (int c0 = 0; c0 < C; c0 += CH) {
@@ -172,10 +175,13 @@ __global__ void __launch_bounds__(256) dice_dot_kernel(const DiceParams p) {
         unpack_raw<T, V>(raw[i], zz);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const float pr = ex2(fmaf(zz[v], kLog2e, nl[v]));
-          if (e2) dot[v] = fmaf(b * pr, pr, dot[v]);
-          else if (e1) dot[v] = fmaf(b, pr, dot[v]);
-          else dot[v] += pr > 0.f ? b * __powf(pr, p.dice_exponent) : 0.f;
+          if (e2) {   // p^2 = 2^(2 (z - lse) log2e): one EX2, no multiply
+            dot[v] = fmaf(b, ex2(fmaf(zz[v], 2.f * kLog2e, nl2[v])), dot[v]);
+          } else {
+            const float pr = ex2(fmaf(zz[v], kLog2e, nl[v]));
+            if (e1) dot[v] = fmaf(b, pr, dot[v]);
+            else dot[v] += pr > 0.f ? b * __powf(pr, p.dice_exponent) : 0.f;
+          }
         }
       }
     }
@@ -206,14 +212,15 @@ template <typename T, int V, int CH>
 __global__ void __launch_bounds__(256) dice_grad_kernel(const DiceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* beta_s = reinterpret_cast<float*>(smem_raw);
-  const int n = blockIdx.y;
+  // reverse launch order: dice_dot_kernel has just read the batch front to back, its tail is still in L2
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int C = p.C;
   const long long HW = p.HW;
   const float god = p.dice_grad_out ? __ldg(p.dice_grad_out) : 1.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     beta_s[c] = p.dice_exponent * god * __ldg(p.dice_coef + ((size_t)n * C + c) * 2 + 1);
   __syncthreads();
-  const long long px0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const long long px0 = ((long long)(gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x) * V;
   if (px0 >= HW) return;
   const bool e2 = (p.dice_exponent == 2.f), e1 = (p.dice_exponent == 1.f);
   const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;

@@ -298,11 +298,12 @@ __device__ __forceinline__ float ce_global_scale(const CeBwdParams& p) {
 template <typename T, int V, int CH, bool UP>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
   static_assert(!UP || V == 1, "resize-fused variant is one pixel per thread");
-  const int n = blockIdx.y;
+  // reverse launch order: the forward kernel read the batch front to back and its tail is still in the 126 MB L2
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int C = p.C;
   const long long HW = (long long)p.H * p.W;
   const long long hw = (long long)p.h * p.w;
-  const long long px0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const long long px0 = ((long long)(gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x) * V;
   if (px0 >= HW) return;
   const float G = ce_global_scale(p);
 
