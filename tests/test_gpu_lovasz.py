@@ -226,6 +226,23 @@ def test_lovasz_cityscapes_shape_properties(B):
     assert rel_err(l1, lo) <= LOSS_TOL
 
 
+def test_lovasz_in_decode_head_call(B):
+    """decode_head.py:283-293: CE + Lovasz on low-resolution logits through the fused call site (the resize is materialised
+    once for the Lovasz module; CE keeps its resize-fused single pass)."""
+    x = synth_logits((2, 7, 16, 24), 9, device='cuda', margin=False).requires_grad_(True)
+    y = synth_labels((2, 64, 96), 7, 9, ignore_index=255, block=8, device='cuda').unsqueeze(1)
+    out = B.fused_resize_losses(x, y, [B.CrossEntropyLoss(), B.LovaszLoss(reduction='none', loss_weight=0.5)], ignore_index=255)
+    assert list(out.keys()) == ['loss_ce', 'loss_lovasz', 'acc_seg']
+    (out['loss_ce'] + out['loss_lovasz']).backward()
+    xo = x.detach().double().requires_grad_(True)
+    full = O.resize(xo, size=(64, 96), mode='bilinear', align_corners=False)
+    ref_ce = O.cross_entropy_loss_module(full, y.squeeze(1), ignore_index=255)
+    ref_lv = O.lovasz_loss_module(full, y.squeeze(1), reduction='none', loss_weight=0.5, ignore_index=255, acc_dtype=torch.float64)
+    (ref_ce + ref_lv).backward()
+    assert rel_err(out['loss_ce'], ref_ce) <= LOSS_TOL and rel_err(out['loss_lovasz'], ref_lv) <= LOSS_TOL
+    _grad_gate('head', x.grad, xo.grad)
+
+
 def test_lovasz_cuda_graph(B):
     x = synth_logits((2, 6, 32, 48), 5, device='cuda', margin=False)
     y = synth_labels((2, 32, 48), 6, 5, ignore_index=255, block=4, device='cuda')

@@ -23,3 +23,10 @@ for i in range(3): fwd(i); fb(i)
 a=bench.timed_events(fwd,10); b=bench.timed_events(fb,10)
 el=16*150*512*512*2; px=16*512*512
 print("C3 fwd %.3f ms (%.2f)  fwd+bwd %.3f ms (%.2f)"%(a,roof(el+px*8,a),b,roof(3*el+2*px*8,b)))
+if os.environ.get("AB_KERNELS", "1") == "1":   # per-kernel device times (CUPTI through torch.profiler)
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(4): fb(i)
+        torch.cuda.synchronize()
+    rows=[(e.key, e.device_time_total/max(e.count,1), e.count) for e in prof.key_averages() if e.device_time_total>0]
+    for k,t,c in sorted(rows,key=lambda r:-r[1])[:8]: print("  %8.1f us x%d  %s"%(t,c,k[:110]))

@@ -48,3 +48,17 @@ if __name__ == '__main__':
         run(8, 19, 512, 1024, torch.float32, per_image=True)
         run(32, 21, 512, 512, torch.float32)
         run(16, 150, 512, 512, torch.bfloat16)
+    if len(sys.argv) == 1:   # per-kernel device times of one forward+backward (CUPTI through torch.profiler)
+        from torch.profiler import ProfilerActivity, profile
+        x = synth_logits((8, 19, 512, 1024), 2, device='cuda', margin=False).requires_grad_(True)
+        y = synth_labels((8, 512, 1024), 19, 2, ignore_index=255, device='cuda')
+        mod = B.LovaszLoss(reduction='none')
+        mod(x, y, ignore_index=255).backward()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            x.grad = None
+            mod(x, y, ignore_index=255).backward()
+            torch.cuda.synchronize()
+        rows = [(e.key, e.device_time_total, e.count) for e in prof.key_averages() if e.device_time_total > 0]
+        for k, t, c in sorted(rows, key=lambda r: -r[1])[:12]:
+            print('  %9.1f us total  x%-4d %s' % (t, c, k[:120]))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small, fixed invocation of every hot kernel — the command line profiled with ncu (profiles/README.md).
 
-    python tools/prof_kernels.py [c2] [c3] [c4] [c5]      (default: all)
+    python tools/prof_kernels.py [c2] [c3] [c4] [c5] [lovasz]      (default: all)
 
 Sizes are the BASELINE configs with reduced batch so that ncu's ~40 replays per kernel stay short; the
 per-launch geometry (tile shapes, classes, dtypes) is that of the full configs.
@@ -20,7 +20,7 @@ import image_segmentation_lab_b200 as B  # noqa: E402
 
 def main():
     warnings.simplefilter('ignore')
-    which = set(sys.argv[1:]) or {'c2', 'c3', 'c4', 'c5'}
+    which = set(sys.argv[1:]) or {'c2', 'c3', 'c4', 'c5', 'lovasz'}
     dev = torch.device('cuda', 0)
     reps = int(os.environ.get('PROF_REPS', '2'))
     if 'c2' in which:
@@ -57,6 +57,13 @@ def main():
         logits = [bench.make_logits((1, 19, 1024, 2048), 60 + i, device=dev) for i in range(8)]
         for _ in range(reps):
             B.areas_device(logits, gts[:8], 19, 255, from_logits=True)
+    if 'lovasz' in which:   # Lovasz-Softmax at the config-2 label resolution, 4 classes' worth of segments
+        x = bench.make_logits((8, 4, 512, 1024), 4, device=dev).requires_grad_(True)
+        y = bench.make_labels((8, 512, 1024), 4, 4, device=dev)
+        lv = B.LovaszLoss(reduction='none')
+        for _ in range(reps):
+            x.grad = None
+            lv(x, y, ignore_index=255).backward()
     torch.cuda.synchronize()
     print('prof_kernels ok, launches =', B.launch_count())
 
