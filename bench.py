@@ -561,6 +561,34 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     bench_losses('C4_voc_fp32_ce_two_pass', (32, 21, 512, 512), torch.float32, ce2, iters=10,
                  plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
 
+    # ---- "next" row f4': LovaszLoss at the config-2 label resolution (19 class segments of 4 M pixels each)
+    try:
+        xl = make_logits((8, 19, 512, 1024), 350, device=dev).requires_grad_(True)
+        yl = make_labels((8, 512, 1024), 19, 350, 255, device=dev)
+        lov = B.LovaszLoss(reduction='none')
+
+        def lv_fwd(i):
+            with torch.no_grad():
+                lov(xl, yl, ignore_index=255)
+
+        def lv_fb(i):
+            xl.grad = None
+            lov(xl, yl, ignore_index=255).backward()
+
+        lv_fwd(0); lv_fb(0)
+        a, b = timed_events(lv_fwd, 5), timed_events(lv_fb, 5)
+        px = 8 * 512 * 1024
+        out['lovasz_softmax_cityscapes_shape'] = {
+            'shape': [8, 19, 512, 1024], 'dtype': 'float32', 'pixels': px,
+            'fwd': dict(ms=a, mpix_s=px / a / 1e3), 'fwd_bwd': dict(ms=b, mpix_s=px / b / 1e3),
+            'plan': 'ce_fwd_kernel (lse) + per class: lovasz_keys_kernel, radix sort (CUB, L2-resident segment), '
+                    'lovasz_count/tilescan/grad kernels; lovasz_finalize_kernel; lovasz_bwd_kernel',
+            'note': 'sort-bound (4 digit passes over 4 M key/index pairs per class); no HBM roofline is claimed for it'}
+        del xl, yl
+        torch.cuda.empty_cache()
+    except Exception as e:   # the extra line must never cost the headline
+        out['lovasz_softmax_cityscapes_shape'] = {'error': repr(e)}
+
     # ---- C5: mIoU sweep. (i) 500 label maps 1024x2048 int64 + float32 gt, one launch; (ii) from logits, 100 images
     Cn, n_img = 19, 500
     g = torch.Generator(device=dev).manual_seed(555)
