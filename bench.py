@@ -442,7 +442,7 @@ def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
     achieved = algo / (ms * 1e-3) / 1e9
     traffic, warp_inst = None, None
     try:   # DRAM bytes / executed warp instructions per launch of the same kernel and shape, from the committed ncu capture
-        with open(os.path.join(ROOT, 'profiles', 'traffic_r1.json')) as fh:
+        with open(os.path.join(ROOT, 'profiles', 'traffic_r1g.json')) as fh:
             k = json.load(fh)['kernels']['up_cell_kernel<float, 5, 1, 64, 6, 0>']
         traffic, warp_inst = k['dram_bytes'], k['warp_inst']
     except Exception:

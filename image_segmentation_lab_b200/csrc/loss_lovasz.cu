@@ -24,7 +24,8 @@
 //                            g_i = I_i/(U_i (U_i-1))  (fg_i = 0),   g_0 = 1 - I_0/U_0
 //                        (the reference's fp32 J_i - J_{i-1} cancels catastrophically: for P = 4 M its increments carry
 //                        ~25 % noise; its cumsums stop being exact at 2^24), loss_c = sum e_i g_i, and
-//                        dloss_c/dp_c = -+g_i scattered to the pixel's slot of G (N,C,H,W) f32.
+//                        dloss_c/dp_c = -+g_i scattered to the pixel's slot of G (C,N,H,W) f32 (class-major: a segment
+//                        is one contiguous slice, the scatter index is the sorted value itself).
 //   lovasz_finalize_kernel  mean over the present / all / listed classes, class weights, per-image reduction
 //                        (weight_reduce_loss), and the coefficient table of the backward. No host sync anywhere.
 //   lovasz_bwd_kernel    softmax Jacobian: grad_z_j = up * p_j (a_j - sum_c a_c p_c), a_c = coef_c G_c.
@@ -219,10 +220,9 @@ struct LovGradParams {
   const uint32_t* vals;       // NULL when no gradient is wanted (multi-class)
   const uint32_t* tile_off;
   double* seg_stat;           // [0] loss accumulator, [1] gts + 1
-  float* G;                   // multi-class: (N,C,HW) f32; binary: (N,HW) f32; NULL = forward only
+  float* G;                   // NULL = forward only
+  float* Gseg;                // this segment's slice of G: multi-class (C,N,HW) f32 at (c, n0), binary (N,HW) at n0
   long long len;
-  long long HW;
-  int C, c, n0, single_image;
 };
 
 template <bool BINARY>
@@ -260,9 +260,10 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
     const long long i = i0 + j;
     const float I = (float)(gts - cum);
     const float U = (float)((unsigned long long)gts + (unsigned long long)(i + 1) - cum);
-    float g;
-    if (i == 0) g = 1.f - I / U;
-    else g = fg ? 1.f / U : I / (U * (U - 1.f));
+    // closed-form Jaccard increment; rcp.approx (1 ulp) instead of IEEE divisions. i == 0: J_0 = 1 - I/U = (U - I)/U
+    const float num = i == 0 ? U - I : (fg ? 1.f : I);
+    const float den = (i == 0 || fg) ? U : U * (U - 1.f);
+    const float g = num * fast_rcp(den);
     float e, dG;
     uint32_t idx;
     if constexpr (BINARY) {
@@ -277,13 +278,7 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
     }
     loss = fmaf(e, g, loss);
     if (p.G) {
-      if constexpr (BINARY) {
-        p.G[(size_t)p.n0 * p.HW + idx] = dG;
-      } else {
-        const uint32_t nl = p.single_image ? 0u : idx / (uint32_t)p.HW;
-        const uint32_t hw = idx - nl * (uint32_t)p.HW;
-        p.G[((size_t)(p.n0 + nl) * p.C + p.c) * p.HW + hw] = dG;
-      }
+      p.Gseg[idx] = dG;                                // G is class-major: (C, N, HW), a segment is contiguous
     }
   }
   loss = warp_sum(loss);
@@ -378,7 +373,8 @@ __global__ void __launch_bounds__(256) lovasz_bwd_kernel(const LovBwdParams p) {
 #pragma unroll
   for (int v = 0; v < V; ++v) nl[v] = -nl[v] * kLog2e;
   const T* zrow = reinterpret_cast<const T*>(p.logits) + (size_t)n * p.C * p.HW + hw0;
-  const float* grow = p.G + (size_t)n * p.C * p.HW + hw0;
+  const float* grow = p.G + (size_t)n * p.HW + hw0;            // (C, N, HW): class stride N * HW
+  const size_t gstride = (size_t)gridDim.y * p.HW;
   const float* cf = p.coef + (size_t)g * p.C;
   float dot[V];
 #pragma unroll
@@ -388,7 +384,7 @@ __global__ void __launch_bounds__(256) lovasz_bwd_kernel(const LovBwdParams p) {
     if (k == 0.f) continue;                           // class left out: its slots of G were never written
     float z[V], gg[V];
     load_vec<T, V>(zrow + (size_t)c * p.HW, z);
-    load_vec<float, V>(grow + (size_t)c * p.HW, gg);
+    load_vec<float, V>(grow + (size_t)c * gstride, gg);
 #pragma unroll
     for (int v = 0; v < V; ++v) dot[v] = fmaf(k * gg[v], ex2(fmaf(z[v], kLog2e, nl[v])), dot[v]);
   }
@@ -398,7 +394,7 @@ __global__ void __launch_bounds__(256) lovasz_bwd_kernel(const LovBwdParams p) {
     float z[V], gg[V], r[V];
     load_vec<T, V>(zrow + (size_t)c * p.HW, z);
     if (k != 0.f) {
-      load_vec<float, V>(grow + (size_t)c * p.HW, gg);
+      load_vec<float, V>(grow + (size_t)c * gstride, gg);
     } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) gg[v] = 0.f;
@@ -524,7 +520,8 @@ static int lov_fwd_typed(const b200seg_lovasz_desc* d, cudaStream_t st) {
       lovasz_tilescan_kernel<<<1, 1024, 0, st>>>(w.tile_cnt, w.tile_off, nb, seg);
       LovGradParams gp;
       gp.keys = w.keys_b; gp.vals = pairs ? w.vals_b : nullptr; gp.tile_off = w.tile_off; gp.seg_stat = seg;
-      gp.G = d->G; gp.len = len; gp.HW = HW; gp.C = d->C; gp.c = c; gp.n0 = n0; gp.single_image = imgs == 1;
+      gp.G = d->G; gp.len = len;
+      gp.Gseg = d->G ? d->G + ((size_t)(binary ? 0 : c) * d->N + n0) * HW : nullptr;
       if (binary) lovasz_grad_kernel<true><<<nb, kLovThreads, 0, st>>>(gp);
       else lovasz_grad_kernel<false><<<nb, kLovThreads, 0, st>>>(gp);
       count_launch(4);

@@ -264,7 +264,7 @@ typedef struct b200seg_lovasz_desc {
   float   loss_weight;
   double  avg_factor;
   int16_t* lab16;               /* out (N,HW): compact class ids (-1 ignored), kept for the backward                */
-  float*   G;                   /* out: multi-class (N,C,HW) f32, binary (N,HW) f32: dloss_seg/dp (resp. /dz), unscaled;
+  float*   G;                   /* out: multi-class (C,N,HW) f32 — CLASS-major —, binary (N,HW) f32: dloss_seg/dp (resp. /dz), unscaled;
                                  * NULL = forward only (the sort then moves keys only)                              */
   void*    workspace;           /* b200seg_lovasz_workspace_bytes(segment length, pairs) bytes, 256-byte aligned    */
   int64_t  workspace_bytes;

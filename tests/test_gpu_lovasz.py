@@ -5,8 +5,8 @@ errors are separated (manifest ``order_margin`` > 1) so that the gradient is ind
 On larger inputs near-tied errors are unavoidable (tens of thousands of fp32 values in [0,1] per segment) and the
 piecewise-constant gradient of the two tied pixels depends on their order — in the reference too (torch.sort's order among
 ties is unspecified). There the gradient is checked (a) element-wise against the exact (float64 Jaccard) oracle with at most
-1e-4 of the elements outside the 1e-4 gate and none outside 1e-2, and (b) through an order-independent property: the
-directional derivative of the oracle's loss along a random direction.
+1e-4 of the elements (or four flipped pairs) outside the 1e-4 gate and none outside 1e-2, and (b) through an order-independent property: the
+directional derivative of the oracle's loss along sign(grad).
 """
 import warnings
 
@@ -72,11 +72,15 @@ def test_lovasz_golden(B, golden):
 
 
 def _grad_gate(name, grad, ref):
+    """Element-wise gate that tolerates a handful of near-tie order flips: one flipped pair of (nearly) equal errors moves
+    the gradient of its two pixels — all C components of each, through the soft-max Jacobian — by a second-order amount."""
     d = (grad.double() - ref.double()).abs()
     scale = float(ref.abs().max())
-    frac = float((d > GRAD_TOL * scale).double().mean())
+    bad = int((d > GRAD_TOL * scale).sum())
+    allowed = max(int(1e-4 * d.numel()), 8 * (ref.shape[1] if ref.dim() == 4 else 1))
     worst = float(d.max()) / scale
-    assert frac <= 1e-4 and worst <= 1e-2, '%s: %.3e of the gradient outside %.0e, worst %.3e' % (name, frac, GRAD_TOL, worst)
+    assert bad <= allowed and worst <= 1e-2, '%s: %d gradient elements outside %.0e (allowed %d), worst %.3e' % (
+        name, bad, GRAD_TOL, allowed, worst)
 
 
 @pytest.mark.parametrize('shape,C,kw', [
@@ -89,13 +93,15 @@ def _grad_gate(name, grad, ref):
 def test_lovasz_softmax_vs_exact_oracle(B, shape, C, kw):
     x = synth_logits(shape, 41, device='cuda', margin=False)
     y = synth_labels((shape[0],) + shape[2:], C, 41, ignore_index=255, block=8, device='cuda')
-    go = torch.rand(shape[0], device='cuda') + 0.5 if (kw.get('per_image') and kw['reduction'] == 'none') else None
+    go = torch.linspace(0.5, 1.5, shape[0], device='cuda') if (kw.get('per_image') and kw['reduction'] == 'none') else None
     loss, grad = _run(B, x, y, kw, grad_out=go)
     lo, go_ref = _oracle64(x, y, kw, grad_out=go)
     assert rel_err(loss, lo) <= LOSS_TOL, '%s loss %.3e' % (shape, rel_err(loss, lo))
     _grad_gate(str(shape), grad, go_ref)
-    # order-independent: directional derivative of the exact loss along a random direction
-    d = torch.randn_like(x)
+    # order-independent: directional derivative of the exact loss along sign(grad) (a random direction projects the
+    # gradient onto almost nothing, and the central difference then mostly measures the kinks of the piecewise-linear
+    # Lovasz extension that lie within +-eps)
+    d = torch.sign(go_ref).float()
     eps = 1e-4
     sel = (lambda l: (l * go.double()).sum()) if go is not None else (lambda l: l)
     with torch.no_grad():
@@ -103,7 +109,7 @@ def test_lovasz_softmax_vs_exact_oracle(B, shape, C, kw):
         lm = sel(O.lovasz_loss_module((x.double() - eps * d.double()), y, ignore_index=255, acc_dtype=torch.float64, **kw))
     fd = float((lp - lm) / (2 * eps))
     an = float((grad.double() * d.double()).sum())
-    assert abs(fd - an) <= 2e-3 * max(abs(fd), 1e-3), '%s directional derivative %.6e vs %.6e' % (shape, an, fd)
+    assert abs(fd - an) <= 2e-3 * abs(fd), '%s directional derivative %.6e vs %.6e' % (shape, an, fd)
     # ignored pixels receive no gradient; the soft-max Jacobian sums to zero over the classes
     ign = (y == 255).unsqueeze(1).expand_as(grad)
     assert float(grad[ign].abs().max()) == 0.0
@@ -267,3 +273,74 @@ def test_lovasz_cuda_graph(B):
     graph.replay()
     torch.cuda.synchronize()
     assert rel_err(l_cap, l_eager) <= 1e-6 and rel_err(xg.grad, g_eager) <= 1e-6
+
+
+def test_lovasz_cabi_buffers_have_no_out_of_bounds_writes(B):
+    """compute-sanitizer is not available on the GPU pool: every buffer the Lovasz entries write (compact labels, G, sort
+    workspace, segment statistics, outputs, coefficients, gradient) sits between canary words; vector and scalar kernels,
+    partial scan tiles, per-image segments and the binary variant."""
+    import ctypes as C
+    from image_segmentation_lab_b200 import _lib
+    lib = B.load_library()
+    dev = torch.device('cuda', 0)
+    stream = _lib.stream_ptr(dev)
+    GUARD = 4096
+
+    def guarded(nbytes):
+        n = (nbytes + 255) // 256 * 256
+        buf = torch.full((n + 2 * GUARD,), 0x5A, dtype=torch.uint8, device=dev)
+        return buf, buf[GUARD:GUARD + n], n
+
+    def intact(buf, n, what):
+        assert bool((buf[:GUARD] == 0x5A).all()) and bool((buf[GUARD + n:] == 0x5A).all()), what + ': guard overwritten'
+
+    cases = [((2, 5, 24, 40), False, False), ((3, 7, 37, 53), False, False), ((1, 3, 50, 41), False, False),
+             ((3, 4, 45, 46), False, True), ((2, 1, 33, 31), True, False), ((3, 1, 64, 48), True, True)]
+    for shape, binary, per_image in cases:
+        N, Cc, H, W = shape
+        HW = H * W
+        x = synth_logits(shape, 13, device='cuda', margin=False)
+        y = synth_labels((N, H, W), 2 if binary else Cc, 13, ignore_index=255, block=5, device='cuda')
+        n_groups = N if per_image else 1
+        n_seg = 1 if binary else Cc
+        lse = torch.logsumexp(x.double(), 1).float().reshape(N, HW).contiguous() if not binary else None
+        seg_len = HW if per_image else N * HW
+        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(seg_len, 1))
+        bufs = {}
+        for name, nbytes in (('lab16', N * HW * 2), ('G', N * n_seg * HW * 4), ('ws', ws_bytes), ('seg', n_groups * n_seg * 16),
+                             ('out', max(n_groups, 1) * 4), ('coef', n_groups * n_seg * 4), ('grad', N * Cc * HW * 4)):
+            bufs[name] = guarded(nbytes)
+        d = _lib.LovaszDesc()
+        d.logits = x.data_ptr(); d.labels = y.data_ptr(); d.lse = lse.data_ptr() if lse is not None else None
+        d.logit_dtype = _lib.F32; d.label_dtype = _lib.L_I64
+        d.N, d.C, d.HW = N, Cc, HW
+        d.ignore_index = 255; d.has_ignore = 1
+        d.binary = int(binary); d.per_image = int(per_image); d.only_present = 1
+        d.reduction = _lib.RED_NONE if per_image else _lib.RED_MEAN
+        d.loss_weight = 1.0
+        d.lab16 = bufs['lab16'][1].data_ptr(); d.G = bufs['G'][1].data_ptr()
+        d.workspace = bufs['ws'][1].data_ptr(); d.workspace_bytes = ws_bytes
+        assert d.workspace % 256 == 0
+        d.seg_stats = bufs['seg'][1].data_ptr(); d.out = bufs['out'][1].data_ptr(); d.coef = bufs['coef'][1].data_ptr()
+        _lib.check(lib.b200seg_lovasz_fwd(C.byref(d), stream))
+        b = _lib.LovaszBwdDesc()
+        b.logits = x.data_ptr(); b.lse = d.lse; b.lab16 = d.lab16; b.G = d.G; b.coef = d.coef
+        b.grad_logits = bufs['grad'][1].data_ptr()
+        b.logit_dtype = _lib.F32; b.N, b.C, b.HW = N, Cc, HW
+        b.binary = int(binary); b.per_image = int(per_image); b.grad_per_group = 0
+        _lib.check(lib.b200seg_lovasz_bwd(C.byref(b), stream))
+        torch.cuda.synchronize()
+        for name, (buf, _, n) in bufs.items():
+            intact(buf, n, '%s %s' % (shape, name))
+        # and the values are the oracle's
+        kw = dict(loss_type='binary' if binary else 'multi_class', per_image=per_image, reduction='none')
+        xo = x.double().requires_grad_(True)
+        lo = O.lovasz_loss_module(xo, y, ignore_index=255, acc_dtype=torch.float64, **kw)
+        lo.sum().backward()
+        got = bufs['out'][1][:max(n_groups, 1) * 4].view(torch.float32)[:n_groups if per_image else 1]
+        assert rel_err(got.reshape(lo.shape), lo) <= LOSS_TOL, shape
+        grad = bufs['grad'][1][:N * Cc * HW * 4].view(torch.float32).reshape(shape)
+        _grad_gate(str(shape), grad, xo.grad)
+    # a too-small workspace is refused before any launch
+    d.workspace_bytes = 1024
+    assert lib.b200seg_lovasz_fwd(C.byref(d), stream) != 0 and 'workspace' in _lib.last_error()
