@@ -72,14 +72,19 @@ struct LovKeysParams {
   const void* logits;     // (N,C,HW) multi-class, (N,HW) binary
   const float* lse;       // (N,HW), multi-class only
   const int16_t* lab16;   // (N,HW)
-  uint32_t* keys;         // (imgs_in_group * HW)
-  uint32_t* vals;         // same, or NULL (keys only)
+  void* keys;             // (imgs * HW) uint32, or uint64 in batched mode
+  uint32_t* vals;         // same count, or NULL (keys only)
   long long HW;
   int C, c, n0;
+  int n_img;              // batched mode: number of images (= segments) in the launch
 };
 
-template <typename T, int V, bool BINARY>
+// KeyT = uint32_t: one segment per launch (the images blockIdx.y of one group are concatenated, value = index in the group).
+// KeyT = uint64_t: BATCHED per-image mode — every image is its own segment, all of them sorted by ONE radix sort: the
+// high word carries (n_img - 1 - image) so that the descending order lists image 0 first; value = pixel index in the image.
+template <typename T, int V, bool BINARY, typename KeyT>
 __global__ void __launch_bounds__(256) lovasz_keys_kernel(const LovKeysParams p) {
+  constexpr bool kBatched = sizeof(KeyT) == 8;
   const int nl = blockIdx.y;
   const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (hw0 >= p.HW) return;
@@ -97,14 +102,15 @@ __global__ void __launch_bounds__(256) lovasz_keys_kernel(const LovKeysParams p)
     lab[0] = p.lab16[px];
   }
   uint32_t key[V], val[V];
-  const uint32_t i0 = (uint32_t)((size_t)nl * p.HW + hw0);
+  const size_t i0 = (size_t)nl * p.HW + hw0;                               // slot in the key / value arrays
+  const uint32_t v0 = kBatched ? (uint32_t)hw0 : (uint32_t)i0;             // index inside the segment
   if constexpr (BINARY) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const uint32_t fg = lab[v] != 0 && lab[v] != kLovIgnored;       // labels are 0 / 1 (:78-79)
       const float sign = fg ? 1.f : -1.f;
       key[v] = lab[v] == kLovIgnored ? 0u : hinge_key(1.f - z[v] * sign);
-      val[v] = (i0 + v) | (fg << 31);
+      val[v] = (v0 + v) | (fg << 31);
     }
   } else {
     float l[V];
@@ -115,26 +121,46 @@ __global__ void __launch_bounds__(256) lovasz_keys_kernel(const LovKeysParams p)
       const uint32_t fg = lab[v] == p.c;
       const float e = fabsf((fg ? 1.f : 0.f) - pc);
       key[v] = lab[v] == kLovIgnored ? 0u : (((__float_as_uint(e) + 1u) << 1) | fg);
-      val[v] = i0 + v;
+      val[v] = v0 + v;
     }
   }
-  if constexpr (V == 4) {
-    *reinterpret_cast<uint4*>(p.keys + i0) = make_uint4(key[0], key[1], key[2], key[3]);
-    if (p.vals) *reinterpret_cast<uint4*>(p.vals + i0) = make_uint4(val[0], val[1], val[2], val[3]);
+  KeyT* kout = reinterpret_cast<KeyT*>(p.keys) + i0;
+  if constexpr (kBatched) {
+    const uint32_t hi = (uint32_t)(p.n_img - 1 - nl);
+    if constexpr (V == 4) {
+      reinterpret_cast<uint4*>(kout)[0] = make_uint4(key[0], hi, key[1], hi);
+      reinterpret_cast<uint4*>(kout)[1] = make_uint4(key[2], hi, key[3], hi);
+    } else {
+      kout[0] = ((KeyT)hi << 32) | key[0];
+    }
   } else {
-    p.keys[i0] = key[0];
-    if (p.vals) p.vals[i0] = val[0];
+    if constexpr (V == 4) *reinterpret_cast<uint4*>(kout) = make_uint4(key[0], key[1], key[2], key[3]);
+    else kout[0] = key[0];
+  }
+  if (p.vals) {
+    if constexpr (V == 4) *reinterpret_cast<uint4*>(p.vals + i0) = make_uint4(val[0], val[1], val[2], val[3]);
+    else p.vals[i0] = val[0];
   }
 }
 
 // ---------------------------------------------------------------------------------------------- scan over the sorted order
-template <bool BINARY>
-__device__ __forceinline__ void lov_load_tile(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                              long long i0, long long len, uint32_t (&k)[kLovItems],
+// 8 consecutive sorted items of one segment (low word of the key = error | foreground bit; the high word of a batched
+// 64-bit key is the image index, not needed once the order is established)
+template <typename KeyT>
+__device__ __forceinline__ void lov_load_tile(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                              long long i0, long long len, bool vec, uint32_t (&k)[kLovItems],
                                               uint32_t (&v)[kLovItems], bool want_vals) {
-  if (i0 + kLovItems <= len) {
-    const uint4 a = *reinterpret_cast<const uint4*>(keys + i0), b = *reinterpret_cast<const uint4*>(keys + i0 + 4);
-    k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+  if (vec && i0 + kLovItems <= len) {
+    if constexpr (sizeof(KeyT) == 4) {
+      const uint4 a = *reinterpret_cast<const uint4*>(keys + i0), b = *reinterpret_cast<const uint4*>(keys + i0 + 4);
+      k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 a = *reinterpret_cast<const uint4*>(keys + i0 + 2 * j);
+        k[2 * j] = a.x; k[2 * j + 1] = a.z;
+      }
+    }
     if (want_vals) {
       const uint4 c = *reinterpret_cast<const uint4*>(vals + i0), d = *reinterpret_cast<const uint4*>(vals + i0 + 4);
       v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
@@ -143,7 +169,7 @@ __device__ __forceinline__ void lov_load_tile(const uint32_t* __restrict__ keys,
 #pragma unroll
     for (int j = 0; j < kLovItems; ++j) {
       const bool in = i0 + j < len;
-      k[j] = in ? keys[i0 + j] : 0u;
+      k[j] = in ? (uint32_t)keys[i0 + j] : 0u;
       v[j] = (in && want_vals) ? vals[i0 + j] : 0u;
     }
   }
@@ -153,14 +179,16 @@ template <bool BINARY> __device__ __forceinline__ uint32_t lov_fg(uint32_t key, 
   else return key & 1u;                                  // ignored items carry key 0
 }
 
-template <bool BINARY>
-__global__ void __launch_bounds__(kLovThreads) lovasz_count_kernel(const uint32_t* __restrict__ keys,
+// grid (tiles per segment, segments): foreground count of every tile
+template <bool BINARY, typename KeyT>
+__global__ void __launch_bounds__(kLovThreads) lovasz_count_kernel(const KeyT* __restrict__ keys,
                                                                    const uint32_t* __restrict__ vals, long long len,
-                                                                   uint32_t* __restrict__ tile_cnt) {
+                                                                   int vec, uint32_t* __restrict__ tile_cnt) {
   __shared__ uint32_t s[kLovThreads / 32];
+  const size_t seg0 = (size_t)blockIdx.y * len;
   const long long i0 = ((long long)blockIdx.x * kLovThreads + threadIdx.x) * kLovItems;
   uint32_t k[kLovItems], v[kLovItems];
-  lov_load_tile<BINARY>(keys, vals, i0, len, k, v, BINARY);
+  lov_load_tile<KeyT>(keys + seg0, vals ? vals + seg0 : nullptr, i0, len, vec != 0, k, v, BINARY);
   uint32_t cnt = 0;
 #pragma unroll
   for (int j = 0; j < kLovItems; ++j) cnt += lov_fg<BINARY>(k[j], v[j]);
@@ -171,14 +199,17 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_count_kernel(const uint32_
     uint32_t t = 0;
 #pragma unroll
     for (int w = 0; w < kLovThreads / 32; ++w) t += s[w];
-    tile_cnt[blockIdx.x] = t;
+    tile_cnt[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
 }
 
-// one CTA: exclusive scan of the tile counts; writes the segment's foreground total (+1 = "segment processed")
-__global__ void __launch_bounds__(1024) lovasz_tilescan_kernel(const uint32_t* __restrict__ tile_cnt,
-                                                               uint32_t* __restrict__ tile_off, int nb,
-                                                               double* __restrict__ seg_stat) {
+// one CTA per segment: exclusive scan of its tile counts; writes the segment's foreground total (+1 = "segment processed")
+__global__ void __launch_bounds__(1024) lovasz_tilescan_kernel(const uint32_t* __restrict__ tile_cnt_all,
+                                                               uint32_t* __restrict__ tile_off_all, int nb,
+                                                               double* __restrict__ seg_stat_all, int seg_stat_stride) {
+  const uint32_t* tile_cnt = tile_cnt_all + (size_t)blockIdx.x * nb;      // one CTA per segment
+  uint32_t* tile_off = tile_off_all + (size_t)blockIdx.x * nb;
+  double* seg_stat = seg_stat_all + (size_t)blockIdx.x * seg_stat_stride;
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,16 +247,18 @@ __global__ void __launch_bounds__(1024) lovasz_tilescan_kernel(const uint32_t* _
 }
 
 struct LovGradParams {
-  const uint32_t* keys;
+  const void* keys;
   const uint32_t* vals;       // NULL when no gradient is wanted (multi-class)
-  const uint32_t* tile_off;
-  double* seg_stat;           // [0] loss accumulator, [1] gts + 1
+  const uint32_t* tile_off;   // (segments, tiles per segment)
+  double* seg_stat;           // segment 0: [0] loss accumulator, [1] gts + 1; segment s at + s * seg_stat_stride
   float* G;                   // NULL = forward only
-  float* Gseg;                // this segment's slice of G: multi-class (C,N,HW) f32 at (c, n0), binary (N,HW) at n0
-  long long len;
+  float* Gseg;                // segment 0's slice of G: multi-class (C,N,HW) f32 at (c, n0), binary (N,HW) at n0
+  long long len;              // items per segment (consecutive segments are `len` apart in keys, vals and G)
+  int seg_stat_stride;
+  int vec;
 };
 
-template <bool BINARY>
+template <bool BINARY, typename KeyT>
 __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradParams p) {
   __shared__ uint32_t s_w[kLovThreads / 32];
   __shared__ float s_l[kLovThreads / 32];
@@ -233,7 +266,10 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
   const long long i0 = ((long long)blockIdx.x * kLovThreads + threadIdx.x) * kLovItems;
   const bool want_vals = BINARY || p.G != nullptr;
   uint32_t k[kLovItems], v[kLovItems];
-  lov_load_tile<BINARY>(p.keys, p.vals, i0, p.len, k, v, want_vals);
+  const size_t seg0 = (size_t)blockIdx.y * p.len;
+  double* seg_stat = p.seg_stat + (size_t)blockIdx.y * p.seg_stat_stride;
+  lov_load_tile<KeyT>(reinterpret_cast<const KeyT*>(p.keys) + seg0, p.vals ? p.vals + seg0 : nullptr, i0, p.len, p.vec != 0, k, v,
+                      want_vals);
   uint32_t tsum = 0;
 #pragma unroll
   for (int j = 0; j < kLovItems; ++j) tsum += lov_fg<BINARY>(k[j], v[j]);
@@ -249,8 +285,8 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
   uint32_t wpre = 0;
 #pragma unroll
   for (int w = 0; w < kLovThreads / 32; ++w) wpre += (w < warp) ? s_w[w] : 0u;
-  uint32_t cum = p.tile_off[blockIdx.x] + wpre + (x - tsum);
-  const uint32_t gts = (uint32_t)(p.seg_stat[1] - 1.0);
+  uint32_t cum = p.tile_off[(size_t)blockIdx.y * gridDim.x + blockIdx.x] + wpre + (x - tsum);
+  const uint32_t gts = (uint32_t)(seg_stat[1] - 1.0);
   float loss = 0.f;
 #pragma unroll
   for (int j = 0; j < kLovItems; ++j) {
@@ -278,7 +314,7 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
     }
     loss = fmaf(e, g, loss);
     if (p.G) {
-      p.Gseg[idx] = dG;                                // G is class-major: (C, N, HW), a segment is contiguous
+      p.Gseg[seg0 + idx] = dG;                         // G is class-major: (C, N, HW), a segment is contiguous
     }
   }
   loss = warp_sum(loss);
@@ -288,7 +324,7 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < kLovThreads / 32; ++w) t += (double)s_l[w];
-    if (t != 0.0) atomicAdd(p.seg_stat, t);
+    if (t != 0.0) atomicAdd(seg_stat, t);
   }
 }
 
@@ -422,34 +458,51 @@ __global__ void __launch_bounds__(256) lovasz_hinge_bwd_kernel(const LovBwdParam
 
 // ---------------------------------------------------------------------------------------------- host side
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline int bits_for(int n) {   // bits needed to hold values 0 .. n-1 (>= 1)
+  int b = 1;
+  while ((1 << b) < n) ++b;
+  return b;
+}
 
 struct LovWorkspace {
-  uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *tile_cnt, *tile_off;
+  void *keys_a, *keys_b;
+  uint32_t *vals_a, *vals_b, *tile_cnt, *tile_off;
   void* cub_temp;
   size_t cub_bytes, total;
 };
 
-static int lov_carve(long long len, bool pairs, void* base, LovWorkspace* w) {
+// items = keys per sort; segs = segments per sort (> 1: batched per-image mode with 64-bit keys)
+static int lov_carve(long long items, int segs, bool pairs, void* base, LovWorkspace* w) {
   size_t cub_bytes = 0;
-  const int n = (int)len;
-  cudaError_t e = pairs ? cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint32_t*)nullptr,
-                                                                    (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                                                    (uint32_t*)nullptr, n, 0, 32, (cudaStream_t)0)
-                        : cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, (const uint32_t*)nullptr,
-                                                                   (uint32_t*)nullptr, n, 0, 32, (cudaStream_t)0);
+  const int n = (int)items;
+  cudaError_t e;
+  if (segs > 1) {
+    const int end_bit = 32 + bits_for(segs);
+    e = pairs ? cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                                          (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, end_bit, (cudaStream_t)0)
+              : cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, n, 0,
+                                                         end_bit, (cudaStream_t)0);
+  } else {
+    e = pairs ? cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                          (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 32, (cudaStream_t)0)
+              : cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 32,
+                                                         (cudaStream_t)0);
+  }
   if (e != cudaSuccess) {
     set_error("lovasz: radix-sort workspace query failed: %s", cudaGetErrorString(e));
     return 2;
   }
-  const size_t arr = align256((size_t)len * sizeof(uint32_t));
-  const size_t nb = (size_t)((len + kLovTile - 1) / kLovTile);
+  const size_t karr = align256((size_t)items * (segs > 1 ? 8 : 4));
+  const size_t varr = align256((size_t)items * 4);
+  const long long seg_len = items / segs;
+  const size_t nb = (size_t)((seg_len + kLovTile - 1) / kLovTile) * segs;
   const size_t tb = align256((nb + 1) * sizeof(uint32_t));
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
-  w->keys_a = reinterpret_cast<uint32_t*>(p + off); off += arr;
-  w->keys_b = reinterpret_cast<uint32_t*>(p + off); off += arr;
-  w->vals_a = reinterpret_cast<uint32_t*>(p + off); off += pairs ? arr : 0;
-  w->vals_b = reinterpret_cast<uint32_t*>(p + off); off += pairs ? arr : 0;
+  w->keys_a = p + off; off += karr;
+  w->keys_b = p + off; off += karr;
+  w->vals_a = reinterpret_cast<uint32_t*>(p + off); off += pairs ? varr : 0;
+  w->vals_b = reinterpret_cast<uint32_t*>(p + off); off += pairs ? varr : 0;
   w->tile_cnt = reinterpret_cast<uint32_t*>(p + off); off += tb;
   w->tile_off = reinterpret_cast<uint32_t*>(p + off); off += tb;
   w->cub_temp = p + off; off += align256(cub_bytes ? cub_bytes : 1);
@@ -458,24 +511,26 @@ static int lov_carve(long long len, bool pairs, void* base, LovWorkspace* w) {
   return 0;
 }
 
-long long lovasz_workspace_bytes(long long seg_len, int pairs) {
-  if (seg_len <= 0) return 256;
+long long lovasz_workspace_bytes(long long seg_len, int segs, int pairs) {
+  if (seg_len <= 0 || segs <= 0) return 256;
   LovWorkspace w;
-  if (lov_carve(seg_len, pairs != 0, nullptr, &w)) return -1;
+  if (lov_carve(seg_len * segs, segs, pairs != 0, nullptr, &w)) return -1;
   return (long long)w.total;
 }
 
-template <typename T>
+template <typename T, typename KeyT>
 static int lov_fwd_typed(const b200seg_lovasz_desc* d, cudaStream_t st) {
+  constexpr bool kBatched = sizeof(KeyT) == 8;
   const bool binary = d->binary != 0;
   const int n_seg = binary ? 1 : d->C;
-  const int n_groups = d->per_image ? d->N : 1;
-  const int imgs = d->per_image ? 1 : d->N;
   const long long HW = d->HW;
-  const long long len = (long long)imgs * HW;
+  // kBatched: every image is a segment and ONE sort orders all of them; else one segment = the whole batch (or N == 1)
+  const int segs = kBatched ? d->N : 1;
+  const long long seg_len = kBatched ? HW : (long long)d->N * HW;
+  const long long items = seg_len * segs;
   const bool pairs = binary || d->G != nullptr;
   LovWorkspace w;
-  if (int e = lov_carve(len, pairs, d->workspace, &w)) return e;
+  if (int e = lov_carve(items, segs, pairs, d->workspace, &w)) return e;
   B200SEG_REQUIRE((long long)w.total <= d->workspace_bytes, "lovasz_fwd: workspace of %lld bytes needed, %lld given",
                   (long long)w.total, (long long)d->workspace_bytes);
   const long long npx = (long long)d->N * HW;
@@ -485,48 +540,52 @@ static int lov_fwd_typed(const b200seg_lovasz_desc* d, cudaStream_t st) {
   if (int e = check_launch("lovasz_prep_kernel")) return e;
 
   const bool vec = HW % 4 == 0 && aligned16(d->logits) && aligned16(d->lab16) && (binary || aligned16(d->lse));
-  const int nb = (int)((len + kLovTile - 1) / kLovTile);
-  for (int g = 0; g < n_groups; ++g) {
-    const int n0 = d->per_image ? g : 0;
-    const int n_list = binary ? 1 : (d->classes_host ? d->n_classes : d->C);
-    for (int j = 0; j < n_list; ++j) {
-      const int c = binary ? 0 : (d->classes_host ? d->classes_host[j] : j);
-      LovKeysParams kp;
-      kp.logits = d->logits; kp.lse = d->lse; kp.lab16 = d->lab16;
-      kp.keys = w.keys_a; kp.vals = pairs ? w.vals_a : nullptr;
-      kp.HW = HW; kp.C = d->C; kp.c = c; kp.n0 = n0;
-      if (vec) {
-        dim3 grid((unsigned)((HW / 4 + 255) / 256), imgs);
-        if (binary) lovasz_keys_kernel<T, 4, true><<<grid, 256, 0, st>>>(kp);
-        else lovasz_keys_kernel<T, 4, false><<<grid, 256, 0, st>>>(kp);
-      } else {
-        dim3 grid((unsigned)((HW + 255) / 256), imgs);
-        if (binary) lovasz_keys_kernel<T, 1, true><<<grid, 256, 0, st>>>(kp);
-        else lovasz_keys_kernel<T, 1, false><<<grid, 256, 0, st>>>(kp);
-      }
-      if (int e = check_launch("lovasz_keys_kernel")) return e;
-      size_t cb = w.cub_bytes;
-      cudaError_t ce = pairs ? cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cb, (const uint32_t*)w.keys_a, w.keys_b,
-                                                                         (const uint32_t*)w.vals_a, w.vals_b, (int)len, 0, 32, st)
-                             : cub::DeviceRadixSort::SortKeysDescending(w.cub_temp, cb, (const uint32_t*)w.keys_a, w.keys_b,
-                                                                        (int)len, 0, 32, st);
-      if (ce != cudaSuccess) {
-        set_error("lovasz_fwd: radix sort failed: %s", cudaGetErrorString(ce));
-        return 2;
-      }
-      double* seg = d->seg_stats + ((size_t)g * n_seg + c) * 2;
-      if (binary) lovasz_count_kernel<true><<<nb, kLovThreads, 0, st>>>(w.keys_b, w.vals_b, len, w.tile_cnt);
-      else lovasz_count_kernel<false><<<nb, kLovThreads, 0, st>>>(w.keys_b, nullptr, len, w.tile_cnt);
-      lovasz_tilescan_kernel<<<1, 1024, 0, st>>>(w.tile_cnt, w.tile_off, nb, seg);
-      LovGradParams gp;
-      gp.keys = w.keys_b; gp.vals = pairs ? w.vals_b : nullptr; gp.tile_off = w.tile_off; gp.seg_stat = seg;
-      gp.G = d->G; gp.len = len;
-      gp.Gseg = d->G ? d->G + ((size_t)(binary ? 0 : c) * d->N + n0) * HW : nullptr;
-      if (binary) lovasz_grad_kernel<true><<<nb, kLovThreads, 0, st>>>(gp);
-      else lovasz_grad_kernel<false><<<nb, kLovThreads, 0, st>>>(gp);
-      count_launch(4);
-      if (int e = check_launch("lovasz scan kernels")) return e;
+  const int scan_vec = (segs == 1 || seg_len % 8 == 0) ? 1 : 0;      // 16-byte loads of the sorted arrays stay aligned
+  const int nb = (int)((seg_len + kLovTile - 1) / kLovTile);
+  const int end_bit = kBatched ? 32 + bits_for(segs) : 32;
+  const int n_list = binary ? 1 : (d->classes_host ? d->n_classes : d->C);
+  for (int j = 0; j < n_list; ++j) {
+    const int c = binary ? 0 : (d->classes_host ? d->classes_host[j] : j);
+    LovKeysParams kp;
+    kp.logits = d->logits; kp.lse = d->lse; kp.lab16 = d->lab16;
+    kp.keys = w.keys_a; kp.vals = pairs ? w.vals_a : nullptr;
+    kp.HW = HW; kp.C = d->C; kp.c = c; kp.n0 = 0; kp.n_img = d->N;
+    if (vec) {
+      dim3 grid((unsigned)((HW / 4 + 255) / 256), d->N);
+      if (binary) lovasz_keys_kernel<T, 4, true, KeyT><<<grid, 256, 0, st>>>(kp);
+      else lovasz_keys_kernel<T, 4, false, KeyT><<<grid, 256, 0, st>>>(kp);
+    } else {
+      dim3 grid((unsigned)((HW + 255) / 256), d->N);
+      if (binary) lovasz_keys_kernel<T, 1, true, KeyT><<<grid, 256, 0, st>>>(kp);
+      else lovasz_keys_kernel<T, 1, false, KeyT><<<grid, 256, 0, st>>>(kp);
     }
+    if (int e = check_launch("lovasz_keys_kernel")) return e;
+    size_t cb = w.cub_bytes;
+    const KeyT* kin = reinterpret_cast<const KeyT*>(w.keys_a);
+    KeyT* kout = reinterpret_cast<KeyT*>(w.keys_b);
+    cudaError_t ce = pairs ? cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cb, kin, kout, (const uint32_t*)w.vals_a,
+                                                                       w.vals_b, (int)items, 0, end_bit, st)
+                           : cub::DeviceRadixSort::SortKeysDescending(w.cub_temp, cb, kin, kout, (int)items, 0, end_bit, st);
+    if (ce != cudaSuccess) {
+      set_error("lovasz_fwd: radix sort failed: %s", cudaGetErrorString(ce));
+      return 2;
+    }
+    // segment s of this launch = image group s: statistics at (s, c), G slice at (c, s)
+    double* seg = d->seg_stats + (size_t)c * 2;
+    const int seg_stride = n_seg * 2;
+    dim3 sgrid(nb, segs);
+    const uint32_t* vsorted = pairs ? w.vals_b : nullptr;
+    if (binary) lovasz_count_kernel<true, KeyT><<<sgrid, kLovThreads, 0, st>>>(kout, vsorted, seg_len, scan_vec, w.tile_cnt);
+    else lovasz_count_kernel<false, KeyT><<<sgrid, kLovThreads, 0, st>>>(kout, nullptr, seg_len, scan_vec, w.tile_cnt);
+    lovasz_tilescan_kernel<<<segs, 1024, 0, st>>>(w.tile_cnt, w.tile_off, nb, seg, seg_stride);
+    LovGradParams gp;
+    gp.keys = kout; gp.vals = vsorted; gp.tile_off = w.tile_off; gp.seg_stat = seg; gp.seg_stat_stride = seg_stride;
+    gp.G = d->G; gp.len = seg_len; gp.vec = scan_vec;
+    gp.Gseg = d->G ? d->G + (size_t)(binary ? 0 : c) * d->N * HW : nullptr;
+    if (binary) lovasz_grad_kernel<true, KeyT><<<sgrid, kLovThreads, 0, st>>>(gp);
+    else lovasz_grad_kernel<false, KeyT><<<sgrid, kLovThreads, 0, st>>>(gp);
+    count_launch(4);
+    if (int e = check_launch("lovasz scan kernels")) return e;
   }
   return 0;
 }
@@ -537,10 +596,13 @@ int lovasz_fwd_dispatch(const b200seg_lovasz_desc* d, cudaStream_t st) {
   B200SEG_CUDA(cudaMemsetAsync(d->seg_stats, 0, (size_t)n_groups * n_seg * 2 * sizeof(double), st));
   if (d->N > 0 && d->HW > 0) {
     int e;
+    const bool batched = d->per_image && d->N > 1;   // all images of a class in one 64-bit-key sort
     switch (d->logit_dtype) {
-      case B200SEG_F32: e = lov_fwd_typed<float>(d, st); break;
-      case B200SEG_BF16: e = lov_fwd_typed<__nv_bfloat16>(d, st); break;
-      default: e = lov_fwd_typed<__half>(d, st); break;
+      case B200SEG_F32: e = batched ? lov_fwd_typed<float, uint64_t>(d, st) : lov_fwd_typed<float, uint32_t>(d, st); break;
+      case B200SEG_BF16:
+        e = batched ? lov_fwd_typed<__nv_bfloat16, uint64_t>(d, st) : lov_fwd_typed<__nv_bfloat16, uint32_t>(d, st);
+        break;
+      default: e = batched ? lov_fwd_typed<__half, uint64_t>(d, st) : lov_fwd_typed<__half, uint32_t>(d, st); break;
     }
     if (e) return e;
   }

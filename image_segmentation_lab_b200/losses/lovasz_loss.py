@@ -75,9 +75,10 @@ class _LovaszFunction(torch.autograd.Function):
                 fd.ce_loss_weight = 1.0
                 _lib.check(lib.b200seg_loss_fwd(C.byref(fd), stream))
                 keep.append(st)
-            seg_len = HW if per_image else N * HW
+            batched = per_image and N > 1          # all images of a class ordered by one sort (64-bit keys)
+            seg_len, segs = (HW, N) if batched else (N * HW, 1)
             pairs = int(binary or needs_grad)
-            ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(seg_len, pairs)) if N * HW > 0 else 256
+            ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(seg_len, segs, pairs)) if N * HW > 0 else 256
             if ws_bytes < 0:
                 raise RuntimeError(_lib.last_error())
             ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
@@ -166,6 +167,8 @@ class LovaszLoss(nn.Module):
         assert classes in ('all', 'present') or _is_list_of_int(classes)                                  # :270
         if not per_image:
             assert reduction == 'none', "reduction should be 'none' when per_image is False."           # :271-273
+        if _is_list_of_int(classes) and len(set(classes)) != len(classes):
+            raise ValueError('classes lists a class more than once: %r' % (classes,))
         self.loss_type = loss_type
         self.classes = classes
         self.per_image = per_image

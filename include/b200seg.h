@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 10
+#define B200SEG_ABI_VERSION 11
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -266,14 +266,16 @@ typedef struct b200seg_lovasz_desc {
   int16_t* lab16;               /* out (N,HW): compact class ids (-1 ignored), kept for the backward                */
   float*   G;                   /* out: multi-class (C,N,HW) f32 — CLASS-major —, binary (N,HW) f32: dloss_seg/dp (resp. /dz), unscaled;
                                  * NULL = forward only (the sort then moves keys only)                              */
-  void*    workspace;           /* b200seg_lovasz_workspace_bytes(segment length, pairs) bytes, 256-byte aligned    */
+  void*    workspace;           /* b200seg_lovasz_workspace_bytes(...) bytes, 256-byte aligned                      */
   int64_t  workspace_bytes;
   double*  seg_stats;           /* (n_groups, C or 1, 2) doubles [loss, #foreground + 1], zeroed by the call        */
   float*   out;                 /* per_image && reduction none: n_groups floats; else 1 float (loss_weight applied) */
   float*   coef;                /* (n_groups, C or 1) f32: d out / d loss_seg, for the backward; or NULL            */
 } b200seg_lovasz_desc;
-/* seg_len = HW (per_image) or N*HW; pairs = 1 when G != NULL or binary. Needs a CUDA device (queries the sort). */
-int64_t b200seg_lovasz_workspace_bytes(int64_t seg_len, int32_t pairs);
+/* per_image with N > 1: (seg_len = HW, segments = N) — all images of a class are ordered by ONE sort of 64-bit keys
+ * (image index in the high word); otherwise (seg_len = N*HW, segments = 1). pairs = 1 when G != NULL or binary.
+ * Needs a CUDA device (queries the sort). */
+int64_t b200seg_lovasz_workspace_bytes(int64_t seg_len, int32_t segments, int32_t pairs);
 int b200seg_lovasz_fwd(const b200seg_lovasz_desc* d, void* stream);
 
 typedef struct b200seg_lovasz_bwd_desc {

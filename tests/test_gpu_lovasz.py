@@ -184,6 +184,8 @@ def test_lovasz_constructor_and_errors(B):
         B.LovaszLoss(reduction='mean')                     # per_image=False needs reduction='none' (:271-273)
     with pytest.raises(AssertionError):
         B.LovaszLoss(classes='some', reduction='none')
+    with pytest.raises(ValueError):
+        B.LovaszLoss(classes=[1, 1, 2], reduction='none')
     m = B.LovaszLoss(per_image=True, reduction='sum')
     assert m.loss_name == 'loss_lovasz' and len(m.state_dict()) == 0
     x = torch.randn(2, 3, 8, 8, device='cuda')
@@ -304,8 +306,8 @@ def test_lovasz_cabi_buffers_have_no_out_of_bounds_writes(B):
         n_groups = N if per_image else 1
         n_seg = 1 if binary else Cc
         lse = torch.logsumexp(x.double(), 1).float().reshape(N, HW).contiguous() if not binary else None
-        seg_len = HW if per_image else N * HW
-        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(seg_len, 1))
+        batched = per_image and N > 1
+        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(HW if batched else N * HW, N if batched else 1, 1))
         bufs = {}
         for name, nbytes in (('lab16', N * HW * 2), ('G', N * n_seg * HW * 4), ('ws', ws_bytes), ('seg', n_groups * n_seg * 16),
                              ('out', max(n_groups, 1) * 4), ('coef', n_groups * n_seg * 4), ('grad', N * Cc * HW * 4)):
