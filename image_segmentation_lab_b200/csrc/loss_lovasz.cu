@@ -7,7 +7,8 @@
 // (P,)-sized temporaries per class in a Python loop, a host sync per class for 'present' (:153), and an autograd graph
 // that walks all of it backwards.
 //
-// Here, per (image group g, class c) SEGMENT (one group = the whole batch, or one image when per_image=True):
+// Here, per (image group g, class c) SEGMENT (one group = the whole batch, or one image when per_image=True; in that
+// case all images of a class are ordered by ONE sort of 64-bit keys with the image index in the high word):
 //   lovasz_keys_kernel   p_c = ex2(z_c*log2e - lse*log2e) from the logits row of class c and the per-pixel log-sum-exp of
 //                        ONE forward pass (b200seg_loss_fwd, WANT_LSE); error and foreground bit packed into one 32-bit
 //                        sort key:  key = ((bits(e) + 1) << 1) | fg  (e >= 0, so its fp32 bit pattern is monotone;
@@ -75,8 +76,8 @@ struct LovKeysParams {
   void* keys;             // (imgs * HW) uint32, or uint64 in batched mode
   uint32_t* vals;         // same count, or NULL (keys only)
   long long HW;
-  int C, c, n0;
-  int n_img;              // batched mode: number of images (= segments) in the launch
+  int C, c;
+  int n_img;              // number of images in the launch (batched mode: = segments)
 };
 
 // KeyT = uint32_t: one segment per launch (the images blockIdx.y of one group are concatenated, value = index in the group).
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) lovasz_keys_kernel(const LovKeysParams p)
   const int nl = blockIdx.y;
   const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (hw0 >= p.HW) return;
-  const size_t n = (size_t)(p.n0 + nl);
+  const size_t n = (size_t)nl;
   const size_t px = n * p.HW + hw0;
   const T* zp = reinterpret_cast<const T*>(p.logits) + (BINARY ? px : (n * p.C + p.c) * p.HW + hw0);
   float z[V];
@@ -252,7 +253,7 @@ struct LovGradParams {
   const uint32_t* tile_off;   // (segments, tiles per segment)
   double* seg_stat;           // segment 0: [0] loss accumulator, [1] gts + 1; segment s at + s * seg_stat_stride
   float* G;                   // NULL = forward only
-  float* Gseg;                // segment 0's slice of G: multi-class (C,N,HW) f32 at (c, n0), binary (N,HW) at n0
+  float* Gseg;                // slice of G where segment 0 starts: multi-class (C,N,HW) f32 at class c, binary (N,HW)
   long long len;              // items per segment (consecutive segments are `len` apart in keys, vals and G)
   int seg_stat_stride;
   int vec;
@@ -549,7 +550,7 @@ static int lov_fwd_typed(const b200seg_lovasz_desc* d, cudaStream_t st) {
     LovKeysParams kp;
     kp.logits = d->logits; kp.lse = d->lse; kp.lab16 = d->lab16;
     kp.keys = w.keys_a; kp.vals = pairs ? w.vals_a : nullptr;
-    kp.HW = HW; kp.C = d->C; kp.c = c; kp.n0 = 0; kp.n_img = d->N;
+    kp.HW = HW; kp.C = d->C; kp.c = c; kp.n_img = d->N;
     if (vec) {
       dim3 grid((unsigned)((HW / 4 + 255) / 256), d->N);
       if (binary) lovasz_keys_kernel<T, 4, true, KeyT><<<grid, 256, 0, st>>>(kp);
