@@ -13,6 +13,8 @@
  *   oc_accuracy_top1    models/losses/accuracy.py:41-60
  *   oc_argmax           core/evaluation/metrics.py:106 (argmax of logits; soft-max is monotone up to rounding)
  *   oc_areas            core/evaluation/metrics.py:236-270
+ *   oc_lovasz           models/losses/lovasz_loss.py:26-231 (lovasz_grad, lovasz_softmax(_flat), lovasz_hinge(_flat)) +
+ *                       the reductions of LovaszLoss.forward :272-298; the Jaccard increments in exact (integer-count) form
  *
  * Parity pinning: checked against tests/golden/ (recorded from the reference's own files) in tests/test_oracle_c.py.
  */
@@ -247,4 +249,122 @@ void oc_areas(const int64_t* pred, const float* gt, int64_t n, int C, int64_t ig
     if (pin) areas[C + p] += 1;
     if (gin) areas[2 * C + gi] += 1;
   }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Lovasz-Softmax / Lovasz hinge (models/losses/lovasz_loss.py). One SEGMENT = the valid pixels of one image group
+ * (the whole batch, or one image when per_image) for one class: errors sorted descending (ties by pixel index), the
+ * Jaccard index of the prefix sets first-differenced (lovasz_grad :26-39, here from integer counts: 1/U for a foreground
+ * item, I/(U(U-1)) otherwise, J_0 for the first), loss = sum e_i g_i.
+ *   logits (N,C,HW) multi-class / (N,HW) binary (C == 1); labels (N,HW) int64
+ *   class_mask (C) 1 = class takes part ('all' / list) ; only_present: skip classes without a foreground pixel (:153-154)
+ *   loss_out: n_groups doubles when per_image && reduction == none (0), else 1 ; grad_out_w: upstream gradient per
+ *   output (NULL = 1) ; grad (N,C,HW) doubles.                                                                      */
+typedef struct { double e; int64_t idx; int fg; } lv_item;
+static int lv_cmp(const void* a, const void* b) {
+  const lv_item* x = (const lv_item*)a; const lv_item* y = (const lv_item*)b;
+  if (x->e > y->e) return -1;
+  if (x->e < y->e) return 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+void oc_lovasz(const float* logits, const int64_t* labels, const float* class_weight, const uint8_t* class_mask, int N, int C,
+               int64_t HW, int has_ignore, int64_t ignore_index, int binary, int per_image, int only_present, int reduction,
+               double avg_factor, double loss_weight, const double* grad_out_w, double* loss_out, double* grad) {
+  const int n_groups = per_image ? N : 1;
+  const int imgs = per_image ? 1 : N;
+  const int64_t P = (int64_t)imgs * HW;
+  const double eps32 = 1.1920928955078125e-07;
+  double* prob = (double*)malloc(sizeof(double) * (size_t)N * C * HW);      /* soft-max probabilities (multi-class) */
+  double* G = (double*)calloc((size_t)N * C * HW, sizeof(double));          /* d loss_out / d p   (binary: / d z)   */
+  lv_item* items = (lv_item*)malloc(sizeof(lv_item) * (size_t)P);
+  double* gl = (double*)malloc(sizeof(double) * (size_t)n_groups);
+  memset(grad, 0, sizeof(double) * (size_t)N * C * HW);
+  if (!binary) {
+    for (int n = 0; n < N; ++n)
+      for (int64_t i = 0; i < HW; ++i) {
+        double m = -INFINITY, sum = 0.0;
+        for (int c = 0; c < C; ++c) { const double z = logits[((size_t)n * C + c) * HW + i]; if (z > m) m = z; }
+        for (int c = 0; c < C; ++c) sum += exp((double)logits[((size_t)n * C + c) * HW + i] - m);
+        for (int c = 0; c < C; ++c) prob[((size_t)n * C + c) * HW + i] = exp((double)logits[((size_t)n * C + c) * HW + i] - m) / sum;
+      }
+  }
+  double gscale = 1.0;
+  if (per_image && reduction == 1) gscale = avg_factor >= 0.0 ? 1.0 / (double)(float)((float)avg_factor + (float)eps32) : 1.0 / n_groups;
+  double total = 0.0;
+  for (int g = 0; g < n_groups; ++g) {
+    const int n0 = per_image ? g : 0;
+    double* lc = (double*)calloc((size_t)C, sizeof(double));
+    int* used = (int*)calloc((size_t)C, sizeof(int));
+    int cnt = 0;
+    for (int c = 0; c < C; ++c) {
+      if (!binary && class_mask && !class_mask[c]) continue;
+      int64_t m = 0, gts = 0;
+      for (int nl = 0; nl < imgs; ++nl)
+        for (int64_t i = 0; i < HW; ++i) {
+          const int64_t y = labels[(size_t)(n0 + nl) * HW + i];
+          if (has_ignore && y == ignore_index) continue;
+          lv_item it;
+          it.idx = (int64_t)nl * HW + i;
+          if (binary) {
+            it.fg = y != 0;
+            it.e = 1.0 - (double)logits[(size_t)(n0 + nl) * HW + i] * (it.fg ? 1.0 : -1.0);
+          } else {
+            it.fg = (y == c);
+            it.e = fabs((it.fg ? 1.0 : 0.0) - prob[((size_t)(n0 + nl) * C + c) * HW + i]);
+          }
+          gts += it.fg;
+          items[m++] = it;
+        }
+      if (!binary && only_present && gts == 0) continue;
+      if (m == 0 && !binary) { used[c] = 1; ++cnt; continue; }
+      qsort(items, (size_t)m, sizeof(lv_item), lv_cmp);
+      int64_t cum = 0;
+      double loss = 0.0;
+      for (int64_t i = 0; i < m; ++i) {
+        cum += items[i].fg;
+        const double I = (double)(gts - cum), U = (double)(gts + (i + 1) - cum);
+        const double gi = i == 0 ? 1.0 - I / U : (items[i].fg ? 1.0 / U : I / (U * (U - 1.0)));
+        const int nl = (int)(items[i].idx / HW);
+        const int64_t px = items[i].idx - (int64_t)nl * HW;
+        double* Gp = G + ((size_t)(n0 + nl) * C + c) * HW + px;
+        if (binary) {
+          const double e = items[i].e;
+          if (e > 0.0) { loss += e * gi; *Gp = items[i].fg ? -gi : gi; }   /* d relu(1 - z*sign)/dz = -sign */
+        } else {
+          loss += items[i].e * gi;
+          *Gp = items[i].fg ? -gi : gi;                                     /* d|fg - p|/dp */
+        }
+      }
+      lc[c] = loss;
+      used[c] = 1;
+      ++cnt;
+    }
+    double sum = 0.0;
+    for (int c = 0; c < C; ++c)
+      if (used[c]) sum += ((class_weight && !binary) ? (double)class_weight[c] : 1.0) * lc[c];
+    gl[g] = cnt ? sum / cnt : 0.0;
+    /* coefficient of every class of this group inside the returned value(s), then the soft-max Jacobian */
+    const int none_vec = per_image && reduction == 0;
+    const double up = (grad_out_w ? grad_out_w[none_vec ? g : 0] : 1.0) * loss_weight * gscale;
+    for (int nl = 0; nl < imgs; ++nl)
+      for (int64_t i = 0; i < HW; ++i) {
+        const size_t base = (size_t)(n0 + nl) * C * HW + i;
+        if (has_ignore && labels[(size_t)(n0 + nl) * HW + i] == ignore_index) continue;
+        if (binary) { grad[base] = up * G[base]; continue; }
+        double dot = 0.0;
+        for (int c = 0; c < C; ++c)
+          if (used[c]) dot += ((class_weight ? (double)class_weight[c] : 1.0) / cnt) * G[base + (size_t)c * HW] * prob[base + (size_t)c * HW];
+        for (int c = 0; c < C; ++c) {
+          const double a = used[c] ? ((class_weight ? (double)class_weight[c] : 1.0) / cnt) * G[base + (size_t)c * HW] : 0.0;
+          grad[base + (size_t)c * HW] = up * prob[base + (size_t)c * HW] * (a - dot);
+        }
+      }
+    if (none_vec) loss_out[g] = loss_weight * gl[g];
+    else total += gl[g];
+    free(lc);
+    free(used);
+  }
+  if (!(per_image && reduction == 0)) loss_out[0] = loss_weight * gscale * total;
+  free(prob); free(G); free(items); free(gl);
 }

@@ -100,3 +100,30 @@ def areas(pred, gt, num_classes, ignore_index):
     lib.oc_areas(_p(p, C.c_int64), _p(g, C.c_float), C.c_int64(p.size), num_classes, C.c_int64(int(ignore_index)),
                  _p(out, C.c_int64))
     return out.reshape(3, num_classes)
+
+
+def lovasz(logits, labels, loss_type='multi_class', classes='present', per_image=False, reduction='mean', class_weight=None,
+           loss_weight=1.0, avg_factor=None, ignore_index=255, grad_out=None):
+    """LovaszLoss forward + gradient in float64 (exact Jaccard increments). Returns dict(loss, grad)."""
+    lib = load()
+    x = _f32(logits)
+    y = np.ascontiguousarray(labels, dtype=np.int64)
+    binary = loss_type == 'binary'
+    N = x.shape[0]
+    Cc = 1 if binary else x.shape[1]
+    HW = x.size // (N * Cc)
+    mask = np.ones(Cc, dtype=np.uint8)
+    if isinstance(classes, (list, tuple)):
+        mask[:] = 0
+        mask[list(classes)] = 1
+    cw = _f32(class_weight)
+    n_out = N if (per_image and reduction == 'none') else 1
+    loss = np.zeros(n_out, dtype=np.float64)
+    grad = np.zeros(x.shape, dtype=np.float64)
+    go = None if grad_out is None else np.ascontiguousarray(grad_out, dtype=np.float64).reshape(-1)
+    lib.oc_lovasz(_p(x, C.c_float), _p(y, C.c_int64), _p(cw, C.c_float), _p(mask, C.c_uint8), N, Cc, C.c_int64(HW),
+                  int(ignore_index is not None), C.c_int64(int(ignore_index or 0)), int(binary), int(bool(per_image)),
+                  int(classes == 'present'), {'none': 0, 'mean': 1, 'sum': 2}[reduction],
+                  C.c_double(-1.0 if avg_factor is None else float(avg_factor)), C.c_double(float(loss_weight)),
+                  _p(go, C.c_double), _p(loss, C.c_double), _p(grad, C.c_double))
+    return dict(loss=loss if n_out > 1 else loss[0], grad=grad)

@@ -48,3 +48,16 @@ def test_c_oracle_resize_and_areas(golden):
         p = OC.argmax(data['process/logits%d' % i])
         a = OC.areas(p, data['process/gt%d' % i], 5, -1)
         np.testing.assert_array_equal(a, data['process/areas'][i][[0, 2, 3]].astype(np.int64))
+
+
+def test_c_oracle_lovasz_cases(golden):
+    """LovaszLoss (models/losses/lovasz_loss.py:26-312): the ATen-independent restatement against the reference's fixtures."""
+    data, manifest = golden
+    cases = [c for c in manifest['cases'] if c['kind'] == 'lovasz']
+    assert len(cases) >= 12
+    for case in cases:
+        name = case['name']
+        r = OC.lovasz(data[name + '/logits'], data[name + '/labels'], avg_factor=case.get('avg_factor'),
+                      ignore_index=case['ignore'], grad_out=data.get(name + '/grad_out'), **case['kw'])
+        assert _rel(r['loss'], data[name + '/loss']) < 1e-5, name
+        assert _rel(r['grad'], data[name + '/grad']) < 1e-4, name
