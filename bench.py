@@ -367,6 +367,25 @@ def b200_main(args):
         cpu_base = {'value': v, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                     'sample': 'full C2 batch (8 images), 6 timed steps of resize + CE fwd/bwd + accuracy on the host CPU '
                               '(torch %s, os.cpu_count()=%s), %.0f ms/step' % (torch.__version__, os.cpu_count(), ms_cpu)}
+        # the same restatement on CUDA tensors: the reference's unfused ATen chain on THIS GPU ("the kernel to
+        # beat on the same box") — a reported baseline like cpu_baseline, never on the product path
+        try:
+            xa = xs[0].detach().clone().requires_grad_(True)
+
+            def aten_step(i):
+                cpu_step(xa, ys[0], ign)
+
+            for i in range(2):
+                aten_step(i)
+            ms_aten = timed_events(aten_step, 10)
+            cpu_base['aten_chain_same_gpu'] = {
+                'value': px_step / ms_aten / 1e3, 'unit': 'Mpix/s', 'ms_per_step': ms_aten,
+                'note': 'F.interpolate -> F.cross_entropy -> weight_reduce_loss -> topk accuracy and their autograd backward '
+                        'on the same B200 and inputs (materialises the 319 MB up-sampled logits)'}
+            del xa
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            cpu_base['aten_chain_same_gpu'] = {'error': repr(ex)}
 
     if world > 1 and not args.no_extras:
         sharded = c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind)
