@@ -16,11 +16,15 @@ if r:
     print('  %s: %.1f us  %.0f GB/s  frac %.3f' % (r.get('kernel'), r['ms_per_launch'] * 1e3, r['achieved'], r['frac']))
 if 'cpu_baseline' in d:
     print('  cpu %.1f Mpix/s on %s cores; clocks %s' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores'], d.get('clocks')))
+    a = d['cpu_baseline'].get('aten_chain_same_gpu')
+    if a and 'value' in a:
+        print('  ATen chain on the same GPU: %.0f Mpix/s (%.2f ms/step)' % (a['value'], a['ms_per_step']))
 for k, v in d.get('workloads', {}).items():
     if isinstance(v, dict) and 'fwd' in v:
-        print('  %-28s fwd %.3f ms (%.2f)  fwd+bwd %.3f ms (%.2f)  %s' % (
-            k, v['fwd']['ms'], v['fwd']['roofline']['frac'], v['fwd_bwd']['ms'], v['fwd_bwd']['roofline']['frac'],
-            v['fwd_bwd'].get('plan', '')[:46]))
+        fr = lambda part: ('%.2f' % part['roofline']['frac']) if 'roofline' in part else 'n/a'
+        print('  %-28s fwd %.3f ms (%s)  fwd+bwd %.3f ms (%s)  %s' % (
+            k, v['fwd']['ms'], fr(v['fwd']), v['fwd_bwd']['ms'], fr(v['fwd_bwd']),
+            (v['fwd_bwd'].get('plan') or v.get('plan', ''))[:46]))
     elif isinstance(v, dict) and 'ms' in v:
         print('  %-28s %.3f ms  %.0f Mpix/s  frac %.2f' % (k, v['ms'], v['mpix_s'], v['roofline']['frac']))
     else:
