@@ -160,16 +160,16 @@ def reference_main(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_img = 1
-    value, ms = run_cpu(args.steps, min(args.warmup, 2), n_img)
+    n_img = C2['N']          # the full batch of the stated config (~0.2 s per step on 16 host cores)
+    value, ms = run_cpu(args.steps, args.warmup, n_img)
     cores = torch.get_num_threads()
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': min(args.warmup, 2), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(),
         'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d of the %d images of the batch per step (resize + CE fwd/bwd + accuracy, torch %s CPU, '
+                         'sample': 'full batch: %d of the %d images per step (resize + CE fwd/bwd + accuracy, torch %s CPU, '
                                    'os.cpu_count()=%s)' % (n_img, C2['N'], torch.__version__, os.cpu_count())},
         'e2e': {'value': value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -181,7 +181,8 @@ def workload_config():
     return {'workload': 'C2: FCN-style head, Cityscapes shape — fp32 logits (8,19,64,128) bilinear-resized (align_corners=False) '
                         'to 512x1024, CE ignore_index=255 + top-1 accuracy, forward+backward',
             'batch_per_gpu': C2['N'], 'num_classes': C2['C'], 'logit_hw': [C2['h'], C2['w']], 'label_hw': [C2['H'], C2['W']],
-            'label_dtype': 'int64', 'pixels_per_step_per_gpu': C2['N'] * C2['H'] * C2['W']}
+            'label_dtype': 'int64 on the device for value / roofline (the reference feeds label.long()); uint8 host label maps for e2e',
+            'pixels_per_step_per_gpu': C2['N'] * C2['H'] * C2['W']}
 
 
 # ---------------------------------------------------------------------------------------------- b200 arm
@@ -195,6 +196,72 @@ def timed_events(fn, iters, stream=None):
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) / iters
+
+
+class GraphRing:
+    """A step captured once per input set (the ring is larger than L2) and replayed; under torchrun ONE all-reduce of
+    the step's 8-double statistics vector rides on a side stream, ordered by events, off the compute stream."""
+
+    def __init__(self, step, n_sets, dev, world, dist):
+        self.R, self.world, self.dist, self.dev = n_sets, world, dist, dev
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(n_sets):
+                step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs, self.outs = [], []
+        for i in range(n_sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.outs.append(step(i))
+            self.graphs.append(g)
+        self.stats = [o['_stats'] for o in self.outs]
+        self.comm = torch.cuda.Stream(device=dev)
+        self.slot_free = [torch.cuda.Event() for _ in range(n_sets)]
+        self.ready = [torch.cuda.Event() for _ in range(n_sets)]
+
+    def run_step(self, k):
+        i = k % self.R
+        cur = torch.cuda.current_stream()
+        if self.world > 1:
+            cur.wait_event(self.slot_free[i])
+        self.graphs[i].replay()
+        if self.world > 1:  # one 64-byte all-reduce per step, off the compute stream
+            self.ready[i].record(cur)
+            self.comm.wait_event(self.ready[i])
+            with torch.cuda.stream(self.comm):
+                self.dist.all_reduce(self.stats[i], op=self.dist.ReduceOp.SUM)
+                self.slot_free[i].record(self.comm)
+
+    def drain(self):
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+    def timed(self, K, W):
+        """W warm-up steps, barrier, 3 more untimed steps (every rank is in steady state when its clock starts), then
+        exactly K steps between two CUDA events on the launching stream; max over ranks. Returns ms per step."""
+        for k in range(W):
+            self.run_step(k)
+        self.drain()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        for k in range(3):
+            self.run_step(W + k)
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for k in range(K):
+            self.run_step(W + 3 + k)
+        self.drain()
+        e_ev.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        t = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()) / K
 
 
 def b200_main(args):
@@ -217,6 +284,11 @@ def b200_main(args):
     K, W = args.steps, max(args.warmup, 3)
     N, Cc, h, w, H, Wd, ign = C2['N'], C2['C'], C2['h'], C2['w'], C2['H'], C2['W'], C2['ignore']
     px_step = N * H * Wd
+    # the clock sampler is a subprocess: started BEFORE the warm-up so that its start-up never sits between the barrier
+    # and the first timed step of rank 0 (the other ranks would wait for rank 0's all-reduce and report the wait)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
 
     # ---- ring of input sets: 8 x (5.0 MB logits + 33.6 MB labels) = 308 MB > 126 MB L2
     R = 8
@@ -238,63 +310,8 @@ def b200_main(args):
     torch.cuda.synchronize()
     launches_per_step = B.launch_count() - c0
 
-    # ---- capture one graph per input set
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for i in range(R):
-            step(i)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graphs, outs = [], []
-    for i in range(R):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            outs.append(step(i))
-        graphs.append(g)
-    stats = [o['_stats'] for o in outs]
-    comm = torch.cuda.Stream(device=dev)
-    slot_free = [torch.cuda.Event() for _ in range(R)]
-    ready = [torch.cuda.Event() for _ in range(R)]
-
-    def run_step(k):
-        i = k % R
-        cur = torch.cuda.current_stream()
-        if world > 1:
-            cur.wait_event(slot_free[i])
-        graphs[i].replay()
-        if world > 1:  # one 64-byte all-reduce per step, off the compute stream
-            ready[i].record(cur)
-            comm.wait_event(ready[i])
-            with torch.cuda.stream(comm):
-                dist.all_reduce(stats[i], op=dist.ReduceOp.SUM)
-                slot_free[i].record(comm)
-
-    for k in range(W):
-        run_step(k)
-    torch.cuda.current_stream().wait_stream(comm)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    torch.cuda.synchronize()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    for k in range(K):
-        run_step(k)
-    torch.cuda.current_stream().wait_stream(comm)
-    e_ev.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms_total = s_ev.elapsed_time(e_ev)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / K
+    ring = GraphRing(step, R, dev, world, dist)
+    ms_step = ring.timed(K, W)
     value = world * px_step / (ms_step * 1e-3) / 1e6
 
     # ---- e2e: host inputs, H2D + step + D2H every step, through the public API. The copies of step k+1 are issued on a
@@ -346,9 +363,10 @@ def b200_main(args):
             vals.append(world * px_step * e2e_steps / float(tt.item()) / 1e6)
         return sorted(vals)[1], xh[0].numel() * 4 + yh[0].numel() * yh[0].element_size(), vals
 
-    e2e_value, h2d, e2e_runs = e2e_run(torch.int64)
-    # same loop with the label maps kept uint8 on the host (the kernels read u8 directly): 8x fewer label bytes over PCIe
-    e2e_u8_value, h2d_u8, _ = e2e_run(torch.uint8)
+    # host label maps are uint8, as a segmentation pipeline delivers them (PNG masks; the reference casts with .long()
+    # AFTER the copy, cross_entropy_loss.py:283) — the kernels read uint8 directly. The int64-host variant is kept beside it.
+    e2e_value, h2d, e2e_runs = e2e_run(torch.uint8)
+    e2e_i64_value, h2d_i64, _ = e2e_run(torch.int64)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- dominant kernel alone (C ABI, CUDA events on the launching stream)
@@ -357,6 +375,7 @@ def b200_main(args):
     cpu_base = None
     if rank == 0:
         roof = kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
+    del ring
     if rank == 0 and world == 1:
         if not args.no_extras:
             try:
@@ -378,18 +397,25 @@ def b200_main(args):
             for i in range(2):
                 aten_step(i)
             ms_aten = timed_events(aten_step, 10)
-            cpu_base['aten_chain_same_gpu'] = {
-                'value': px_step / ms_aten / 1e3, 'unit': 'Mpix/s', 'ms_per_step': ms_aten,
-                'note': 'F.interpolate -> F.cross_entropy -> weight_reduce_loss -> topk accuracy and their autograd backward '
-                        'on the same B200 and inputs (materialises the 319 MB up-sampled logits)'}
+            cpu_base['aten_same_gpu_mpix_s'] = px_step / ms_aten / 1e3
+            cpu_base['aten_same_gpu_ms_per_step'] = ms_aten
+            cpu_base['aten_same_gpu_note'] = ('F.interpolate -> F.cross_entropy -> weight_reduce_loss -> topk accuracy and '
+                                              'their autograd backward on the same B200 and inputs')
             del xa
             torch.cuda.empty_cache()
         except Exception as ex:
-            cpu_base['aten_chain_same_gpu'] = {'error': repr(ex)}
+            cpu_base['aten_same_gpu_error'] = repr(ex)
 
     if world > 1 and not args.no_extras:
+        del xs, ys
+        torch.cuda.empty_cache()
+        try:
+            c4 = c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W)
+        except Exception as ex:
+            c4 = {'error': repr(ex)}
         sharded = c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind)
         if rank == 0:
+            extras['C4_dp'] = c4
             extras['C5i_miou_label_maps_sharded'] = sharded
 
     if rank == 0:
@@ -398,17 +424,18 @@ def b200_main(args):
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': dict(workload_config(), l2='ring of %d input sets (%.0f MB) > 126 MB L2; one CUDA graph per set' % (
-                R, R * (xs[0].numel() * 4 + ys[0].numel() * 8) / 1e6),
+                R, R * (N * Cc * h * w * 4 + N * H * Wd * 8) / 1e6),
                 cpu_affinity='GPU-local NUMA node (NVML)' if numa_bound else 'inherited',
                 collective='1 all_reduce(8 doubles)/step on a side stream'
                 if world > 1 else 'none (single GPU)'),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                    'steps': e2e_steps, 'repeats_mpix_s': [round(v, 1) for v in e2e_runs], 'note': 'pinned host logits + int64 labels copied every step on a copy stream (double-'
-                                                'buffered, overlapping the previous step), loss read back every step; PCIe-bound (38.5 MB at the '
-                                                'measured 54 GB/s pinned H2D rate = 0.71 ms/step = 5.9 Gpix/s); median of 3 repeats',
-                    'uint8_labels': {'value': e2e_u8_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d_u8,
-                                     'note': 'same step with the label maps kept uint8 on the host (read directly by the kernels)'}},
+                    'steps': e2e_steps, 'host_label_dtype': 'uint8',
+                    'repeats_mpix_s': [round(v, 1) for v in e2e_runs],
+                    'int64_host_labels_value': e2e_i64_value, 'int64_host_labels_h2d_bytes_per_step': h2d_i64,
+                    'note': 'pinned host fp32 logits + uint8 label maps (as a pipeline delivers masks; read directly by the '
+                            'kernels) copied every step on a copy stream, double-buffered; loss read back every step; '
+                            'median of 3 repeats. int64_host_labels_value = same loop with int64 host labels (8x label bytes)'},
             'gpu_launches': int(launches_per_step * K),
             'launches_per_step': int(launches_per_step),
             'roofline': roof,
@@ -417,10 +444,54 @@ def b200_main(args):
             line['cpu_baseline'] = cpu_base
         if extras:
             line['workloads'] = extras
+            flatten_workloads(line, extras)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def flatten_workloads(line, extras):
+    """The driver keeps scalar keys of the known objects: every workload's ms / roofline fraction is mirrored into
+    `roofline` as flat scalars (c3_*, c4_*, c5*_*), next to the nested `workloads` detail."""
+    r = line.get('roofline')
+    if not isinstance(r, dict):
+        return
+
+    def put(key, d, *path):
+        try:
+            for k in path:
+                d = d[k]
+            r[key] = d
+        except Exception:
+            pass
+
+    put('c3_fwd_bwd_ms', extras, 'C3_ade20k_bf16_ce_dice', 'fwd_bwd', 'ms')
+    put('c3_fwd_bwd_frac', extras, 'C3_ade20k_bf16_ce_dice', 'fwd_bwd', 'roofline', 'frac')
+    put('c3_fwd_ms', extras, 'C3_ade20k_bf16_ce_dice', 'fwd', 'ms')
+    put('c3_fwd_frac', extras, 'C3_ade20k_bf16_ce_dice', 'fwd', 'roofline', 'frac')
+    put('c3_ce_only_fwd_bwd_frac', extras, 'C3_ade20k_bf16_ce_only', 'fwd_bwd', 'roofline', 'frac')
+    put('c4_fwd_bwd_ms', extras, 'C4_voc_fp32_ce', 'fwd_bwd', 'ms')
+    put('c4_fwd_bwd_frac', extras, 'C4_voc_fp32_ce', 'fwd_bwd', 'roofline', 'frac')
+    put('c4_fwd_frac', extras, 'C4_voc_fp32_ce', 'fwd', 'roofline', 'frac')
+    put('c2_ac_true_ms', extras, 'C2_align_corners_true', 'fwd_bwd', 'ms')
+    put('c2_c150_general_ms', extras, 'C2_like_c150_64to512', 'fwd_bwd', 'ms')
+    put('c5i_ms', extras, 'C5i_miou_label_maps', 'ms')
+    put('c5i_frac', extras, 'C5i_miou_label_maps', 'roofline', 'frac')
+    put('c5ii_ms', extras, 'C5ii_miou_from_logits', 'ms')
+    put('c5ii_frac', extras, 'C5ii_miou_from_logits', 'roofline', 'frac')
+    put('c5_resized_ms', extras, 'C5_resized_lowres_logits', 'ms')
+    put('c5_resized_frac', extras, 'C5_resized_lowres_logits', 'roofline', 'frac')
+    put('lovasz_fwd_bwd_ms', extras, 'lovasz_softmax_cityscapes_shape', 'fwd_bwd', 'ms')
+    put('c4dp_strong_ms', extras, 'C4_dp', 'strong', 'ms')
+    put('c4dp_strong_frac', extras, 'C4_dp', 'strong', 'roofline', 'frac')
+    put('c4dp_strong_mpix_s', extras, 'C4_dp', 'strong', 'mpix_s')
+    put('c4dp_weak_ms', extras, 'C4_dp', 'weak', 'ms')
+    put('c4dp_weak_frac', extras, 'C4_dp', 'weak', 'roofline', 'frac')
+    put('c4dp_weak_mpix_s', extras, 'C4_dp', 'weak', 'mpix_s')
+    put('c5i_sharded_ms', extras, 'C5i_miou_label_maps_sharded', 'ms')
+    put('c5i_sharded_frac', extras, 'C5i_miou_label_maps_sharded', 'roofline', 'frac')
+    put('c5i_sharded_mpix_s', extras, 'C5i_miou_label_maps_sharded', 'mpix_s')
 
 
 def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind):
@@ -459,31 +530,74 @@ def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
     s = 4
     algo = 2 * N * Cc * h * w * s + N * H * Wd * 8          # logits read + gradient written + int64 labels read
     achieved = algo / (ms * 1e-3) / 1e9
-    traffic, warp_inst = None, None
-    try:   # DRAM bytes / executed warp instructions per launch of the same kernel and shape, from the committed ncu capture
-        with open(os.path.join(ROOT, 'profiles', 'traffic_r1g.json')) as fh:
-            k = json.load(fh)['kernels']['up_cell_kernel<float, 5, 1, 64, 6, 0>']
-        traffic, warp_inst = k['dram_bytes'], k['warp_inst']
-    except Exception:
-        pass
+    traffic, warp_inst, src = None, None, None
+    for name in ('traffic_r2.json', 'traffic_r1g.json'):   # DRAM bytes / warp instructions per launch from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as fh:
+                ks = json.load(fh)['kernels']
+            k = next(v for kk, v in ks.items() if kk.startswith('up_cell_kernel<float, 5, 1'))
+            traffic, warp_inst, src = k['dram_bytes'], k['warp_inst'], 'profiles/' + name
+            break
+        except Exception:
+            continue
     out = {'bound': 'hbm', 'kernel': 'up_cell_kernel<float,CPT=5,GRAD,64 threads,int64 labels>', 'achieved': achieved, 'peak': peak,
-           'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_kind': peak_kind, 'ms_per_launch': ms,
+           'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+           'traffic_source': (src + ' (ncu --set full capture of the same kernel and shape; not measured in this run)') if src else None,
+           'peak_kind': peak_kind, 'ms_per_launch': ms,
            'algorithmic_bytes_per_launch': algo,
            'note': 'not HBM bound: with the logits at 1/8 resolution the only full-resolution tensor touched is the label map '
                    '(33.6 of the 43.5 MB), while every output pixel owes C exponentials (MUFU) and ~11 issue slots per class; '
-                   'see issue_roofline and DESIGN.md. The HBM-bound kernels of the path are reported under workloads'}
+                   'see issue_frac and DESIGN.md. The HBM-bound kernels of the path are the c3_/c4_/c5 keys'}
     if warp_inst:
         sm_clock = 1.965e9
         issue_peak = 148 * 4 * sm_clock          # warp instructions / s: 4 schedulers x 148 SMs at clocks.max.sm
-        out['issue_roofline'] = {'bound': 'issue', 'achieved': warp_inst / (ms * 1e-3), 'peak': issue_peak, 'unit': 'warp-inst/s',
-                                 'frac': warp_inst / (ms * 1e-3) / issue_peak, 'warp_inst_per_launch': warp_inst}
+        out['issue_frac'] = warp_inst / (ms * 1e-3) / issue_peak
+        out['issue_warp_inst_per_launch'] = warp_inst
+        out['issue_peak_warp_inst_s'] = issue_peak
+    return out
+
+
+def c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W):
+    """BASELINE config 4 (PSPNet head at Pascal VOC shape: 21 classes, 512x512, fp32 CE fwd+bwd, batch 32) data-parallel
+    over the ranks: STRONG = the 32 images split over the GPUs, WEAK = 32 images on every GPU. CUDA-graph replay over a ring
+    of input sets larger than L2, one all-reduce of the statistics vector per step on a side stream."""
+    out = {}
+    Cn, Hh, Ww, ign = 21, 512, 512, 255
+    ce = B.CrossEntropyLoss()
+    for mode in ('strong', 'weak'):
+        n_loc = max(32 // world, 1) if mode == 'strong' else 32
+        set_bytes = n_loc * Cn * Hh * Ww * 4 * 2 + n_loc * Hh * Ww * 8
+        R = max(2, min(8, int(400e6 // set_bytes) + 1))
+        xs = [make_logits((n_loc, Cn, Hh, Ww), 4000 + 10 * i + rank, device=dev).requires_grad_(True) for i in range(R)]
+        ys = [make_labels((n_loc, Hh, Ww), Cn, 4000 + 10 * i + rank, ign, device=dev).unsqueeze(1) for i in range(R)]
+
+        def step(i):
+            xs[i].grad = None
+            r = B.fused_resize_losses(xs[i], ys[i], ce, ignore_index=ign, return_stats=True)
+            r['loss_ce'].backward()
+            return r
+
+        ring = GraphRing(step, R, dev, world, dist)
+        ms = ring.timed(K, W)
+        px = n_loc * world * Hh * Ww
+        algo = 2 * n_loc * world * Cn * Hh * Ww * 4 + px * 8          # single pass: read + write logits, read labels
+        a = algo / (ms * 1e-3) / 1e9
+        out[mode] = {'images_per_gpu': n_loc, 'global_batch': n_loc * world, 'ms': ms, 'mpix_s': px / ms / 1e3, 'n_gpus': world,
+                     'ring_sets': R,
+                     'roofline': {'bound': 'hbm', 'achieved': a, 'peak': peak * world, 'unit': 'GB/s', 'frac': a / (peak * world),
+                                  'peak_kind': peak_kind}}
+        del ring, xs, ys
+        torch.cuda.empty_cache()
+    out['note'] = ('ce_bulk_kernel + finalize per step from a CUDA graph; 1 all_reduce(8 doubles)/step on a side stream; '
+                   'strong = 32/G images per GPU, weak = 32 per GPU')
     return out
 
 
 def c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind):
-    """BASELINE config 5 across ranks: the 500-image sweep sharded by image (ceil split), one launch per rank for its
-    image list, then ONE packed all-reduce of the (3, C) int64 area totals. Timed with CUDA events between barriers,
-    max over ranks; pixels counted over all 500 images."""
+    """BASELINE config 5 across ranks: the 500-image sweep sharded by image (ceil split). Per sweep and rank: ONE
+    b200seg_confusion_labels launch that accumulates the (3, C) int64 totals of its image list inside the kernel, then ONE
+    int64 all-reduce of those 456 bytes. The image table of the (unchanging) buffers is uploaded once. Timed with CUDA
+    events between barriers, max over ranks; pixels counted over all 500 images."""
     Cn, n_img = 19, 500
     lo, hi = D.shard_range(n_img, rank, world)
     g = torch.Generator(device=dev).manual_seed(555 + rank)
@@ -491,16 +605,17 @@ def c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind):
     pred_base = [torch.randint(0, Cn, (1024, 2048), generator=g, device=dev) for _ in range(8)]
     preds = [pred_base[i % 8].clone() for i in range(lo, hi)]
     gt_all = [gts[i % 4].clone() for i in range(lo, hi)]
+    table = B.prepare_images(preds, gt_all, Cn)
 
     def sweep():
-        areas = B.areas_device(preds, gt_all, Cn, 255)
-        return D.all_reduce_areas({'areas': areas.sum(0)})['areas']
+        tot = B.area_totals_device(table, None, Cn, 255)
+        return D.all_reduce_areas({'areas': tot})['areas']
 
-    for _ in range(2):
+    for _ in range(3):
         tot = sweep()
     torch.cuda.synchronize()
     dist.barrier()
-    iters = 5
+    iters = 10
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s_ev.record()
     for _ in range(iters):
@@ -518,8 +633,8 @@ def c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind):
             'roofline': {'bound': 'hbm', 'achieved': a, 'peak': peak * world, 'unit': 'GB/s', 'frac': a / (peak * world),
                          'peak_kind': peak_kind},
             'all_reduced_label_pixels': label_px,
-            'note': 'sharded by image over the ranks, one b200seg_confusion_labels launch per rank + one packed all-reduce of '
-                    'the area totals per sweep'}
+            'note': 'sharded by image over the ranks; per sweep one b200seg_confusion_labels launch per rank (in-kernel (3,C) '
+                    'totals) + one int64 all-reduce of the area totals'}
 
 
 def extra_workloads(B, _lib, dev, peak, peak_kind):
@@ -608,7 +723,7 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     except Exception as e:   # the extra line must never cost the headline
         out['lovasz_softmax_cityscapes_shape'] = {'error': repr(e)}
 
-    # ---- C5: mIoU sweep. (i) 500 label maps 1024x2048 int64 + float32 gt, one launch; (ii) from logits, 100 images
+    # ---- C5: mIoU sweep. (i) 500 label maps 1024x2048 int64 + float32 gt, one launch; (ii) from logits, all 500 images
     Cn, n_img = 19, 500
     g = torch.Generator(device=dev).manual_seed(555)
     gts = [make_labels((1, 1024, 2048), Cn, 500 + i, 255, device=dev)[0].float() for i in range(4)]
@@ -629,9 +744,9 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
                                           '(worst case for the histogram), blocky ground truth'}
     del preds, pred_base
     torch.cuda.empty_cache()
-    n_l = 100
+    n_l = 500
     lbase = [make_logits((1, Cn, 1024, 2048), 900 + i, device=dev) for i in range(4)]
-    logits = [lbase[i % 4].clone() for i in range(n_l)]           # 100 x 159 MB = 15.9 GB
+    logits = [lbase[i % 4].clone() for i in range(n_l)]           # 500 x 159 MB = 79.7 GB of distinct buffers
     gl = gt_all[:n_l]
 
     def sweep2(i):
@@ -642,7 +757,9 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     px = n_l * 1024 * 2048
     out['C5ii_miou_from_logits'] = {'images': n_l, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
                                     'roofline': roof(px * (Cn * 4 + 4), ms), 'algorithmic_bytes': px * (Cn * 4 + 4),
-                                    'note': '100 of the 500 images (15.9 GB of fp32 logits), fused arg-max + areas'}
+                                    'note': 'all 500 images (79.7 GB of fp32 logits), fused arg-max + areas, one launch'}
+    del logits, lbase, gl, gt_all
+    torch.cuda.empty_cache()
     return out
 
 

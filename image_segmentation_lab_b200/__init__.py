@@ -16,9 +16,9 @@ Everything computes in libb200seg.so (include/b200seg.h); there is no CPU or PyT
 """
 from . import distributed, registry
 from ._lib import launch_count, lib_path, load as load_library
-from .evaluation import SegEvaluator, areas_device
+from .evaluation import ImageTable, SegEvaluator, area_totals_device, areas_device, prepare_images
 from .fused import B200DecodeHeadLossMixin, fused_resize_losses
-from .losses import (Accuracy, CrossEntropyLoss, DiceLoss, LovaszLoss, TverskyLoss, accuracy, cross_entropy, dice_loss, get_class_weight,
+from .losses import (Accuracy, CrossEntropyLoss, DiceLoss, LovaszLoss, TverskyLoss, accuracy, binary_cross_entropy, cross_entropy, dice_loss, get_class_weight,
                      reduce_loss, weight_reduce_loss, weighted_loss)
 from .ops import Upsample, add_prefix, resize
 from .train_utils import parse_losses
@@ -26,8 +26,8 @@ from .train_utils import parse_losses
 __version__ = '0.1.0'
 
 __all__ = [
-    'resize', 'Upsample', 'add_prefix', 'CrossEntropyLoss', 'cross_entropy', 'DiceLoss', 'dice_loss', 'TverskyLoss', 'LovaszLoss', 'accuracy',
-    'Accuracy', 'SegEvaluator', 'areas_device', 'fused_resize_losses', 'B200DecodeHeadLossMixin', 'registry',
+    'resize', 'Upsample', 'add_prefix', 'CrossEntropyLoss', 'cross_entropy', 'binary_cross_entropy', 'DiceLoss', 'dice_loss', 'TverskyLoss', 'LovaszLoss', 'accuracy',
+    'Accuracy', 'SegEvaluator', 'areas_device', 'area_totals_device', 'prepare_images', 'ImageTable', 'fused_resize_losses', 'B200DecodeHeadLossMixin', 'registry',
     'distributed', 'get_class_weight', 'reduce_loss', 'weight_reduce_loss', 'weighted_loss', 'load_library',
     'lib_path', 'launch_count', 'parse_losses',
 ]

@@ -18,9 +18,8 @@ L_U8, L_I16, L_I32, L_I64, L_F32, L_F64 = 0, 1, 2, 3, 4, 5
 WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 MODE_DICE, MODE_TVERSKY = 0, 1
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
-OUT_LOSS_CE, OUT_LOSS_DICE, OUT_ACC, OUT_WORDS = 0, 1, 2, 4
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 11
+ABI_VERSION = 12
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -60,7 +59,8 @@ class FinalizeDesc(C.Structure):
         ("ce_loss_weight", C.c_float), ("dice_loss_weight", C.c_float),
         ("dice_smooth", C.c_float), ("dice_reduction", C.c_int32),
         ("dice_ignore_index", C.c_int64),
-        ("out", C.c_void_p), ("dice_coef", C.c_void_p), ("log_vec", C.c_void_p),
+        ("out_loss_ce", C.c_void_p), ("out_loss_dice", C.c_void_p), ("out_acc", C.c_void_p),
+        ("dice_coef", C.c_void_p), ("log_vec", C.c_void_p),
         ("dice_mode", C.c_int32), ("tversky_alpha", C.c_float), ("tversky_beta", C.c_float), ("reserved0", C.c_int32),
     ]
 
@@ -147,9 +147,9 @@ SYMBOLS = [
     ("b200seg_resize_bilinear_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     ("b200seg_resize_bilinear_bwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     ("b200seg_resize_nearest_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
-    ("b200seg_confusion_labels", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
-    ("b200seg_confusion_logits", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p, _p]),
-    ("b200seg_confusion_logits_resized", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p, _p]),
+    ("b200seg_confusion_labels", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _i32, _p]),
+    ("b200seg_confusion_logits", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p, _i32, _p]),
+    ("b200seg_confusion_logits_resized", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p, _i32, _p]),
     ("b200seg_confusion_chunk_pixels", _i32, []),
     ("b200seg_topk_counts", C.c_int,
      [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _i64, C.POINTER(_i32), _i32, _i32, _f, _p, _p]),

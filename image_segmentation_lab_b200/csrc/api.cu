@@ -4,6 +4,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -25,6 +28,21 @@ int check_launch(const char* what) {
     set_error("%s launch failed: %s", what, cudaGetErrorString(e));
     return 3;
   }
+  return 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, device): remembered per pair, so that the first
+// launch on a second GPU of the same process opts in again, and safe from several host threads.
+int ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  B200SEG_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int& have = done[std::make_pair(func, dev)];
+  if (have >= bytes) return 0;
+  B200SEG_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have = bytes;
   return 0;
 }
 
@@ -133,7 +151,7 @@ extern "C" int b200seg_loss_fwd(const b200seg_loss_desc* d, void* stream) {
 }
 
 extern "C" int b200seg_loss_finalize(const b200seg_finalize_desc* d, void* stream) {
-  B200SEG_REQUIRE(d != nullptr && d->stats && d->out, "loss_finalize: NULL argument");
+  B200SEG_REQUIRE(d != nullptr && d->stats && d->out_loss_ce, "loss_finalize: NULL argument");
   B200SEG_REQUIRE(!(d->ce_has_avg_factor && d->ce_reduction == B200SEG_RED_SUM),
                   "avg_factor can not be used with reduction=\"sum\"");  // models/losses/utils.py:78-79
   B200SEG_REQUIRE(!(d->dice_has_avg_factor && d->dice_reduction == B200SEG_RED_SUM),

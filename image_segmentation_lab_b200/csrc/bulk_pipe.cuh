@@ -1,0 +1,51 @@
+// mbarrier / bulk-copy (TMA engine, non-tensor form) primitives shared by the bulk-copy pipelines, sm_100a.
+// SASS: cp.async.bulk -> UBLKCP.S.G / UBLKCP.G.S, expect_tx -> SYNCS.ARRIVE.TRANS64.
+#pragma once
+#include "common.cuh"
+
+namespace b200seg {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ long long smem_label(const unsigned char* row, int dt, int t) {
+  switch (dt) {
+    case B200SEG_L_U8: return (long long)row[t];
+    case B200SEG_L_I16: return (long long)reinterpret_cast<const short*>(row)[t];
+    case B200SEG_L_I32: return (long long)reinterpret_cast<const int*>(row)[t];
+    case B200SEG_L_I64: return reinterpret_cast<const long long*>(row)[t];
+    case B200SEG_L_F32: return (long long)reinterpret_cast<const float*>(row)[t];
+    default: return (long long)reinterpret_cast<const double*>(row)[t];
+  }
+}
+
+}  // namespace b200seg

@@ -16,6 +16,7 @@ constexpr int kSMs = 148;                            // B200: 2 dies x 74 SMs
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);
+int ensure_dyn_smem(const void* func, int bytes);   // per (kernel, device) opt-in to > 48 KB of dynamic shared memory
 
 #define B200SEG_REQUIRE(cond, ...)       \
   do {                                   \

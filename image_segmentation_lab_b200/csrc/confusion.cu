@@ -25,6 +25,7 @@ namespace b200seg {
 
 constexpr int kChunk = 4096;
 constexpr int kIgnored = -2;
+constexpr long long kMaxChunksPerFlush = 1ll << 18;   // totals mode: 2^30 pixels per CTA between flushes keep the 32-bit counters exact
 
 struct ConfParams {
   const b200seg_image* images;
@@ -36,6 +37,7 @@ struct ConfParams {
   long long ignore;
   long long* areas;
   long long* const* pred_out;
+  int totals_only;   // areas is (3,C): the sum over the images, flushed once per CTA instead of once per image touched
 };
 
 // Decoder of V consecutive samples of a label-like tensor into class indices.
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
   const long long chunk_end = (chunk + per < p.total_chunks) ? chunk + per : p.total_chunks;
   if (chunk >= chunk_end) return;
   int img = find_image(p.chunk_prefix, p.n_images, chunk);
+  long long since_flush = 0;
   constexpr int V = 8;
   ClassDecoder dgt, dpr;
   dgt.init(p.gt_dtype, C, true, p.ignore);
@@ -347,9 +350,15 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
         if (rn) ctr.update(rp, rg, rn);
       }
     }
-    ctr.flush(p.areas + (size_t)img * 3 * C);
+    if (!p.totals_only) {
+      ctr.flush(p.areas + (size_t)img * 3 * C);
+    } else {
+      since_flush += img_chunk_end - chunk;
+      if (since_flush >= kMaxChunksPerFlush) { ctr.flush(p.areas); since_flush = 0; }
+    }
     chunk = img_chunk_end;
   }
+  if (p.totals_only) ctr.flush(p.areas);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,6 +377,7 @@ __global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfPar
   const long long chunk_end = (chunk + per < p.total_chunks) ? chunk + per : p.total_chunks;
   if (chunk >= chunk_end) return;
   int img = find_image(p.chunk_prefix, p.n_images, chunk);
+  long long since_flush = 0;
   ClassDecoder dgt;
   dgt.init(p.gt_dtype, C, true, p.ignore);
   const bool ac = align_corners != 0;
@@ -404,9 +414,15 @@ __global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfPar
       if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv);
       else if (gv != kIgnored) ctr.update(bi, gv);
     }
-    ctr.flush(p.areas + (size_t)img * 3 * C);
+    if (!p.totals_only) {
+      ctr.flush(p.areas + (size_t)img * 3 * C);
+    } else {
+      since_flush += img_chunk_end - chunk;
+      if (since_flush >= kMaxChunksPerFlush) { ctr.flush(p.areas); since_flush = 0; }
+    }
     chunk = img_chunk_end;
   }
+  if (p.totals_only) ctr.flush(p.areas);
 }
 
 // Persistent grid: exactly (SMs x resident CTAs per SM), so the static chunk partition has no tail wave.
@@ -426,14 +442,12 @@ template <typename T, bool FROM_LOGITS> static int launch_confusion(const ConfPa
   int grid = 1;
   if (need256 <= 72 * 1024) {
     auto k = confusion_kernel<T, 256, true, FROM_LOGITS>;
-    static bool attr = false;
-    if (!attr) { B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); attr = true; }
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), 72 * 1024)) return e;
     if (int e = persistent_grid(k, 256, need256, p.total_chunks, &grid)) return e;
     k<<<grid, 256, need256, st>>>(p);
   } else if (need128 <= 200 * 1024) {
     auto k = confusion_kernel<T, 128, true, FROM_LOGITS>;
-    static bool attr = false;
-    if (!attr) { B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), 200 * 1024)) return e;
     if (int e = persistent_grid(k, 128, need128, p.total_chunks, &grid)) return e;
     k<<<grid, 128, need128, st>>>(p);
   } else {
@@ -450,8 +464,7 @@ template <typename T> static int launch_confusion_resize(const ConfParams& p, in
   int grid = 1;
   if (need256 <= 72 * 1024) {
     auto k = confusion_resize_kernel<T, 256, true>;
-    static bool attr = false;
-    if (!attr) { B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); attr = true; }
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), 72 * 1024)) return e;
     if (int e = persistent_grid(k, 256, need256, p.total_chunks, &grid)) return e;
     k<<<grid, 256, need256, st>>>(p, align_corners);
   } else {
@@ -472,14 +485,14 @@ extern "C" int32_t b200seg_confusion_chunk_pixels(void) { return kChunk; }
 extern "C" int b200seg_confusion_logits_resized(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                                                 int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype,
                                                 int32_t gt_dtype, int32_t C, int64_t ignore_index, int32_t align_corners,
-                                                int64_t* areas, int64_t* const* pred_out, void* stream) {
+                                                int64_t* areas, int64_t* const* pred_out, int32_t totals_only, void* stream) {
   B200SEG_REQUIRE(chunk_pixels == kChunk, "confusion: chunk_pixels must be %d", kChunk);
   B200SEG_REQUIRE(C >= 1 && C <= 4096, "confusion: num_classes %d out of range [1,4096]", C);
   B200SEG_REQUIRE(n_images >= 0 && areas, "confusion: bad arguments");
   if (n_images == 0 || total_chunks == 0) return 0;
   B200SEG_REQUIRE(images && chunk_prefix, "confusion: NULL image table");
   ConfParams p{images, (const long long*)chunk_prefix, n_images, total_chunks, 0, gt_dtype, C,
-               ignore_index, (long long*)areas, (long long* const*)pred_out};
+               ignore_index, (long long*)areas, (long long* const*)pred_out, totals_only};
   cudaStream_t st = (cudaStream_t)stream;
   switch (logit_dtype) {
     case B200SEG_F32: return launch_confusion_resize<float>(p, align_corners, st);
@@ -493,28 +506,28 @@ extern "C" int b200seg_confusion_logits_resized(const b200seg_image* images, con
 extern "C" int b200seg_confusion_labels(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                                         int64_t total_chunks, int32_t chunk_pixels, int32_t pred_dtype,
                                         int32_t gt_dtype, int32_t C, int64_t ignore_index, int64_t* areas,
-                                        void* stream) {
+                                        int32_t totals_only, void* stream) {
   B200SEG_REQUIRE(chunk_pixels == kChunk, "confusion: chunk_pixels must be %d", kChunk);
   B200SEG_REQUIRE(C >= 1 && C <= 4096, "confusion: num_classes %d out of range [1,4096]", C);
   B200SEG_REQUIRE(n_images >= 0 && areas, "confusion: bad arguments");
   if (n_images == 0 || total_chunks == 0) return 0;
   B200SEG_REQUIRE(images && chunk_prefix, "confusion: NULL image table");
   ConfParams p{images, (const long long*)chunk_prefix, n_images, total_chunks, pred_dtype, gt_dtype, C,
-               ignore_index, (long long*)areas, nullptr};
+               ignore_index, (long long*)areas, nullptr, totals_only};
   return launch_confusion<float, false>(p, (cudaStream_t)stream);
 }
 
 extern "C" int b200seg_confusion_logits(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                                         int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype,
                                         int32_t gt_dtype, int32_t C, int64_t ignore_index, int64_t* areas,
-                                        int64_t* const* pred_out, void* stream) {
+                                        int64_t* const* pred_out, int32_t totals_only, void* stream) {
   B200SEG_REQUIRE(chunk_pixels == kChunk, "confusion: chunk_pixels must be %d", kChunk);
   B200SEG_REQUIRE(C >= 1 && C <= 4096, "confusion: num_classes %d out of range [1,4096]", C);
   B200SEG_REQUIRE(n_images >= 0 && areas, "confusion: bad arguments");
   if (n_images == 0 || total_chunks == 0) return 0;
   B200SEG_REQUIRE(images && chunk_prefix, "confusion: NULL image table");
   ConfParams p{images, (const long long*)chunk_prefix, n_images, total_chunks, 0, gt_dtype, C,
-               ignore_index, (long long*)areas, (long long* const*)pred_out};
+               ignore_index, (long long*)areas, (long long* const*)pred_out, totals_only};
   cudaStream_t st = (cudaStream_t)stream;
   switch (logit_dtype) {
     case B200SEG_F32: return launch_confusion<float, true>(p, st);

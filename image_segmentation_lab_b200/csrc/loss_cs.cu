@@ -1,0 +1,644 @@
+// CE + Dice (+ top-1 accuracy) for MANY classes (32 < C <= 152) with ONE read of the logits per direction, sm_100a.
+//
+// Replaces, for class counts that do not fit one warp's register tile (ADE20K: 150 classes):
+//   forward   F.cross_entropy + weight_reduce_loss + accuracy + DiceLoss.forward
+//             (models/losses/cross_entropy_loss.py:56-72, models/losses/utils.py:48-80, models/losses/accuracy.py:41-60,
+//              models/losses/dice_loss.py:23-58,103-134: F.softmax, the int64 (N,H,W,C) one-hot, the C-iteration loop)
+//   backward  the autograd graph behind them
+// by ONE pass over the logits each way. The streaming kernels this supersedes (loss_stream.cu + loss_dice.cu) needed two
+// reads forward (log-sum-exp, then sum_px p_c^2) and two reads + one write backward (sum_c p_c g_c, then the gradient),
+// because a pixel's 150 soft-max values do not fit one thread and a register tile has no loads in flight while it is
+// computed on.
+//
+// Structure — a "class-sliced" bulk-copy pipeline:
+//   * A persistent CTA owns a contiguous range of 128-pixel tiles. A producer warp issues one `cp.async.bulk`
+//     (global -> shared, completion on an mbarrier) per class row of the tile plus one for the label row (and the saved
+//     log-sum-exp row in the backward), 2-4 stages ahead: bytes in flight are set by the stage count, not by registers.
+//   * Eight consumer warps; a warp owns 16 pixels of the tile, and inside the warp the 32 lanes form 4 pixel groups x 8
+//     CLASS SLICES: lane (j, g) holds classes {8 i + j} of pixels 4 g .. 4 g + 3 — CPT x 4 values, read with one 8-byte
+//     (16-bit logits) or 16-byte (fp32) shared-memory access per class row. Rows are padded by one warp span so that the
+//     8 x 4 accesses of a wavefront hit distinct banks.
+//   * Per-pixel reductions over the class dimension (max, sum of exponentials, the backward's dot product) are CPT
+//     register operations plus THREE xor-shuffles — the slices of a pixel live in one warp, so there is no CTA barrier
+//     and no shared-memory exchange. The maximum is taken on the PACKED 16-bit pairs (HMNMX2).
+//   * One MUFU.EX2 per element per direction: the exponentials stay in registers between the sum and the p^2 / gradient
+//     sweep.
+//   * Per-pixel scalar work (label decode, label logit, log, loss, accuracy, one-hot Dice terms) is done once per pixel
+//     by lane (j = pixel-in-group, g); its contribution to the backward's dot product rides on the same shuffle tree.
+//   * Backward: the tile is overwritten in place with the gradient and handed to a store warp (`cp.async.bulk`
+//     shared -> global).
+// Tiles are walked back to front by the backward kernel: with the same tile partition as the forward, every CTA starts on
+// the part of its range the forward left in the 126 MB L2.
+//
+// Top-1 accuracy: the label's class counts as the arg-max iff its logit equals the pixel's maximum (an exact tie with
+// another class counts as correct; torch.topk's choice among ties is unspecified) — same rule as the resize-fused kernel.
+//
+// Bound: HBM (forward is close to issue balance at 16-bit width: ~8.5 thread instructions per element).
+// Algorithmic bytes per launch: forward N*C*H*W*s + N*H*W*(L+4), backward 2*N*C*H*W*s + N*H*W*(L+4).
+#include "bulk_pipe.cuh"
+#include "common.cuh"
+
+namespace b200seg {
+
+constexpr int kCsSlices = 8;      // class slices per pixel group (lane bits 2..4)
+constexpr int kCsLanePx = 4;      // consecutive pixels per lane
+constexpr int kCsWarpPx = 16;     // pixels per consumer warp per tile (4 groups x 4 pixels)
+constexpr int kCsGroupWarps = 8;  // consumer warps per tile (a "group"); a CTA runs G groups on alternating tiles
+constexpr int kCsMaxStages = 4;
+
+struct CsParams {
+  const void* logits;
+  const void* labels;
+  const float* pw;
+  const float* cw;
+  float* lse;                        // forward: written; backward: read (bulk-copied with the tile)
+  unsigned long long* stats;
+  double* dice_part;                 // forward: (N,C,3) [sum p_y v, sum p^2, sum t]
+  const float* dice_coef;            // backward: (N,C,2) [alpha, beta]
+  const float* dice_grad_out;
+  const float* ce_grad_out;
+  void* grad;
+  int label_dtype, label_bytes;
+  int N, C;
+  long long HW;
+  int tiles_per_image;
+  long long total_tiles, tiles_per_cta;
+  int stages, stage_bytes, row_pitch, label_off, lse_off;
+  int flags;
+  long long ignore_index, dice_ignore;
+  int acc_has_ignore;
+  long long acc_ignore;
+  float ce_scale_host;
+  int ce_use_nvalid;
+};
+
+// PX consecutive pixels of one class row in the storage format (16-bit logits stay packed): a lane's 4 pixels of a
+// tile are processed as 4 / PX passes — two passes of 2 pixels for 16-bit logits (the live exponentials of 4 pixels x 19
+// classes do not fit the 96 registers two resident CTAs leave a thread), one pass of 4 for fp32 (one CTA per SM).
+template <typename T> struct CsCfg {
+  static constexpr int PX = sizeof(T) == 2 ? 2 : 4;
+  static constexpr int kPasses = kCsLanePx / PX;
+  static constexpr int kWords = PX * (int)sizeof(T) / 4;      // 1 (16-bit) or 4 (fp32)
+  static constexpr int kPadPx = sizeof(T) == 2 ? 8 : 16;      // row padding: the 8 slices x 4 groups of a wavefront hit distinct banks
+};
+template <typename T> struct CsRow {
+  uint32_t w[CsCfg<T>::kWords];
+};
+template <typename T> __device__ __forceinline__ CsRow<T> cs_load(const unsigned char* p) {
+  CsRow<T> r;
+  if constexpr (sizeof(T) == 4) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    r.w[0] = t.x; r.w[1] = t.y; r.w[2] = t.z; r.w[3] = t.w;
+  } else {
+    r.w[0] = *reinterpret_cast<const uint32_t*>(p);
+  }
+  return r;
+}
+template <typename T> __device__ __forceinline__ void cs_unpack(const CsRow<T>& r, float (&z)[CsCfg<T>::PX]) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = __uint_as_float(r.w[k]);
+  } else {
+    unpack2<T>(r.w[0], z[0], z[1]);
+  }
+}
+template <typename T> __device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t max2_packed<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t max2_packed<__half>(uint32_t a, uint32_t b) {
+  const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <typename T> __device__ __forceinline__ void cs_max(CsRow<T>& m, const CsRow<T>& z) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m.w[k] = __float_as_uint(fmaxf(__uint_as_float(m.w[k]), __uint_as_float(z.w[k])));
+  } else {
+    m.w[0] = max2_packed<T>(m.w[0], z.w[0]);
+  }
+}
+template <typename T> __device__ __forceinline__ void cs_store(unsigned char* p, const float (&g)[CsCfg<T>::PX]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]), __float_as_uint(g[3]));
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = pack2<T>(g[0], g[1]);
+  }
+}
+template <typename T> __device__ __forceinline__ uint32_t neg_inf_word() {
+  if constexpr (sizeof(T) == 4) return 0xff800000u;
+  else if constexpr (Elem<T>::kDtype == B200SEG_BF16) return 0xff80ff80u;
+  else return 0xfc00fc00u;
+}
+__device__ __forceinline__ float pick4(const float (&a)[4], int k) {
+  return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3]));
+}
+
+// One tile of the CTA's range: image, first pixel, pixel count.
+struct CsTile {
+  int n, npx;
+  long long px0;
+};
+__device__ __forceinline__ CsTile cs_tile(const CsParams& p, long long t, int TP) {
+  CsTile r;
+  r.n = (int)(t / p.tiles_per_image);
+  r.px0 = (t - (long long)r.n * p.tiles_per_image) * TP;
+  r.npx = (int)((p.HW - r.px0 < TP) ? p.HW - r.px0 : TP);
+  return r;
+}
+
+// Producer warp body shared by both directions (REVERSE walks the range back to front).
+template <typename T, bool WITH_LSE, bool REVERSE>
+__device__ __forceinline__ void cs_producer(const CsParams& p, unsigned char* smem, unsigned long long* full_bar,
+                                            unsigned long long* empty_bar, long long t0, long long t1, int TP, int lane) {
+  const int C = p.C, NS = p.stages;
+  int k = 0;
+  for (long long tt = t0; tt < t1; ++tt, ++k) {
+    const long long t = REVERSE ? (t1 - 1 - (tt - t0)) : tt;
+    const int s = k % NS;
+    if (k >= NS) mbar_wait(&empty_bar[s], ((k / NS) - 1) & 1);
+    const CsTile tl = cs_tile(p, t, TP);
+    const unsigned row_bytes = (unsigned)(tl.npx * sizeof(T));
+    const unsigned lab_bytes = (unsigned)(tl.npx * p.label_bytes);
+    const unsigned lse_bytes = WITH_LSE ? (unsigned)(tl.npx * 4) : 0u;
+    unsigned char* stage = smem + (size_t)s * p.stage_bytes;
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (unsigned)C * row_bytes + lab_bytes + lse_bytes);
+    __syncwarp();
+    const char* src = reinterpret_cast<const char*>(p.logits) + ((size_t)tl.n * C * p.HW + tl.px0) * sizeof(T);
+    for (int c = lane; c < C; c += 32)
+      bulk_g2s(stage + (size_t)c * p.row_pitch, src + (size_t)c * p.HW * sizeof(T), row_bytes, &full_bar[s]);
+    if (lane == 0)
+      bulk_g2s(stage + p.label_off, reinterpret_cast<const char*>(p.labels) + ((size_t)tl.n * p.HW + tl.px0) * p.label_bytes,
+               lab_bytes, &full_bar[s]);
+    if (WITH_LSE && lane == 1)
+      bulk_g2s(stage + p.lse_off, reinterpret_cast<const char*>(p.lse + (size_t)tl.n * p.HW + tl.px0), lse_bytes, &full_bar[s]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <typename T, int CPT, int G>
+__global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel(const CsParams p) {
+  constexpr int NWG = kCsGroupWarps, NW = NWG * G;
+  constexpr int TP = NWG * kCsWarpPx;
+  constexpr int CP = CPT * kCsSlices;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[kCsMaxStages], empty_bar[kCsMaxStages];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, NS = p.stages, RP = p.row_pitch;
+  const bool dice = (p.flags & B200SEG_WANT_DICE) != 0;
+  float* bins = reinterpret_cast<float*>(smem_raw + (size_t)NS * p.stage_bytes);   // [NW][2][C]
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWG); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // rows C..CP-1 of every stage are never written by the bulk copies: -inf once (exp -> 0, max unaffected)
+  {
+    const int words_per_row = (TP * (int)sizeof(T)) / 4;
+    const int pad_words = (CP - C) * words_per_row;
+    for (int s = 0; s < NS; ++s)
+      for (int i = tid; i < pad_words; i += blockDim.x) {
+        const int r = i / words_per_row, wd = i - r * words_per_row;
+        reinterpret_cast<uint32_t*>(smem_raw + (size_t)s * p.stage_bytes + (size_t)(C + r) * RP)[wd] = neg_inf_word<T>();
+      }
+    for (int i = tid; i < NW * 2 * C; i += blockDim.x) bins[i] = 0.f;
+  }
+  __syncthreads();
+
+  const long long t0 = (long long)blockIdx.x * p.tiles_per_cta;
+  const long long t1 = (t0 + p.tiles_per_cta < p.total_tiles) ? t0 + p.tiles_per_cta : p.total_tiles;
+  float loss_acc = 0.f;
+  int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
+
+  if (warp == NW) {
+    cs_producer<T, false, false>(p, smem_raw, full_bar, empty_bar, t0, t1, TP, lane);
+  } else {
+    constexpr int PX = CsCfg<T>::PX, kPasses = CsCfg<T>::kPasses;
+    const int j = lane >> 2, g = lane & 3;
+    const int grp = warp / NWG;
+    const int pxo = (warp % NWG) * kCsWarpPx;                // first pixel of this warp inside the tile
+    float* A_w = bins + (size_t)warp * 2 * C;
+    float* T_w = A_w + C;
+    float acc[CPT];                                          // sum_px p_c^2 of this lane's classes for the current image
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
+    int n_cur = -1;
+
+    auto flush_image = [&](int n) {
+      if (dice) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float t = acc[i];
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          const int c = i * kCsSlices + j;
+          if (g == 0 && c < C) atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 1, (double)t);
+          acc[i] = 0.f;
+        }
+        __syncwarp();
+        for (int c = lane; c < C; c += 32) {
+          const float a = A_w[c], t = T_w[c];
+          if (t != 0.f) {
+            atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 0, (double)a);
+            atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 2, (double)t);
+            A_w[c] = 0.f;
+            T_w[c] = 0.f;
+          }
+        }
+        __syncwarp();
+      }
+    };
+
+    for (int k = grp; k < (int)(t1 - t0); k += G) {     // group grp consumes tiles grp, grp + G, ... of the CTA's range
+      const long long t = t0 + k;
+      const int s = k % NS;
+      const CsTile tl = cs_tile(p, t, TP);
+      if (tl.n != n_cur) {
+        if (n_cur >= 0) flush_image(n_cur);
+        n_cur = tl.n;
+      }
+      mbar_wait(&full_bar[s], (k / NS) & 1);
+      const unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
+      float m[4], S[4];                                     // per pixel of this lane (all 4, both passes)
+#pragma unroll
+      for (int h = 0; h < kPasses; ++h) {
+        const int pxh = pxo + h * 4 * PX + g * PX;          // first pixel of this lane in pass h
+        const unsigned char* col = stage + (size_t)j * RP + (size_t)pxh * sizeof(T);   // class 8 i + j: col + i * 8 * RP
+        const bool in = pxh < tl.npx;   // npx is a multiple of 16 bytes / sizeof(T) >= PX: a lane's pixels are all in or all out
+
+        // sweep 1: the lane's CPT x PX logits (kept packed) and their maximum per pixel
+        CsRow<T> zr[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) zr[i] = cs_load<T>(col + (size_t)i * kCsSlices * RP);
+        CsRow<T> mx = zr[0];
+#pragma unroll
+        for (int i = 1; i < CPT; ++i) cs_max<T>(mx, zr[i]);
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+          CsRow<T> ot;
+#pragma unroll
+          for (int q = 0; q < CsCfg<T>::kWords; ++q) ot.w[q] = __shfl_xor_sync(0xffffffffu, mx.w[q], o);
+          cs_max<T>(mx, ot);
+        }
+        float mh[PX], nm[PX], Sh[PX];
+        cs_unpack<T>(mx, mh);
+#pragma unroll
+        for (int v = 0; v < PX; ++v) { nm[v] = -mh[v] * kLog2e; Sh[v] = 0.f; }
+
+        // sweep 2: exponentials (kept) and their sum
+        float e[CPT][PX];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float z[PX];
+          cs_unpack<T>(zr[i], z);
+#pragma unroll
+          for (int v = 0; v < PX; ++v) {
+            e[i][v] = ex2(fmaf(z[v], kLog2e, nm[v]));
+            Sh[v] += e[i][v];
+          }
+        }
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+          for (int v = 0; v < PX; ++v) Sh[v] += __shfl_xor_sync(0xffffffffu, Sh[v], o);
+        }
+
+        // sweep 3: sum_px p^2 per class (Dice denominator: NOT masked by the valid mask, dice_loss.py:55-56)
+        if (dice && in) {
+          float r[PX];
+#pragma unroll
+          for (int v = 0; v < PX; ++v) r[v] = fast_rcp(Sh[v]);
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+            for (int v = 0; v < PX; ++v) {
+              const float pr = e[i][v] * r[v];
+              acc[i] = fmaf(pr, pr, acc[i]);
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < PX; ++v) { m[h * PX + v] = mh[v]; S[h * PX + v] = Sh[v]; }
+      }
+
+      // per-pixel scalar work: lane (j < 4, g) owns pixel (pass j / PX, v = j % PX) of group g
+      int cls = -1;
+      float pyv = 0.f;
+      const int t_px = pxo + (j / PX) * 4 * PX + g * PX + (j % PX);
+      if (j < 4 && t_px < tl.npx) {
+        const float m_own = pick4(m, j), S_own = pick4(S, j);
+        const float lse = m_own + fast_log(S_own);
+        const long long yy = smem_label(stage + p.label_off, p.label_dtype, t_px);
+        const bool ign = (yy == p.ignore_index);
+        const bool inr = (yy >= 0 && yy < (long long)C);
+        const bool valid = !ign && inr;
+        n_bad += (!ign && !inr);
+        n_valid += !ign;
+        const int ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);
+        const float zy = to_float<T>(reinterpret_cast<const T*>(stage + (size_t)ycc * RP)[t_px]);
+        const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
+        if (valid && (p.flags & B200SEG_WANT_CE)) {
+          const float wt = p.cw ? __ldg(p.cw + ycc) : 1.f;
+          const float pwv = p.pw ? __ldg(p.pw + gpx) : 1.f;
+          loss_acc = fmaf(wt * pwv, lse - zy, loss_acc);
+        }
+        const bool av = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
+        n_acc += av;
+        n_correct += (av && inr && zy == m_own);
+        if (dice) {
+          const bool dv = (yy != p.dice_ignore);                       // valid_mask
+          cls = ycc;                                                   // one-hot of the CLAMPED label (dice_loss.py:119-122)
+          pyv = dv ? ex2((zy - lse) * kLog2e) : 0.f;
+        }
+        if (p.lse) p.lse[gpx] = lse;
+      }
+      if (dice) onehot_bins_add(A_w, T_w, cls, pyv, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    if (n_cur >= 0) flush_image(n_cur);
+  }
+  cta_flush_stats(loss_acc, n_valid, n_correct, n_bad, n_acc, p.stats, (p.flags & B200SEG_WANT_CE) != 0);
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// grad_c = p_c (b_c p_c + sub) - onehot_c (p_y da + kk),   sub = kk - dot,   dot = sum_c b_c p_c^2 - da p_y
+//   b_c = 2 god beta[n][c],  da = god alpha[n][y] (Dice-valid pixels),  kk = Gce pw cw[y] (CE-valid pixels)
+template <typename T, int CPT, int G>
+__global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel(const CsParams p) {
+  constexpr int NWG = kCsGroupWarps, NW = NWG * G;
+  constexpr int TP = NWG * kCsWarpPx;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[kCsMaxStages], done_bar[kCsMaxStages], empty_bar[kCsMaxStages];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, NS = p.stages, RP = p.row_pitch;
+  constexpr int CP = CPT * kCsSlices;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&done_bar[s], NWG); mbar_init(&empty_bar[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const int words_per_row = (TP * (int)sizeof(T)) / 4;
+    const int pad_words = (CP - C) * words_per_row;
+    for (int s = 0; s < NS; ++s)
+      for (int i = tid; i < pad_words; i += blockDim.x) {
+        const int r = i / words_per_row, wd = i - r * words_per_row;
+        reinterpret_cast<uint32_t*>(smem_raw + (size_t)s * p.stage_bytes + (size_t)(C + r) * RP)[wd] = neg_inf_word<T>();
+      }
+  }
+  __syncthreads();
+  const long long t0 = (long long)blockIdx.x * p.tiles_per_cta;
+  const long long t1 = (t0 + p.tiles_per_cta < p.total_tiles) ? t0 + p.tiles_per_cta : p.total_tiles;
+
+  if (warp == NW) {
+    cs_producer<T, true, true>(p, smem_raw, full_bar, empty_bar, t0, t1, TP, lane);
+  } else if (warp == NW + 1) {
+    // store warp: every lane hands its class rows of a finished tile to the bulk-store engine; the stage goes back to the
+    // producer as soon as the engine has READ it
+    int k = 0;
+    for (long long tt = t0; tt < t1; ++tt, ++k) {
+      const long long t = t1 - 1 - (tt - t0);
+      const int s = k % NS;
+      mbar_wait(&done_bar[s], (k / NS) & 1);
+      const CsTile tl = cs_tile(p, t, TP);
+      const unsigned row_bytes = (unsigned)(tl.npx * sizeof(T));
+      unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
+      char* dst = reinterpret_cast<char*>(p.grad) + ((size_t)tl.n * C * p.HW + tl.px0) * sizeof(T);
+      for (int c = lane; c < C; c += 32) bulk_s2g(dst + (size_t)c * p.HW * sizeof(T), stage + (size_t)c * RP, row_bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    constexpr int PX = CsCfg<T>::PX, kPasses = CsCfg<T>::kPasses;
+    const int j = lane >> 2, g = lane & 3;
+    const int grp = warp / NWG;
+    const int pxo = (warp % NWG) * kCsWarpPx;
+    const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;
+    const float god = p.dice_grad_out ? __ldg(p.dice_grad_out) : 1.f;
+    float Gce = 0.f;
+    if (want_ce) {
+      Gce = p.ce_scale_host;
+      if (p.ce_grad_out) Gce *= __ldg(p.ce_grad_out);
+      if (p.ce_use_nvalid) {
+        const double nv = (double)(long long)p.stats[B200SEG_ST_N_VALID];
+        Gce = (float)((double)Gce / (nv + 1.1920928955078125e-07));
+      }
+    }
+    float b[CPT];
+    int n_cur = -1;
+    for (int k = grp; k < (int)(t1 - t0); k += G) {
+      const long long t = t1 - 1 - k;
+      const int s = k % NS;
+      const CsTile tl = cs_tile(p, t, TP);
+      if (tl.n != n_cur) {
+        n_cur = tl.n;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int c = i * kCsSlices + j;
+          b[i] = c < C ? 2.f * god * __ldg(p.dice_coef + ((size_t)tl.n * C + c) * 2 + 1) : 0.f;
+        }
+      }
+      mbar_wait(&full_bar[s], (k / NS) & 1);
+      unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
+
+      // per-pixel scalars of the pixel this lane owns (lane j < 4: pass j / PX, v = j % PX): issued first, consumed
+      // after the class sweep
+      float extra = 0.f, py = 0.f, da = 0.f, kk = 0.f, by = 0.f;
+      int ycc = 0;
+      const int t_px = pxo + (j / PX) * 4 * PX + g * PX + (j % PX);
+      const bool owner = (j < 4) && t_px < tl.npx;
+      if (owner) {
+        const long long yy = smem_label(stage + p.label_off, p.label_dtype, t_px);
+        const bool valid = (yy != p.ignore_index) && yy >= 0 && yy < (long long)C;
+        ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);
+        const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
+        if (want_ce && valid) kk = Gce * (p.pw ? __ldg(p.pw + gpx) : 1.f) * (p.cw ? __ldg(p.cw + ycc) : 1.f);
+        if (yy != p.dice_ignore) da = god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 0);
+        by = 2.f * god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 1);
+        const float lse_own = reinterpret_cast<const float*>(stage + p.lse_off)[t_px];
+        const float zy = to_float<T>(reinterpret_cast<const T*>(stage + (size_t)ycc * RP)[t_px]);
+        py = ex2(fmaf(zy, kLog2e, -lse_own * kLog2e));
+        extra = -fmaf(da, py, kk);
+      }
+      float Down = 0.f;                                     // D of the owned pixel (set in its pass)
+#pragma unroll
+      for (int h = 0; h < kPasses; ++h) {
+        const int pxh = pxo + h * 4 * PX + g * PX;
+        unsigned char* col = stage + (size_t)j * RP + (size_t)pxh * sizeof(T);
+        float nl[PX], D[PX];
+#pragma unroll
+        for (int v = 0; v < PX; ++v) {
+          nl[v] = -reinterpret_cast<const float*>(stage + p.lse_off)[pxh + v] * kLog2e;
+          D[v] = 0.f;
+        }
+        float pr[CPT][PX];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const CsRow<T> zr = cs_load<T>(col + (size_t)i * kCsSlices * RP);
+          float z[PX];
+          cs_unpack<T>(zr, z);
+#pragma unroll
+          for (int v = 0; v < PX; ++v) {
+            pr[i][v] = ex2(fmaf(z[v], kLog2e, nl[v]));
+            D[v] = fmaf(pr[i][v] * b[i], pr[i][v], D[v]);
+          }
+        }
+        // the owner adds -(da p_y + kk): after the tree every lane of the pixel holds D = dot - kk = -sub
+#pragma unroll
+        for (int v = 0; v < PX; ++v) D[v] += (j == h * PX + v) ? extra : 0.f;
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+          for (int v = 0; v < PX; ++v) D[v] += __shfl_xor_sync(0xffffffffu, D[v], o);
+        }
+#pragma unroll
+        for (int v = 0; v < PX; ++v) Down = (j == h * PX + v) ? D[v] : Down;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float gq[PX];
+#pragma unroll
+          for (int v = 0; v < PX; ++v) gq[v] = pr[i][v] * fmaf(pr[i][v], b[i], -D[v]);
+          if (i < CPT - 1 || i * kCsSlices + j < C) cs_store<T>(col + (size_t)i * kCsSlices * RP, gq);   // pad rows stay -inf
+        }
+      }
+      __syncwarp();
+      // one-hot term: the label's class is re-stored by the owner (after the slice lanes, same warp) with -(p_y da + kk)
+      if (owner && (da != 0.f || kk != 0.f))
+        reinterpret_cast<T*>(stage + (size_t)ycc * RP)[t_px] = from_float<T>(py * fmaf(py, by, -Down) - fmaf(py, da, kk));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done_bar[s]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct CsGeom {
+  int cpt, stages, stage_bytes, row_pitch, label_off, lse_off, ctas_per_sm;
+  size_t smem_fwd, smem_bwd;
+};
+
+static int cs_cpt_for(int C) {
+  if (C <= 64) return 8;
+  if (C <= 96) return 12;
+  if (C <= 128) return 16;
+  if (C <= 152) return 19;
+  return 0;
+}
+
+static bool cs_geometry(int C, int elem, CsGeom* g) {
+  const int cpt = cs_cpt_for(C);
+  if (!cpt) return false;
+  constexpr int TP = 8 * kCsWarpPx;
+  g->cpt = cpt;
+  g->row_pitch = (TP + (elem == 2 ? 8 : 16)) * elem;   // CsCfg<T>::kPadPx
+  g->label_off = cpt * kCsSlices * g->row_pitch;
+  g->lse_off = g->label_off + TP * 8;
+  g->stage_bytes = g->lse_off + TP * 4;
+  g->ctas_per_sm = 1;
+  const size_t bins = (size_t)kCsGroupWarps * (elem == 2 ? 2 : 1) * 2 * C * sizeof(float);
+  const size_t budget = (size_t)(225 * 1024);
+  int st = (int)((budget - bins) / g->stage_bytes);
+  if (st > kCsMaxStages) st = kCsMaxStages;
+  if (st < 2) return false;
+  g->stages = st;
+  g->smem_fwd = (size_t)st * g->stage_bytes + bins;
+  g->smem_bwd = (size_t)st * g->stage_bytes;
+  return true;
+}
+
+// 16-byte tileable CE + Dice (exponent 2) at label resolution with 32 < C <= 152
+bool cs_supported(const void* logits, const void* labels, const void* lse, const void* grad, int logit_dtype, int label_dtype,
+                  int C, long long HW, float dice_exponent, int dice_mode, bool want_dice) {
+  if (C <= 32 || !cs_cpt_for(C) || HW < 1) return false;
+  if (want_dice && (dice_mode != B200SEG_MODE_DICE || dice_exponent != 2.f)) return false;
+  const int elem = logit_bytes(logit_dtype), lb = label_bytes(label_dtype);
+  if (!aligned16(logits) || !aligned16(labels) || !aligned16(lse) || (grad && !aligned16(grad))) return false;
+  if ((HW * elem) % 16 || (HW * lb) % 16 || (HW * 4) % 16) return false;
+  CsGeom g;
+  return cs_geometry(C, elem, &g);
+}
+
+template <typename T, int CPT, bool BWD> static int cs_launch_t(CsParams p, const CsGeom& g, cudaStream_t st) {
+  constexpr int G = sizeof(T) == 2 ? 2 : 1;   // 16-bit: two consumer groups share one CTA (112 registers per thread)
+  constexpr int NW = kCsGroupWarps * G;
+  long long grid = (long long)kSMs * g.ctas_per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
+  grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  if constexpr (BWD) {
+    auto k = cs_bwd_kernel<T, CPT, G>;
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)g.smem_bwd)) return e;
+    k<<<(unsigned)grid, (NW + 2) * 32, g.smem_bwd, st>>>(p);
+    count_launch();
+    return check_launch("cs_bwd_kernel");
+  } else {
+    auto k = cs_fwd_kernel<T, CPT, G>;
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)g.smem_fwd)) return e;
+    k<<<(unsigned)grid, (NW + 1) * 32, g.smem_fwd, st>>>(p);
+    count_launch();
+    return check_launch("cs_fwd_kernel");
+  }
+}
+
+template <typename T, bool BWD> static int cs_launch(const CsParams& p, const CsGeom& g, cudaStream_t st) {
+  switch (g.cpt) {
+    case 8: return cs_launch_t<T, 8, BWD>(p, g, st);
+    case 12: return cs_launch_t<T, 12, BWD>(p, g, st);
+    case 16: return cs_launch_t<T, 16, BWD>(p, g, st);
+    case 19: return cs_launch_t<T, 19, BWD>(p, g, st);
+  }
+  set_error("class-sliced pipeline: unsupported class count %d", p.C);
+  return 1;
+}
+
+template <bool BWD> static int cs_dispatch(CsParams p, int logit_dtype, cudaStream_t st) {
+  CsGeom g;
+  const int elem = logit_bytes(logit_dtype);
+  B200SEG_REQUIRE(cs_geometry(p.C, elem, &g), "class-sliced pipeline: unsupported shape (C=%d)", p.C);
+  constexpr int TP = 8 * kCsWarpPx;
+  p.stages = g.stages; p.stage_bytes = g.stage_bytes; p.row_pitch = g.row_pitch; p.label_off = g.label_off; p.lse_off = g.lse_off;
+  p.tiles_per_image = (int)((p.HW + TP - 1) / TP);
+  p.total_tiles = (long long)p.tiles_per_image * p.N;
+  switch (logit_dtype) {
+    case B200SEG_F32: return cs_launch<float, BWD>(p, g, st);
+    case B200SEG_BF16: return cs_launch<__nv_bfloat16, BWD>(p, g, st);
+    case B200SEG_F16: return cs_launch<__half, BWD>(p, g, st);
+  }
+  set_error("unsupported logit dtype %d", logit_dtype);
+  return 1;
+}
+
+int cs_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
+  CsParams p = {};
+  p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;
+  p.lse = (d->flags & B200SEG_WANT_LSE) ? d->lse : nullptr;
+  p.stats = reinterpret_cast<unsigned long long*>(d->stats);
+  p.dice_part = (d->flags & B200SEG_WANT_DICE) ? d->dice_part : nullptr;
+  p.label_dtype = d->label_dtype; p.label_bytes = label_bytes(d->label_dtype);
+  p.N = d->N; p.C = d->C; p.HW = (long long)d->H * d->W;
+  p.flags = d->flags;
+  p.ignore_index = d->ignore_index; p.dice_ignore = d->dice_ignore_index;
+  p.acc_has_ignore = d->acc_has_ignore; p.acc_ignore = d->acc_ignore_index;
+  return cs_dispatch<false>(p, d->logit_dtype, st);
+}
+
+int cs_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
+  CsParams p = {};
+  p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;
+  p.lse = const_cast<float*>(d->lse);
+  p.stats = const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(d->stats));
+  p.dice_coef = d->dice_coef; p.dice_grad_out = d->dice_grad_out; p.ce_grad_out = d->ce_grad_out;
+  p.grad = d->grad_logits;
+  p.label_dtype = d->label_dtype; p.label_bytes = label_bytes(d->label_dtype);
+  p.N = d->N; p.C = d->C; p.HW = (long long)d->H * d->W;
+  p.flags = d->flags;
+  p.ignore_index = d->ignore_index; p.dice_ignore = d->dice_ignore_index;
+  p.ce_scale_host = d->ce_scale_host; p.ce_use_nvalid = d->ce_use_nvalid;
+  return cs_dispatch<true>(p, d->logit_dtype, st);
+}
+
+}  // namespace b200seg

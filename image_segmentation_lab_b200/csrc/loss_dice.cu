@@ -14,6 +14,8 @@
 //            D  dice_grad_kernel: pixel-major, grad = p (g - dot) + k (p - onehot), streamed store
 // Traffic: forward 2 reads, backward 2 reads + 1 write of the logits (algorithmic: 1 and 1 + 1), one MUFU.EX2 per
 // element per pass. Roofline: HBM.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200seg {
@@ -361,6 +363,15 @@ template <typename T> static int dice_bwd_t(const DiceParams& p, bool vec, cudaS
 }
 
 int ce_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
+int cs_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
+int cs_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st);
+bool cs_supported(const void* logits, const void* labels, const void* lse, const void* grad, int logit_dtype, int label_dtype,
+                  int C, long long HW, float dice_exponent, int dice_mode, bool want_dice);
+// B200SEG_NO_CS=1 keeps the five-pass streaming kernels (A/B measurements and tests of the fallback)
+static bool cs_disabled() {
+  const char* e = getenv("B200SEG_NO_CS");
+  return e && e[0] == '1';
+}
 
 // forward for C > 32: A (CE stream kernel with the one-hot Dice sums) then B
 int dice_stream_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
@@ -369,6 +380,11 @@ int dice_stream_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   B200SEG_REQUIRE(d->dice_part != nullptr, "dice_part workspace is NULL");
   B200SEG_REQUIRE(d->dice_exponent > 0.f, "dice exponent must be > 0");
   B200SEG_REQUIRE((d->flags & B200SEG_WANT_LSE) && d->lse, "dice forward with more than 32 classes needs the lse buffer");
+  // one read of the logits (class-sliced bulk-copy pipeline, loss_cs.cu) when the tensors are 16-byte tileable
+  if (!cs_disabled() && !(d->flags & B200SEG_WANT_LOSS_PX) &&
+      cs_supported(d->logits, d->labels, d->lse, nullptr, d->logit_dtype, d->label_dtype, d->C, (long long)d->H * d->W,
+                   d->dice_exponent, d->dice_mode, true))
+    return cs_fwd_dispatch(d, st);
   if (int e = ce_fwd_dispatch(d, st)) return e;
   DiceParams p = {};
   p.logits = d->logits; p.lse = d->lse; p.dice_part = d->dice_part;
@@ -388,6 +404,11 @@ int dice_stream_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
 int dice_stream_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
   B200SEG_REQUIRE(d->h == d->H && d->w == d->W, "dice backward needs logits at label resolution");
   B200SEG_REQUIRE(d->dice_coef != nullptr && d->lse != nullptr, "dice backward needs dice_coef and lse");
+  if (!cs_disabled() && !d->ce_grad_px && (d->flags & B200SEG_WANT_DICE) &&
+      cs_supported(d->logits, d->labels, d->lse, d->grad_logits, d->logit_dtype, d->label_dtype, d->C, (long long)d->H * d->W,
+                   d->dice_exponent, d->dice_mode, true) &&
+      (!d->pixel_weight || aligned16(d->pixel_weight)))
+    return cs_bwd_dispatch(d, st);
   B200SEG_REQUIRE(d->scratch_px != nullptr, "dice backward with more than 32 classes needs the (N,H,W) f32 scratch_px");
   DiceParams p = {};
   p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;

@@ -400,10 +400,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
       else if (d.ce_avg_non_ignore) loss = sum / (double)(float)(n_valid + eps);
       else loss = sum / (double)d.n_pixels;
     }
-    d.out[B200SEG_OUT_LOSS_CE] = (float)((double)d.ce_loss_weight * loss);
+    *d.out_loss_ce = (float)((double)d.ce_loss_weight * loss);
     // accuracy.py:55-60: (correct.float().sum() + eps) * (100.0 / (n + eps)), evaluated in fp32
     const float r = (float)(100.0 / (n_acc + eps));
-    d.out[B200SEG_OUT_ACC] = ((float)n_correct + (float)eps) * r;
+    if (d.out_acc) *d.out_acc = ((float)n_correct + (float)eps) * r;
     if (d.log_vec) {
       d.log_vec[B200SEG_LOG_CE_SUM] = sum;
       d.log_vec[B200SEG_LOG_N_VALID] = n_valid;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
     }
   }
   if (d.dice_part == nullptr) {
-    if (threadIdx.x == 0) d.out[B200SEG_OUT_LOSS_DICE] = 0.f;
+    if (threadIdx.x == 0 && d.out_loss_dice) *d.out_loss_dice = 0.f;
     return;
   }
   // K: d(loss_dice)/d(per-sample, per-class dice term)
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const b200seg_finalize_de
   double r[1] = {part};
   block_sum<double, 1>(r, sred);
   if (threadIdx.x == 0) {
-    d.out[B200SEG_OUT_LOSS_DICE] = (float)(K * r[0]);
+    if (d.out_loss_dice) *d.out_loss_dice = (float)(K * r[0]);
     // sum over (n,c) of cw_c * (1 - num/den): additive over images, so ranks can all-reduce it
     if (d.log_vec) d.log_vec[B200SEG_LOG_DICE_SUM] = r[0];
   }

@@ -424,11 +424,7 @@ template <typename T, int CPT, bool GRAD, int THR, int MINB, int LK> static int 
   constexpr size_t smem = upcell_smem_bytes<CPT, THR>(GRAD);
   constexpr int kCellThreads = THR;
   auto k = up_cell_kernel<T, CPT, GRAD, THR, MINB, LK>;
-  static bool attr = false;
-  if (!attr) {
-    B200SEG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)smem)) return e;
   const long long cells_per_cta = (long long)(kCellThreads / 32) * (8 >> p.logRG);
   const long long grid = (p.cells + cells_per_cta - 1) / cells_per_cta;   // one cell group per warp: measured faster
                                                                           // than persistent warps with next-cell prefetch

@@ -127,12 +127,28 @@ class PackedAllReduce:
 
 
 def all_reduce_areas(areas: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
-    """Sum int64 area tensors over ranks with one collective for all keys (sorted, so ranks agree)."""
+    """Sum int64 area tensors over ranks with ONE collective for all keys (sorted, so ranks agree). NCCL and gloo sum
+    int64 natively, so the counts travel as they are: no float64 packing, no rounding pass, and for a single key not
+    even a concatenation — the reduction happens in place on the stream the areas were produced on."""
     keys = sorted(areas.keys())
     if not keys:
         return {}
-    red = PackedAllReduce(group, side_stream=False)(tuple(areas[k] for k in keys))
-    return dict(zip(keys, red))
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return {k: areas[k] for k in keys}
+    for k in keys:
+        assert areas[k].dtype == torch.int64, 'area tensors are int64 (got %s for %r)' % (areas[k].dtype, k)
+    if len(keys) == 1:
+        t = areas[keys[0]].contiguous()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return {keys[0]: t}
+    flat = torch.cat([areas[k].reshape(-1) for k in keys])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out, off = {}, 0
+    for k in keys:
+        n = areas[k].numel()
+        out[k] = flat[off:off + n].reshape(areas[k].shape)
+        off += n
+    return out
 
 
 def global_loss_scalars(vec: torch.Tensor, loss_weight: float = 1.0, avg_non_ignore: bool = False):
@@ -144,3 +160,9 @@ def global_loss_scalars(vec: torch.Tensor, loss_weight: float = 1.0, avg_non_ign
     loss = (loss_weight * vec[_lib.LOG_CE_SUM] / denom).to(torch.float32)
     acc = (100.0 * (vec[_lib.LOG_N_CORRECT] + eps) / (vec[_lib.LOG_N_ACC] + eps)).to(torch.float32)
     return loss, acc
+
+
+def global_dice_loss(vec: torch.Tensor, num_classes: int, loss_weight: float = 1.0):
+    """Global-batch Dice / Tversky loss from the all-reduced statistics vector: the per-(sample, class) terms are additive
+    over images (dice_loss.py:31-58: class mean of the batch means), so loss = lw * sum / (C * N_global)."""
+    return (loss_weight * vec[_lib.LOG_DICE_SUM] / (float(num_classes) * vec[_lib.LOG_N_IMAGES])).to(torch.float32)

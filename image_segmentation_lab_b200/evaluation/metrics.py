@@ -43,81 +43,125 @@ def _common(tensors, device, allowed, fallback):
     return out, dt
 
 
-def areas_device(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num_classes: int, ignore_index: int,
-                 from_logits: bool = False, pred_maps: Optional[list] = None, align_corners: bool = False) -> torch.Tensor:
+class ImageTable:
+    """Device-side description of a list of (prediction, ground truth) images: the per-image table
+    {pred*, gt*, n_pixels, (h,w), (H,W)} and the chunk prefix sum the kernels walk, built once and uploaded with one
+    host-to-device copy. Build it with :func:`prepare_images` and pass it to :func:`areas_device` /
+    :func:`area_totals_device` in place of the two lists when the same buffers are evaluated again (the table keeps
+    the tensors alive)."""
+
+    def __init__(self, preds, gts, from_logits, num_classes):
+        lib = _lib.load()
+        n = len(preds)
+        self.n = n
+        self.from_logits = bool(from_logits)
+        self.resized = False
+        self.device = _device_of(list(preds) + list(gts)) if n else torch.device('cuda', torch.cuda.current_device())
+        self.chunk = lib.b200seg_confusion_chunk_pixels()
+        if n == 0:
+            self.total_chunks, self.meta, self.gdt, self.pdt, self.gts, self.preds = 0, None, None, None, [], []
+            return
+        dev = self.device
+        gts_c, self.gdt = _common(list(gts), dev, _lib.LABEL_DTYPES, torch.float32)
+        if from_logits:
+            preds_c, self.pdt = _common(list(preds), dev, _lib.LOGIT_DTYPES, torch.float32)
+        else:
+            preds_c, self.pdt = _common(list(preds), dev, _lib.LABEL_DTYPES, torch.int64)
+        self.preds, self.gts = preds_c, gts_c
+        # a few vectorised passes (a 500-image sweep must not be bound by this loop)
+        table = np.zeros((n, 5), dtype=np.int64)
+        table[:, 0] = np.fromiter((p.data_ptr() for p in preds_c), dtype=np.int64, count=n)
+        table[:, 1] = np.fromiter((g.data_ptr() for g in gts_c), dtype=np.int64, count=n)
+        npx = np.fromiter((g.numel() for g in gts_c), dtype=np.int64, count=n)
+        table[:, 2] = npx
+        if from_logits:
+            Cn = int(num_classes)
+            for i, (p, g) in enumerate(zip(preds_c, gts_c)):
+                if p.dim() == 4:
+                    assert p.size(0) == 1, 'each prediction must be (1,C,H,W)'
+                assert p.shape[-3] == Cn, 'logits have %d classes, evaluator has %d' % (p.shape[-3], Cn)
+                if tuple(p.shape[-2:]) != tuple(g.shape[-2:]):
+                    assert g.dim() >= 2, 'a 2-D ground truth is needed to resize the logits to it'
+                    self.resized = True
+                table[i, 3] = int(p.shape[-2]) | (int(p.shape[-1]) << 32)
+                table[i, 4] = int(g.shape[-2]) | (int(g.shape[-1]) << 32)
+        else:
+            pnum = np.fromiter((p.numel() for p in preds_c), dtype=np.int64, count=n)
+            assert (pnum == npx).all(), 'prediction / ground-truth size mismatch'
+        prefix = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum((npx + self.chunk - 1) // self.chunk, out=prefix[1:])
+        self.total_chunks = int(prefix[n])
+        with torch.cuda.device(dev):
+            self.meta = torch.from_numpy(np.concatenate([table.reshape(-1), prefix])).to(dev, non_blocking=True)
+        self.images_p = self.meta.data_ptr()
+        self.prefix_p = self.images_p + table.size * 8
+
+
+def prepare_images(preds: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], num_classes: int,
+                   from_logits: bool = False) -> ImageTable:
+    assert len(preds) == len(gts)  # metrics.py:236
+    return ImageTable(preds, gts, from_logits, num_classes)
+
+
+def areas_device(preds, gts: Optional[Sequence[torch.Tensor]], num_classes: int, ignore_index: int,
+                 from_logits: bool = False, pred_maps: Optional[list] = None, align_corners: bool = False,
+                 totals_only: bool = False) -> torch.Tensor:
     """int64 (n_images, 3, C) device tensor [intersect, pred, label] for a list of images; no host sync.
+    With ``totals_only`` the result is the (3, C) sum over the images, accumulated inside the kernel.
 
     ``preds[i]`` is a label map (H_i,W_i) — or, with ``from_logits``, logits (1,C,H_i,W_i) / (C,H_i,W_i) whose
     arg-max over classes is taken in the same kernel (lowest index wins ties). ``gts[i]`` is (H_i,W_i) in
     any integer / float dtype (the reference's ``ori_gt`` is float32, core/dataset/kvasir_seg.py:37).
+    ``preds`` may also be an :class:`ImageTable` from :func:`prepare_images` (then ``gts`` is ignored).
     ``pred_maps``: optional list that receives the int64 arg-max maps (logits mode only).
     Logits whose spatial size differs from their ground truth are bilinearly resized to it (``align_corners``)
     INSIDE the arg-max kernel — the rescale of decode_head.py:297-320 without materialising the (1,C,H,W) tensor.
     """
-    assert len(preds) == len(gts)  # metrics.py:236
     lib = _lib.load()
-    n = len(preds)
     Cn = int(num_classes)
+    if isinstance(preds, ImageTable):
+        tab = preds
+        from_logits = tab.from_logits
+    else:
+        assert len(preds) == len(gts)  # metrics.py:236
+        tab = ImageTable(preds, gts, from_logits, Cn)
+    n, dev = tab.n, tab.device
+    shape = (3, Cn) if totals_only else (n, 3, Cn)
     if n == 0:
-        dev = torch.device('cuda', torch.cuda.current_device())
-        return torch.zeros((0, 3, Cn), dtype=torch.int64, device=dev)
-    dev = _device_of(list(preds) + list(gts))
-    gts_c, gdt = _common(list(gts), dev, _lib.LABEL_DTYPES, torch.float32)
-    if from_logits:
-        preds_c, pdt = _common(list(preds), dev, _lib.LOGIT_DTYPES, torch.float32)
-    else:
-        preds_c, pdt = _common(list(preds), dev, _lib.LABEL_DTYPES, torch.int64)
-    chunk = lib.b200seg_confusion_chunk_pixels()
-    # per-image table {pred*, gt*, n_pixels, (h,w) of the logits, (H,W) of the ground truth} and the chunk prefix sum,
-    # built with a few vectorised passes (a 500-image sweep must not be bound by this loop)
-    table = np.zeros((n, 5), dtype=np.int64)
-    table[:, 0] = np.fromiter((p.data_ptr() for p in preds_c), dtype=np.int64, count=n)
-    table[:, 1] = np.fromiter((g.data_ptr() for g in gts_c), dtype=np.int64, count=n)
-    npx = np.fromiter((g.numel() for g in gts_c), dtype=np.int64, count=n)
-    table[:, 2] = npx
-    resized = False
-    if from_logits:
-        for i, (p, g) in enumerate(zip(preds_c, gts_c)):
-            if p.dim() == 4:
-                assert p.size(0) == 1, 'each prediction must be (1,C,H,W)'
-            assert p.shape[-3] == Cn, 'logits have %d classes, evaluator has %d' % (p.shape[-3], Cn)
-            if tuple(p.shape[-2:]) != tuple(g.shape[-2:]):
-                assert g.dim() >= 2, 'a 2-D ground truth is needed to resize the logits to it'
-                resized = True
-            table[i, 3] = int(p.shape[-2]) | (int(p.shape[-1]) << 32)
-            table[i, 4] = int(g.shape[-2]) | (int(g.shape[-1]) << 32)
-    else:
-        pnum = np.fromiter((p.numel() for p in preds_c), dtype=np.int64, count=n)
-        assert (pnum == npx).all(), 'prediction / ground-truth size mismatch'
-    prefix = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum((npx + chunk - 1) // chunk, out=prefix[1:])
-    total_chunks = int(prefix[n])
+        return torch.zeros(shape, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        meta = torch.from_numpy(np.concatenate([table.reshape(-1), prefix])).to(dev, non_blocking=True)
-        areas = torch.zeros((n, 3, Cn), dtype=torch.int64, device=dev)
+        areas = torch.zeros(shape, dtype=torch.int64, device=dev)
         stream = _lib.stream_ptr(dev)
-        images_p = meta.data_ptr()
-        prefix_p = images_p + table.size * 8
+        tot = int(bool(totals_only))
         if from_logits:
             pout_p = None
             if pred_maps is not None:
-                maps = [torch.empty(tuple(g.shape), dtype=torch.int64, device=dev) for g in gts_c]
+                maps = [torch.empty(tuple(g.shape), dtype=torch.int64, device=dev) for g in tab.gts]
                 ptrs = torch.tensor([m.data_ptr() for m in maps], dtype=torch.int64).to(dev, non_blocking=True)
                 pout_p = ptrs.data_ptr()
                 pred_maps.extend(maps)
-            if resized:
+            if tab.resized:
                 _lib.check(lib.b200seg_confusion_logits_resized(
-                    images_p, prefix_p, n, total_chunks, chunk, _lib.LOGIT_DTYPES[pdt], _lib.LABEL_DTYPES[gdt], Cn,
-                    int(ignore_index), int(bool(align_corners)), areas.data_ptr(), pout_p, stream))
+                    tab.images_p, tab.prefix_p, n, tab.total_chunks, tab.chunk, _lib.LOGIT_DTYPES[tab.pdt],
+                    _lib.LABEL_DTYPES[tab.gdt], Cn, int(ignore_index), int(bool(align_corners)), areas.data_ptr(), pout_p, tot,
+                    stream))
             else:
-                _lib.check(lib.b200seg_confusion_logits(images_p, prefix_p, n, total_chunks, chunk, _lib.LOGIT_DTYPES[pdt],
-                                                        _lib.LABEL_DTYPES[gdt], Cn, int(ignore_index), areas.data_ptr(),
-                                                        pout_p, stream))
+                _lib.check(lib.b200seg_confusion_logits(tab.images_p, tab.prefix_p, n, tab.total_chunks, tab.chunk,
+                                                        _lib.LOGIT_DTYPES[tab.pdt], _lib.LABEL_DTYPES[tab.gdt], Cn,
+                                                        int(ignore_index), areas.data_ptr(), pout_p, tot, stream))
         else:
-            _lib.check(lib.b200seg_confusion_labels(images_p, prefix_p, n, total_chunks, chunk, _lib.LABEL_DTYPES[pdt],
-                                                    _lib.LABEL_DTYPES[gdt], Cn, int(ignore_index), areas.data_ptr(),
-                                                    stream))
+            _lib.check(lib.b200seg_confusion_labels(tab.images_p, tab.prefix_p, n, tab.total_chunks, tab.chunk,
+                                                    _lib.LABEL_DTYPES[tab.pdt], _lib.LABEL_DTYPES[tab.gdt], Cn,
+                                                    int(ignore_index), areas.data_ptr(), tot, stream))
     return areas
+
+
+def area_totals_device(preds, gts, num_classes: int, ignore_index: int, from_logits: bool = False,
+                       align_corners: bool = False) -> torch.Tensor:
+    """int64 (3, C) device totals [intersect, pred, label] over all images — what seg_metrics sums up (metrics.py:163-166)
+    — accumulated inside the kernel: one launch, one (3, C) buffer, ready for a single int64 all-reduce across ranks."""
+    return areas_device(preds, gts, num_classes, ignore_index, from_logits=from_logits, align_corners=align_corners,
+                        totals_only=True)
 
 
 def _iupl(areas: torch.Tensor) -> torch.Tensor:

@@ -117,11 +117,23 @@ def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=
     if pred.size(1) == 1 and pred.dim() == label.dim() + 1:
         single = True                       # the reference squeezes the channel (:133) and checks label <= 1 (:130)
     elif pred.dim() == label.dim():
-        # element-wise targets: treat every element as its own pixel of a 1-channel prediction
+        # element-wise targets: treat every element as its own pixel of a 1-channel prediction. The reference forwards
+        # pos_weight=class_weight here too (:160-161); a scalar weight maps onto the single channel, anything else would
+        # broadcast against the LAST dimension of pred, which the kernel's per-class table cannot express.
         shape = pred.shape
+        pos_w = None
+        if class_weight is not None:
+            pos_w = torch.as_tensor(class_weight, dtype=torch.float32, device=pred.device).reshape(-1).contiguous()
+            if pos_w.numel() != 1:
+                raise NotImplementedError('binary_cross_entropy with element-wise targets supports a scalar class_weight only '
+                                          '(got %d entries)' % pos_w.numel())
         out = _BceFunction.apply(pred.reshape(-1, 1, 1), label.reshape(-1, 1), None if weight is None else weight.reshape(-1, 1),
-                                 None, reduction, avg_factor, ignore_index, avg_non_ignore, True, torch.is_grad_enabled())
-        return out.reshape(shape) if reduction == 'none' else out
+                                 pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, True, torch.is_grad_enabled())
+        if reduction == 'none':
+            out = out.reshape(shape)
+        if pred.dtype != torch.float32 and not torch.is_autocast_enabled():
+            out = out.to(pred.dtype)
+        return out
     else:
         assert (pred.dim() == 2 and label.dim() == 1) or (pred.dim() == 4 and label.dim() == 3), \
             'Only pred shape [N, C], label shape [N] or pred shape [N, C, H, W], label shape [N, H, W] are supported'
@@ -129,8 +141,6 @@ def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=
     pos_w = None
     if class_weight is not None:
         pos_w = torch.as_tensor(class_weight, dtype=torch.float32, device=pred.device).contiguous()
-        if single and pos_w.numel() != 1:
-            pos_w = pos_w.reshape(-1)[:1].contiguous() if pos_w.numel() == 1 else pos_w
     out = _BceFunction.apply(x, label, weight, pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, single,
                              torch.is_grad_enabled())
     if reduction == 'none':

@@ -109,14 +109,18 @@ class FusedLossFunction(torch.autograd.Function):
 
         with torch.cuda.device(dev):
             nc = N * Cc if spec.want_dice else 0
-            ws = torch.empty(_lib.STATS_WORDS + 2 + _lib.LOG_WORDS + 4 * nc, dtype=torch.int64, device=dev)
+            ws = torch.empty(_lib.STATS_WORDS + _lib.LOG_WORDS + 4 * nc, dtype=torch.int64, device=dev)
             base = ws.data_ptr()
             stats_p = base
-            out_p = base + 8 * _lib.STATS_WORDS
-            log_p = out_p + 16
+            log_p = base + 8 * _lib.STATS_WORDS
             part_p = log_p + 8 * _lib.LOG_WORDS
             coef_p = part_p + 24 * nc
-            out_f = ws[_lib.STATS_WORDS:_lib.STATS_WORDS + 2].view(torch.float32)
+            # The differentiable outputs are tensors of their own, NOT views of one workspace: the stock head does
+            # `loss[name] += loss_decode(...)` for losses sharing a loss_name (decode_head.py:290), and autograd refuses
+            # an in-place update of a view handed out by a multi-output Function.
+            out_ce = torch.empty((), dtype=torch.float32, device=dev)
+            out_dice = torch.empty((), dtype=torch.float32, device=dev)
+            out_acc = torch.empty(1, dtype=torch.float32, device=dev)
 
             ce_none = spec.want_ce and spec.ce_reduction == "none"
             use_nvalid = bool(spec.want_ce and spec.ce_reduction == "mean" and spec.ce_avg_non_ignore
@@ -155,7 +159,11 @@ class FusedLossFunction(torch.autograd.Function):
                 if up:
                     if lib.b200seg_loss_fused_workspace_bytes(N, Cc, h, w, H, W, fd.align_corners) > 0:
                         plan = "up_single"
-                elif needs_grad and not use_nvalid and lib.b200seg_loss_flat_single_ok(
+                # float16 never takes this plan: its gradient is formed during the forward with the upstream gradient
+                # still unknown, i.e. at loss_weight/(N*H*W) ~ 5e-7 * (p - onehot), below the float16 normal range — the
+                # GradScaler's 65536 applied afterwards cannot bring the lost bits back. two_pass multiplies the scale
+                # in fp32 before the single cast, as the reference's autograd does.
+                elif needs_grad and not use_nvalid and logits_c.dtype != torch.float16 and lib.b200seg_loss_flat_single_ok(
                         logits_c.data_ptr(), labels.data_ptr(), fd.logit_dtype, fd.label_dtype, Cc, H * W, int(pw is not None)):
                     plan = "flat_single"   # bulk-copy pipeline (any C whose tile fits shared memory) or register tile (C <= 32)
 
@@ -208,15 +216,17 @@ class FusedLossFunction(torch.autograd.Function):
             fin.dice_mode = fd.dice_mode
             fin.tversky_alpha = float(spec.tversky_alpha)
             fin.tversky_beta = float(spec.tversky_beta)
-            fin.out = out_p
+            fin.out_loss_ce = out_ce.data_ptr()
+            fin.out_loss_dice = out_dice.data_ptr()
+            fin.out_acc = out_acc.data_ptr()
             fin.dice_coef = coef_p if (spec.want_dice and needs_grad) else None
             fin.log_vec = log_p
             _lib.check(lib.b200seg_loss_finalize(C.byref(fin), stream))
 
-        loss_ce = loss_px if ce_none else out_f[_lib.OUT_LOSS_CE]
-        loss_dice = out_f[_lib.OUT_LOSS_DICE]
-        acc = out_f[_lib.OUT_ACC:_lib.OUT_ACC + 1]
-        log_vec = ws[_lib.STATS_WORDS + 2:_lib.STATS_WORDS + 2 + _lib.LOG_WORDS].view(torch.float64)
+        loss_ce = loss_px if ce_none else out_ce
+        loss_dice = out_dice
+        acc = out_acc
+        log_vec = ws[_lib.STATS_WORDS:_lib.STATS_WORDS + _lib.LOG_WORDS].view(torch.float64)
         ctx.mark_non_differentiable(acc, log_vec)
         if needs_grad:
             ctx.spec = spec

@@ -1,7 +1,7 @@
 """CrossEntropyLoss with the reference's signatures (models/losses/cross_entropy_loss.py).
 
 ``cross_entropy`` :23-74 and ``CrossEntropyLoss`` :206-306 run on the fused sm_100a kernels
-(csrc/loss_stream.cu, csrc/loss_fused.cu); ``binary_cross_entropy`` :100-164 (use_sigmoid) runs on
+(csrc/loss_stream.cu, csrc/loss_bulk.cu, csrc/loss_rt.cuh, csrc/loss_upcell.cuh); ``binary_cross_entropy`` :100-164 (use_sigmoid) runs on
 csrc/loss_bce.cu. ``mask_cross_entropy`` :167-203 is an instance-segmentation helper outside the
 per-pixel path and is not provided.
 """

@@ -1,4 +1,4 @@
-"""DiceLoss with the reference's signatures (models/losses/dice_loss.py:23-148), on csrc/loss_tile.cu.
+"""DiceLoss with the reference's signatures (models/losses/dice_loss.py:23-148), on csrc/loss_rt.cuh (C <= 32) and csrc/loss_dice.cu (C > 32).
 
 Quirks of the reference that are preserved:
   * the denominator sum(p^e + t^e) is NOT masked by valid_mask (:56);

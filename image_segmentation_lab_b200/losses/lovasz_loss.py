@@ -91,7 +91,9 @@ class _LovaszFunction(torch.autograd.Function):
             seg_stats = small[:max(n_groups, 1) * n_seg * 2]
             f32 = small[max(n_groups, 1) * n_seg * 2:].view(torch.float32)
             coef = f32[:max(n_groups, 1) * n_seg]
-            out = f32[max(n_groups, 1) * n_seg:max(n_groups, 1) * n_seg + max(n_groups, 1)]
+            # the result is a tensor of its own (not a view of `small`): `loss[name] += ...` in the stock head
+            # (decode_head.py:290) updates it in place, which autograd refuses for a view made inside a Function
+            out = torch.empty(() if not none_vec else (n_groups,), dtype=torch.float32, device=dev)
 
             d = _lib.LovaszDesc()
             d.logits = x.data_ptr(); d.labels = labels.data_ptr()
@@ -121,7 +123,7 @@ class _LovaszFunction(torch.autograd.Function):
             d.seg_stats = seg_stats.data_ptr(); d.out = out.data_ptr()
             d.coef = coef.data_ptr() if needs_grad else None
             _lib.check(lib.b200seg_lovasz_fwd(C.byref(d), stream))
-        result = out[:n_groups] if none_vec else out[0]
+        result = out
         if needs_grad:
             ctx.cfg = dict(binary=binary, per_image=per_image, none_vec=none_vec, N=N, C=Cc, HW=HW)
             ctx.small = small

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 11
+#define B200SEG_ABI_VERSION 12
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -63,9 +63,6 @@ enum {
   B200SEG_ST_N_ACC     = 4,   /* int64  : accuracy denominator (honours acc_has_ignore)      */
   B200SEG_STATS_WORDS  = 8
 };
-
-/* outputs of b200seg_loss_finalize (float32 words) */
-enum { B200SEG_OUT_LOSS_CE = 0, B200SEG_OUT_LOSS_DICE = 1, B200SEG_OUT_ACC = 2, B200SEG_OUT_WORDS = 4 };
 
 /* layout of b200seg_finalize_desc.log_vec */
 enum { B200SEG_LOG_CE_SUM = 0, B200SEG_LOG_N_VALID = 1, B200SEG_LOG_N_CORRECT = 2, B200SEG_LOG_N_ACC = 3,
@@ -129,7 +126,11 @@ typedef struct b200seg_finalize_desc {
   float   dice_smooth;
   int32_t dice_reduction;
   int64_t dice_ignore_index;
-  float*  out;                      /* B200SEG_OUT_WORDS floats                                */
+  /* one float each, separately allocated by the caller (so that a framework can hand them out as independent
+   * tensors: `loss[name] += ...` in decode_head.py:290 needs loss scalars that are not views of one buffer)   */
+  float*  out_loss_ce;              /* loss_weight * reduced CE (0 written when ce_reduction is NONE: use loss_px) */
+  float*  out_loss_dice;            /* or NULL                                                 */
+  float*  out_acc;                  /* top-1 accuracy in percent (accuracy.py:55-60), or NULL  */
   float*  dice_coef;                /* (N,C,2) f32 [alpha,beta] for the backward, or NULL      */
   double* log_vec;                  /* B200SEG_LOG_WORDS doubles or NULL: the additive quantities of
                                      * this call as float64 (exact below 2^53), i.e. the payload of the
@@ -313,24 +314,26 @@ typedef struct b200seg_image {
 
 /* Area histograms from label maps. areas: (n_images,3,C) int64 [intersect, pred, label],
  * ACCUMULATED into (caller zeroes). `images` is a device array of n_images descriptors.
- * `chunk_prefix` is a device array of n_images+1 int64: prefix sum of ceil(n_pixels/chunk).  */
+ * `chunk_prefix` is a device array of n_images+1 int64: prefix sum of ceil(n_pixels/chunk).
+ * totals_only != 0: `areas` is (3,C), the sum over all images (what seg_metrics needs, metrics.py:163-166) — every CTA
+ * flushes its counters once instead of once per image it touches.                             */
 int b200seg_confusion_labels(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                              int64_t total_chunks, int32_t chunk_pixels, int32_t pred_dtype, int32_t gt_dtype,
-                             int32_t C, int64_t ignore_index, int64_t* areas, void* stream);
+                             int32_t C, int64_t ignore_index, int64_t* areas, int32_t totals_only, void* stream);
 
 /* Same, with the arg-max over classes fused in (logits (C,H,W) per image; lowest index wins ties);
  * optionally writes the int64 label map to pred_out[i] ((H,W) each, may be NULL).              */
 int b200seg_confusion_logits(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                              int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype, int32_t gt_dtype,
                              int32_t C, int64_t ignore_index, int64_t* areas, int64_t* const* pred_out,
-                             void* stream);
+                             int32_t totals_only, void* stream);
 /* Same, with the bilinear resize of low-resolution logits (C,h,w) to the ground-truth size (H,W) fused into the
  * arg-max (decode_head.py:297-320 + metrics.py:101-107): image.h/w = logit size, image.H/W = ground-truth size,
  * image.n_pixels = H*W. The rescaled logits are never materialised.                                            */
 int b200seg_confusion_logits_resized(const b200seg_image* images, const int64_t* chunk_prefix, int32_t n_images,
                                      int64_t total_chunks, int32_t chunk_pixels, int32_t logit_dtype, int32_t gt_dtype,
                                      int32_t C, int64_t ignore_index, int32_t align_corners, int64_t* areas,
-                                     int64_t* const* pred_out, void* stream);
+                                     int64_t* const* pred_out, int32_t totals_only, void* stream);
 int32_t b200seg_confusion_chunk_pixels(void);
 
 /* top-k accuracy counts (models/losses/accuracy.py:6-61) for arbitrary k and thresh:

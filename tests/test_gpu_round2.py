@@ -1,0 +1,213 @@
+"""GPU: round-2 parity cases — AMP (float16 + GradScaler) gradients on label-resolution logits, the stock head's in-place
+`loss[name] += ...` flow, several devices in one process, and the multi-GPU (NCCL) sharded totals.
+
+Gates as in test_gpu_parity.py."""
+import os
+import subprocess
+import sys
+import warnings
+
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.helpers import rel_err, synth_labels, synth_logits
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOSS_TOL = 1e-5
+GRAD_TOL = 1e-4
+HALF_TOL = 2.0 ** -7
+
+
+@pytest.fixture(scope='module')
+def B():
+    import image_segmentation_lab_b200 as pkg
+    pkg.load_library()
+    warnings.simplefilter('ignore')
+    return pkg
+
+
+def test_fp16_gradscaler_gradient_keeps_its_bits(B):
+    """The reference's shipped schedule is fp16 autocast + GradScaler (configs/schedule/kvasir_training_schedule.py:22,
+    utils/train_utils.py:85-91): the upstream gradient is 65536 and autograd applies it in fp32 before the single cast
+    to float16. A gradient formed at loss_weight/(N*H*W) ~ 5e-7 and scaled afterwards would be subnormal float16."""
+    for shape, C in (((2, 19, 128, 256), 19), ((2, 21, 64, 96), 21), ((1, 60, 64, 64), 60)):
+        x = synth_logits(shape, 11, device='cuda').half()
+        y = synth_labels((shape[0],) + shape[2:], C, 11, device='cuda', block=8)
+        xa = x.clone().requires_grad_(True)
+        la = B.CrossEntropyLoss()(xa, y, ignore_index=255)
+        (la.float() * 65536.0).backward()
+        xb = x.float().requires_grad_(True)
+        lb = O.cross_entropy_loss_module(xb, y, ignore_index=255)
+        (lb * 65536.0).backward()
+        assert xa.grad.dtype == torch.float16
+        # float16 has 11 significand bits: 2**-10 relative to the largest entry, and small entries must not collapse
+        assert rel_err(xa.grad, xb.grad) <= 2.0 ** -10, rel_err(xa.grad, xb.grad)
+        ref = xb.grad
+        big = ref.abs() > 1e-3 * ref.abs().max()
+        ratio = (xa.grad.float()[big] / ref[big])
+        assert float((ratio - 1).abs().max()) <= 2.0 ** -9, float((ratio - 1).abs().max())
+
+
+def test_same_named_losses_accumulate_in_place(B):
+    """decode_head.py:283-293: `loss[name] = ...` then `loss[name] += ...` for losses sharing a loss_name. The loss
+    scalars must therefore be tensors of their own (autograd refuses in-place updates of views made by a Function)."""
+    x = synth_logits((2, 6, 32, 32), 3, device='cuda').requires_grad_(True)
+    y = synth_labels((2, 32, 32), 6, 3, device='cuda', block=4)
+    mods = [B.CrossEntropyLoss(loss_weight=1.0), B.DiceLoss(loss_weight=3.0, loss_name='loss_ce'),
+            B.CrossEntropyLoss(loss_weight=0.5, loss_name='loss_ce'), B.LovaszLoss(reduction='none', loss_name='loss_ce'),
+            B.TverskyLoss(loss_name='loss_ce')]
+    loss = dict()
+    for m in mods:                                   # the reference's loop, verbatim semantics
+        if m.loss_name not in loss:
+            loss[m.loss_name] = m(x, y, ignore_index=255)
+        else:
+            loss[m.loss_name] += m(x, y, ignore_index=255)
+    loss['loss_ce'].backward()
+    xo = x.detach().clone().requires_grad_(True)
+    ref = (O.cross_entropy_loss_module(xo, y, ignore_index=255) + O.dice_loss_module(xo, y, loss_weight=3.0)
+           + O.cross_entropy_loss_module(xo, y, ignore_index=255, loss_weight=0.5)
+           + O.lovasz_loss_module(xo, y, reduction='none', ignore_index=255)
+           + O.tversky_loss_module(xo, y, ignore_index=255))
+    ref.backward()
+    assert rel_err(loss['loss_ce'], ref) <= LOSS_TOL
+    assert rel_err(x.grad, xo.grad) <= GRAD_TOL
+    # fused entry: every scalar it hands out accepts an in-place update as well
+    r = B.fused_resize_losses(x, y.unsqueeze(1), [B.CrossEntropyLoss(), B.DiceLoss()], ignore_index=255)
+    r['loss_ce'] += r['loss_dice']
+    r['acc_seg'] += 1.0
+    r['loss_ce'].backward()
+
+
+def test_bce_elementwise_forwards_scalar_class_weight(B):
+    """cross_entropy_loss.py:160-161: pos_weight=class_weight on every branch, element-wise targets included."""
+    g = torch.Generator().manual_seed(5)
+    p = torch.randn((4, 3, 8, 8), generator=g).cuda().requires_grad_(True)
+    t = (torch.rand((4, 3, 8, 8), generator=g) > 0.5).float().cuda()
+    a = B.binary_cross_entropy(p, t, class_weight=[2.5])
+    a.backward()
+    po = p.detach().clone().requires_grad_(True)
+    b = O.binary_cross_entropy(po, t, class_weight=torch.tensor([2.5], device='cuda'))
+    b.backward()
+    assert rel_err(a, b) <= LOSS_TOL and rel_err(p.grad, po.grad) <= GRAD_TOL
+    with pytest.raises(NotImplementedError):
+        B.binary_cross_entropy(p, t, class_weight=[1.0, 2.0, 3.0])
+    h = B.binary_cross_entropy(p.detach().bfloat16(), t, class_weight=[2.5])
+    assert h.dtype == torch.bfloat16
+
+
+def test_second_device_in_one_process(B):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): the first launch on a second GPU of the same
+    process must opt in again (confusion kernels with C >= 17, the bulk-copy pipeline, the cell-owner kernel)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 visible GPUs')
+    res = []
+    for dev in ('cuda:0', 'cuda:1'):
+        x = synth_logits((2, 21, 64, 96), 2, device=dev).requires_grad_(True)
+        y = synth_labels((2, 64, 96), 21, 2, device=dev, block=8)
+        l = B.CrossEntropyLoss()(x, y, ignore_index=255)
+        l.backward()
+        xl = synth_logits((2, 19, 8, 16), 4, device=dev).requires_grad_(True)
+        yl = synth_labels((2, 64, 128), 19, 4, device=dev, block=8)
+        r = B.fused_resize_losses(xl, yl.unsqueeze(1), B.CrossEntropyLoss(), ignore_index=255)
+        r['loss_ce'].backward()
+        preds = [torch.randint(0, 19, (64, 80), device=dev) for _ in range(3)]
+        gts = [torch.randint(0, 19, (64, 80), device=dev).float() for _ in range(3)]
+        areas = B.areas_device(preds, gts, 19, 255)
+        res.append((float(l), x.grad.cpu(), float(r['loss_ce']), xl.grad.cpu(), areas.cpu()))
+    torch.cuda.synchronize()
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2] and torch.equal(res[0][3], res[1][3])
+    assert int(res[0][4].sum()) > 0
+
+
+def test_multi_gpu_nccl_sharded_totals_match_single_gpu(B, tmp_path):
+    """Row (e): two NCCL ranks shard a config-4-shaped batch and a 16-image config-5 list with shard_range; the
+    all-reduced loss scalars / int64 areas must equal the single-GPU result (areas bit-for-bit, loss to 1e-6)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 visible GPUs')
+    out = tmp_path / 'mgpu.pt'
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''), MGPU_OUT=str(out))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29633', os.path.join(ROOT, 'tests', 'mgpu_worker.py')]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    got = torch.load(str(out))
+    # single GPU, whole batch
+    N, C = 8, 21
+    x = synth_logits((N, C, 128, 128), 77, device='cuda').requires_grad_(True)
+    y = synth_labels((N, 128, 128), C, 77, device='cuda', block=8)
+    rs = B.fused_resize_losses(x, y.unsqueeze(1), [B.CrossEntropyLoss(), B.DiceLoss(loss_weight=3.0)], ignore_index=255,
+                               return_stats=True)
+    (rs['loss_ce'] + rs['loss_dice']).backward()
+    assert abs(got['loss_ce'] - float(rs['loss_ce'])) <= 1e-6 * abs(float(rs['loss_ce']))
+    assert abs(got['loss_dice'] - float(rs['loss_dice'])) <= 1e-6 * abs(float(rs['loss_dice']))
+    assert abs(got['acc_seg'] - float(rs['acc_seg'])) <= 1e-4
+    assert rel_err(got['grad'], x.grad) <= 1e-6
+    preds = [torch.randint(0, 19, (96, 160), generator=torch.Generator().manual_seed(900 + i)).cuda() for i in range(16)]
+    gts = [synth_labels((1, 96, 160), 19, 900 + i, device='cuda', block=8)[0].float() for i in range(16)]
+    tot = B.areas_device(preds, gts, 19, 255).sum(0).cpu()
+    assert got['areas'].dtype == torch.int64 and torch.equal(got['areas'], tot)
+
+
+# ------------------------------------------------------------------------------------------------ class-sliced pipeline
+def _ce_dice(B, x, y, ce_kw, dice_kw, pw=None, scale=1.0):
+    xa = x.clone().requires_grad_(True)
+    r = B.fused_resize_losses(xa, y.unsqueeze(1), [B.CrossEntropyLoss(**ce_kw), B.DiceLoss(**dice_kw)], ignore_index=255,
+                              seg_weight=pw)
+    ((r['loss_ce'] + r['loss_dice']) * scale).backward()
+    return r['loss_ce'].detach(), r['loss_dice'].detach(), r['acc_seg'].detach(), xa.grad
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16])
+def test_class_sliced_pipeline_matches_oracle_and_streaming_kernels(B, dtype):
+    """csrc/loss_cs.cu (one read of the logits per direction, 32 < C <= 152) against the oracle and against the five-pass
+    streaming kernels it supersedes (B200SEG_NO_CS=1), over every class-slice width, ragged tiles, label dtypes, pixel
+    weights, a skipped Dice class and an upstream gradient."""
+    cases = [((2, 150, 64, 64), {}, dict(loss_weight=3.0), False, torch.int64, 1.0),
+             ((3, 40, 24, 40), dict(class_weight=torch.linspace(0.5, 1.5, 40).tolist()), dict(), True, torch.uint8, 1.0),
+             ((1, 100, 32, 32), dict(avg_non_ignore=True), dict(ignore_index=3, class_weight=[0.7] * 100), False, torch.int32, 8.0),
+             ((2, 70, 16, 24), dict(reduction='sum'), dict(smooth=2.0), False, torch.float32, 1.0),
+             ((2, 150, 24, 40), dict(class_weight=torch.linspace(0.5, 1.5, 150).tolist()), dict(loss_weight=3.0), True, torch.int64, 1.0),
+             ((1, 33, 8, 16), {}, dict(), False, torch.int64, 1.0)]
+    tol_l, tol_g = (LOSS_TOL, GRAD_TOL) if dtype == torch.float32 else (HALF_TOL, 2 * HALF_TOL)
+    for shape, ce_kw, dice_kw, with_pw, ldt, scale in cases:
+        n, c, h, w = shape
+        x = synth_logits(shape, 31, dtype=dtype, device='cuda')
+        y = synth_labels((n, h, w), c, 31, device='cuda', block=4).to(ldt)
+        pw = (torch.rand((n, h, w), device='cuda') + 0.5) if with_pw else None
+        got = _ce_dice(B, x, y, ce_kw, dice_kw, pw, scale)
+        os.environ['B200SEG_NO_CS'] = '1'
+        try:
+            old = _ce_dice(B, x, y, ce_kw, dice_kw, pw, scale)
+        finally:
+            del os.environ['B200SEG_NO_CS']
+        xo = x.float().requires_grad_(True)
+        ce_o = dict(ce_kw)
+        dice_o = dict(dice_kw)
+        for kw in (ce_o, dice_o):
+            if 'class_weight' in kw:
+                kw['class_weight'] = list(kw['class_weight'])
+        lce = O.cross_entropy_loss_module(xo, y.long(), weight=pw, ignore_index=255, **ce_o)
+        ldi = O.dice_loss_module(xo, y.long(), **dice_o)
+        ((lce + ldi) * scale).backward()
+        name = '%s %s' % (shape, dtype)
+        assert rel_err(got[0], lce) <= tol_l, name
+        assert rel_err(got[1], ldi) <= tol_l or float((got[1].double().cpu() - ldi.double().cpu()).abs()) < 2e-6, name
+        assert rel_err(got[3], xo.grad) <= tol_g, (name, rel_err(got[3], xo.grad))
+        # the two CUDA paths agree far below the gate (same fp32 arithmetic, different summation order)
+        assert rel_err(got[0], old[0]) <= 1e-6 and rel_err(got[1], old[1]) <= (1e-5 if dtype == torch.float32 else 1e-3), name
+        assert rel_err(got[3].float(), old[3].float()) <= (2e-5 if dtype == torch.float32 else 2.0 ** -7), name
+        if dtype == torch.float32:
+            assert abs(float(got[2]) - float(O.accuracy(x, y.long(), ignore_index=255))) <= 1e-3, name
+    # forward only (no_grad), and determinism of the gradient
+    x = synth_logits((2, 150, 32, 64), 5, dtype=dtype, device='cuda')
+    y = synth_labels((2, 32, 64), 150, 5, device='cuda', block=4)
+    with torch.no_grad():
+        r = B.fused_resize_losses(x, y.unsqueeze(1), [B.CrossEntropyLoss(), B.DiceLoss()], ignore_index=255)
+    a = _ce_dice(B, x, y, {}, {})
+    b = _ce_dice(B, x, y, {}, {})
+    assert rel_err(r['loss_ce'], a[0]) <= 1e-6
+    assert torch.equal(a[3], b[3]) or rel_err(a[3].float(), b[3].float()) <= 1e-6   # dice sums are fp64 atomics
