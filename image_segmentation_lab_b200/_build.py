@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libb200seg.so")
-SOURCES = ["api.cu", "loss_stream.cu", "loss_rt.cu", "loss_rt_f32.cu", "loss_rt_bf16.cu", "loss_rt_f16.cu", "loss_up.cu", "loss_upcell_f32.cu", "loss_upcell_bf16.cu", "loss_upcell_f16.cu",
+SOURCES = ["api.cu", "loss_stream.cu", "loss_rt.cu", "loss_rt_f32.cu", "loss_rt_bf16.cu", "loss_rt_f16.cu", "loss_up.cu", "loss_upcell_f32.cu", "loss_upcell_bf16.cu", "loss_upcell_f16.cu", "loss_upgen_f32.cu", "loss_upgen_bf16.cu", "loss_upgen_f16.cu",
            "loss_dice.cu", "loss_cs.cu", "loss_bulk.cu", "loss_bce.cu", "loss_lovasz.cu", "resize.cu", "confusion.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

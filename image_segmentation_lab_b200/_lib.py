@@ -77,7 +77,7 @@ class LossBwdDesc(C.Structure):
         ("ce_grad_out", C.c_void_p), ("ce_grad_px", C.c_void_p), ("stats", C.c_void_p),
         ("ce_use_nvalid", C.c_int32), ("dice_mode", C.c_int32),
         ("dice_coef", C.c_void_p), ("dice_grad_out", C.c_void_p),
-        ("grad_logits", C.c_void_p), ("grad_accum", C.c_void_p), ("scratch_px", C.c_void_p),
+        ("grad_logits", C.c_void_p), ("reserved_scratch", C.c_void_p), ("scratch_px", C.c_void_p),
     ]
 
 

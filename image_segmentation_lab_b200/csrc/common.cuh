@@ -405,28 +405,36 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
-// ---------------------------------------------------------------- bilinear source index (ATen)
-// torch/include/ATen/native/UpSample.h:271-312 (area_pixel_compute_scale / _source_index),
-// evaluated in fp32 exactly as ATen does.
+// ---------------------------------------------------------------- bilinear resize, ATen's arithmetic operation for operation
+// torch/include/ATen/native/UpSample.h:271-312 (area_pixel_compute_scale / _source_index) and the expression of
+// upsample_bilinear2d_out_frame, with the FMA contraction nvcc gives ATen's build PINNED by intrinsics: measured with
+// tools/probe/run_fma_probe.py on B200 / torch 2.11.0+cu128 — of 29 candidate evaluations exactly one reproduces
+// F.interpolate bit for bit (0 of 9.6 M elements differ, both align_corners settings, non-power-of-two shapes):
+//     src = fma(scale, dst + 0.5, -0.5)                   (align_corners=False; scale * dst otherwise)
+//     X   = fma(w0, v00, w1 * v01),  Y = fma(w0, v10, w1 * v11),  out = fma(h0, X, h1 * Y)
 __host__ __device__ __forceinline__ float resize_scale(int in, int out, bool align_corners) {
   if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
   return (float)in / (float)out;
 }
+__device__ __forceinline__ float aten_src_index(float scale, int dst, bool align_corners) {
+  if (align_corners) return __fmul_rn(scale, (float)dst);
+  const float s = __fmaf_rn(scale, __fadd_rn((float)dst, 0.5f), -0.5f);
+  return s < 0.f ? 0.f : s;
+}
+__device__ __forceinline__ float aten_bilerp(float h0, float h1, float w0, float w1, float v00, float v01, float v10, float v11) {
+  const float X = __fmaf_rn(w0, v00, __fmul_rn(w1, v01));
+  const float Y = __fmaf_rn(w0, v10, __fmul_rn(w1, v11));
+  return __fmaf_rn(h0, X, __fmul_rn(h1, Y));
+}
+// taps (i0, i1) and the weight l1 of tap i1 (the weight of i0 is 1 - l1, formed by the caller as ATen does: 1.f - l1)
 __device__ __forceinline__ void resize_src(float scale, int dst, int in, bool align_corners, int& i0, int& i1,
                                            float& l1) {
-  float src;
-  if (align_corners) {
-    src = scale * (float)dst;
-  } else {
-    src = scale * ((float)dst + 0.5f) - 0.5f;
-    src = src < 0.f ? 0.f : src;
-  }
+  const float src = aten_src_index(scale, dst, align_corners);
   int i = (int)src;
-  i = i < in - 1 ? i : in - 1;
+  i = i < in - 1 ? i : in - 1;      // never active for a valid source index (< in); keeps the taps in range regardless
   i0 = i;
   i1 = i + (i < in - 1 ? 1 : 0);
-  float l = src - (float)i;
-  l1 = l < 0.f ? 0.f : (l > 1.f ? 1.f : l);
+  l1 = __fsub_rn(src, (float)i);
 }
 
 }  // namespace b200seg

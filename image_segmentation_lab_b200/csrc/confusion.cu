@@ -364,10 +364,71 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
 // ------------------------------------------------------------------------------------------------
 // Resize-fused variant: logits (C,h,w) are bilinearly interpolated to the ground-truth size (H,W) inside the
 // arg-max loop (decode_head.py:297-320 rescale + metrics.py:101-107 argmax), so the (1,C,H,W) rescaled logits are
-// never written. ATen's evaluation order h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11) in fp32.
+// never written. The interpolation is ATen's, operation for operation with its FMA contraction pinned (common.cuh:
+// aten_src_index / aten_bilerp), and for 16-bit logits the value is rounded to the logit dtype before the comparison,
+// as F.interpolate's output is: the arg-max — and with it every area — is BIT-EXACT against the reference's
+// resize -> argmax at any ratio and either align_corners setting (on inputs without soft-max rounding ties).
+//
+// Work unit = one output row x one RUN of columns sharing the same pair of source columns (x0, x1): a thread loads the
+// 4 taps of a class once per run (L1 hits: the low-resolution logits are small) and evaluates 6 fp32 operations + a
+// compare / select pair per class-pixel for the run's pixels, in chunks of 8. Run boundaries come from the source-index
+// map itself (any ratio), tabulated per image in shared memory. Bound: instruction issue (C interpolations per output
+// pixel); DRAM traffic is the ground-truth map (4 B per pixel) plus the small logits.
+constexpr int kRunTableMax = 4096;   // w + 2 entries per image; wider logits take the simple per-pixel kernel
+
+// band key of an output position: 0 = source index clamped to 0 (align_corners=False), k + 1 = source floor k
+__device__ __forceinline__ int aten_run_key(float scale, int dst, int in, bool ac) {
+  const float raw = ac ? __fmul_rn(scale, (float)dst) : __fmaf_rn(scale, __fadd_rn((float)dst, 0.5f), -0.5f);
+  if (raw < 0.f) return 0;
+  const int i = (int)raw;
+  return (i < in - 1 ? i : in - 1) + 1;
+}
+// first output position in [0, out] whose key is >= r (keys are non-decreasing)
+__device__ __forceinline__ int aten_run_start(float scale, int r, int in, int out, bool ac) {
+  if (r <= 0) return 0;
+  if (r > in || !(scale > 0.f)) return out;
+  const float est = ac ? ((float)(r - 1) / scale) : (((float)(r - 1) + 0.5f) / scale - 0.5f);
+  int d = (int)fminf(fmaxf(ceilf(est), 0.f), (float)out);
+  while (d > 0 && aten_run_key(scale, d - 1, in, ac) >= r) --d;
+  while (d < out && aten_run_key(scale, d, in, ac) < r) ++d;
+  return d;
+}
+
+// Per-pixel form (no run table) for images whose logits are wider than the table: one pixel per thread, 4 taps per class.
+template <typename T, int THREADS, bool PRIVATE>
+__device__ __forceinline__ void resize_pixels_simple(const b200seg_image& im, long long px_begin, long long px_end, float sh, float sw,
+                                                     bool ac, int C, const ClassDecoder& dgt, long long* pout,
+                                                     Counters<THREADS, PRIVATE>& ctr) {
+  const long long hw = (long long)im.h * im.w;
+  const T* base = reinterpret_cast<const T*>(im.pred);
+  for (long long px = px_begin + threadIdx.x; px < px_end; px += THREADS) {
+    const int gv = dgt.one(im.gt, (size_t)px);
+    const int Y = (int)(px / im.W), X = (int)(px - (long long)Y * im.W);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_src(sh, Y, im.h, ac, y0, y1, ly);
+    resize_src(sw, X, im.w, ac, x0, x1, lx);
+    const float h1 = ly, h0 = __fsub_rn(1.f, ly), w1 = lx, w0 = __fsub_rn(1.f, lx);
+    const int o00 = y0 * im.w + x0, o01 = y0 * im.w + x1, o10 = y1 * im.w + x0, o11 = y1 * im.w + x1;
+    float best = neg_inf();
+    int bi = 0;
+    const T* pl = base;
+    for (int c = 0; c < C; ++c) {
+      float z = aten_bilerp(h0, h1, w0, w1, to_float<T>(pl[o00]), to_float<T>(pl[o01]), to_float<T>(pl[o10]), to_float<T>(pl[o11]));
+      if constexpr (sizeof(T) == 2) z = to_float<T>(from_float<T>(z));
+      if (z > best) { best = z; bi = c; }   // lowest index wins ties
+      pl += hw;
+    }
+    if (pout) pout[px] = bi;
+    if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv);
+    else if (gv != kIgnored) ctr.update(bi, gv);
+  }
+}
+
 template <typename T, int THREADS, bool PRIVATE>
 __global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfParams p, const int align_corners) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int run_x[kRunTableMax + 2];
   Counters<THREADS, PRIVATE> ctr{reinterpret_cast<unsigned int*>(smem_raw), p.C};
   ctr.zero();
   __syncthreads();
@@ -381,38 +442,86 @@ __global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfPar
   ClassDecoder dgt;
   dgt.init(p.gt_dtype, C, true, p.ignore);
   const bool ac = align_corners != 0;
+  constexpr int PXC = 8;
   while (chunk < chunk_end) {
     while (img + 1 < p.n_images && chunk >= p.chunk_prefix[img + 1]) ++img;
     const b200seg_image im = p.images[img];
     const long long img_chunk_end = p.chunk_prefix[img + 1] < chunk_end ? p.chunk_prefix[img + 1] : chunk_end;
-    const long long px_begin = (chunk - p.chunk_prefix[img]) * kChunk;
-    long long px_end = (img_chunk_end - p.chunk_prefix[img]) * kChunk;
-    if (px_end > im.n_pixels) px_end = im.n_pixels;
     const float sh = resize_scale(im.h, im.H, ac), sw = resize_scale(im.w, im.W, ac);
-    const long long hw = (long long)im.h * im.w;
     long long* pout = p.pred_out ? p.pred_out[img] : nullptr;
-    const T* base = reinterpret_cast<const T*>(im.pred);
-    for (long long px = px_begin + threadIdx.x; px < px_end; px += THREADS) {
-      const int gv = dgt.one(im.gt, (size_t)px);
-      const int Y = (int)(px / im.W), X = (int)(px - (long long)Y * im.W);
-      int y0, y1, x0, x1;
-      float ly, lx;
-      resize_src(sh, Y, im.h, ac, y0, y1, ly);
-      resize_src(sw, X, im.w, ac, x0, x1, lx);
-      const float h1 = ly, h0 = 1.f - ly, w1 = lx, w0 = 1.f - lx;
-      const int o00 = y0 * im.w + x0, o01 = y0 * im.w + x1, o10 = y1 * im.w + x0, o11 = y1 * im.w + x1;
-      float best = neg_inf();
-      int bi = 0;
-      const T* pl = base;
-      for (int c = 0; c < C; ++c) {
-        const float z = h0 * (w0 * to_float<T>(pl[o00]) + w1 * to_float<T>(pl[o01])) +
-                        h1 * (w0 * to_float<T>(pl[o10]) + w1 * to_float<T>(pl[o11]));
-        if (z > best) { best = z; bi = c; }   // lowest index wins ties
-        pl += hw;
+    if (im.w + 2 > kRunTableMax) {   // logits wider than the run table: per-pixel form
+      const long long px_begin = (chunk - p.chunk_prefix[img]) * kChunk;
+      long long px_end = (img_chunk_end - p.chunk_prefix[img]) * kChunk;
+      if (px_end > im.n_pixels) px_end = im.n_pixels;
+      resize_pixels_simple<T, THREADS, PRIVATE>(im, px_begin, px_end, sh, sw, ac, C, dgt, pout, ctr);
+      if (!p.totals_only) {
+        ctr.flush(p.areas + (size_t)img * 3 * C);
+      } else {
+        since_flush += img_chunk_end - chunk;
+        if (since_flush >= kMaxChunksPerFlush) { ctr.flush(p.areas); since_flush = 0; }
       }
-      if (pout) pout[px] = bi;
-      if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv);
-      else if (gv != kIgnored) ctr.update(bi, gv);
+      chunk = img_chunk_end;
+      continue;
+    }
+    const int hw = im.h * im.w;
+    const T* base = reinterpret_cast<const T*>(im.pred);
+    // run starts of this image: run r = columns [run_x[r], run_x[r + 1])
+    __syncthreads();
+    for (int r = threadIdx.x; r <= im.w + 1; r += THREADS) run_x[r] = aten_run_start(sw, r, im.w, im.W, ac);
+    __syncthreads();
+    // this CTA's share of the image's (row, run) units: the image's chunks split the units evenly
+    const int runs = im.w + 1;
+    const long long units = (long long)im.H * runs;
+    const long long img_chunks = p.chunk_prefix[img + 1] - p.chunk_prefix[img];
+    const long long upc = (units + img_chunks - 1) / img_chunks;
+    const long long u_begin = (chunk - p.chunk_prefix[img]) * upc;
+    long long u_end = (img_chunk_end - p.chunk_prefix[img]) * upc;
+    if (u_end > units) u_end = units;
+    for (long long u = u_begin + threadIdx.x; u < u_end; u += THREADS) {
+      const int Y = (int)(u / runs), r = (int)(u - (long long)Y * runs);
+      const int X0 = run_x[r], X1 = run_x[r + 1];
+      if (X0 >= X1) continue;
+      int y0, y1, x0, x1;
+      float ly, lxf;
+      resize_src(sh, Y, im.h, ac, y0, y1, ly);
+      resize_src(sw, X0, im.w, ac, x0, x1, lxf);           // (x0, x1) is the same for every column of the run
+      const float h1 = ly, h0 = __fsub_rn(1.f, ly);
+      const int o00 = y0 * im.w + x0, o01 = y0 * im.w + x1, o10 = y1 * im.w + x0, o11 = y1 * im.w + x1;
+      const long long row_px = (long long)Y * im.W;
+      for (int Xc = X0; Xc < X1; Xc += PXC) {
+        const int npx = min(PXC, X1 - Xc);
+        float w0[PXC], w1[PXC], best[PXC];
+        int bi[PXC];
+#pragma unroll
+        for (int j = 0; j < PXC; ++j) {
+          const float s = aten_src_index(sw, Xc + min(j, npx - 1), ac);
+          w1[j] = __fsub_rn(s, (float)x0);                 // ATen: lambda1 = src - (int)src, and (int)src == x0 in this run
+          w0[j] = __fsub_rn(1.f, w1[j]);
+          best[j] = neg_inf();
+          bi[j] = 0;
+        }
+        const T* pl = base;
+        for (int c = 0; c < C; ++c) {
+          const float a = to_float<T>(__ldg(pl + o00)), b = to_float<T>(__ldg(pl + o01));
+          const float cc = to_float<T>(__ldg(pl + o10)), d = to_float<T>(__ldg(pl + o11));
+          pl += hw;
+#pragma unroll
+          for (int j = 0; j < PXC; ++j) {
+            float z = aten_bilerp(h0, h1, w0[j], w1[j], a, b, cc, d);
+            if constexpr (sizeof(T) == 2) z = to_float<T>(from_float<T>(z));   // F.interpolate returns the logit dtype
+            if (z > best[j]) { best[j] = z; bi[j] = c; }                      // lowest index wins ties
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < PXC; ++j) {
+          const bool ok = j < npx;
+          const long long px = row_px + Xc + min(j, npx - 1);
+          const int gv = ok ? dgt.one(im.gt, (size_t)px) : kIgnored;
+          if (ok && pout) pout[px] = bi[j];
+          if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi[j], gv);
+          else if (gv != kIgnored) ctr.update(bi[j], gv);
+        }
+      }
     }
     if (!p.totals_only) {
       ctr.flush(p.areas + (size_t)img * 3 * C);

@@ -11,13 +11,17 @@
 // computed on.
 //
 // Structure — a "class-sliced" bulk-copy pipeline:
-//   * A persistent CTA owns a contiguous range of 128-pixel tiles. A producer warp issues one `cp.async.bulk`
-//     (global -> shared, completion on an mbarrier) per class row of the tile plus one for the label row (and the saved
-//     log-sum-exp row in the backward), 2-4 stages ahead: bytes in flight are set by the stage count, not by registers.
-//   * Eight consumer warps; a warp owns 16 pixels of the tile, and inside the warp the 32 lanes form 4 pixel groups x 8
-//     CLASS SLICES: lane (j, g) holds classes {8 i + j} of pixels 4 g .. 4 g + 3 — CPT x 4 values, read with one 8-byte
-//     (16-bit logits) or 16-byte (fp32) shared-memory access per class row. Rows are padded by one warp span so that the
-//     8 x 4 accesses of a wavefront hit distinct banks.
+//   * A persistent CTA owns a contiguous range of 128-pixel tiles. A producer warp issues TENSOR-MAP TMA copies
+//     (`cp.async.bulk.tensor.2d`, global -> shared, completion on an mbarrier): one instruction per box of
+//     (128 bytes of pixels) x (all C class rows), i.e. 2 (16-bit) or 4 (fp32) per tile, plus one plain bulk copy for the
+//     label row (and the saved log-sum-exp row in the backward), 2-5 stages ahead: bytes in flight are set by the stage
+//     count, not by registers. (One `cp.async.bulk` per 256-byte class row — the first version — was bound by the copy
+//     ISSUE rate: ~70 cycles per copy per SM, 1.2 ms per pass at ADE20K shape.)
+//   * Boxes land 128B-swizzled (16-byte chunk index XOR row index mod 8). Consumer warps (8 per tile): a warp owns 16
+//     pixels of the tile, and inside the warp the 32 lanes form 4 pixel groups x 8 CLASS SLICES: lane (j, g) holds
+//     classes {8 i + j} of its group's pixels, read with one 4-byte (16-bit logits, 2 pixels) or 16-byte (fp32, 4 pixels)
+//     shared-memory access per class row; row 8 i + j sits at chunk (c XOR j), so the 8 slices x 4 groups of a wavefront
+//     hit 32 distinct banks.
 //   * Per-pixel reductions over the class dimension (max, sum of exponentials, the backward's dot product) are CPT
 //     register operations plus THREE xor-shuffles — the slices of a pixel live in one warp, so there is no CTA barrier
 //     and no shared-memory exchange. The maximum is taken on the PACKED 16-bit pairs (HMNMX2).
@@ -35,6 +39,8 @@
 //
 // Bound: HBM (forward is close to issue balance at 16-bit width: ~8.5 thread instructions per element).
 // Algorithmic bytes per launch: forward N*C*H*W*s + N*H*W*(L+4), backward 2*N*C*H*W*s + N*H*W*(L+4).
+#include <cuda.h>   // CUtensorMap (the encode entry point is fetched through the runtime: no link against libcuda)
+
 #include "bulk_pipe.cuh"
 #include "common.cuh"
 
@@ -44,7 +50,8 @@ constexpr int kCsSlices = 8;      // class slices per pixel group (lane bits 2..
 constexpr int kCsLanePx = 4;      // consecutive pixels per lane
 constexpr int kCsWarpPx = 16;     // pixels per consumer warp per tile (4 groups x 4 pixels)
 constexpr int kCsGroupWarps = 8;  // consumer warps per tile (a "group"); a CTA runs G groups on alternating tiles
-constexpr int kCsMaxStages = 4;
+constexpr int kCsMaxStages = 6;
+constexpr int kCsBoxBytes = 128;   // inner extent of a TMA box = one swizzle row
 
 struct CsParams {
   const void* logits;
@@ -63,7 +70,7 @@ struct CsParams {
   long long HW;
   int tiles_per_image;
   long long total_tiles, tiles_per_cta;
-  int stages, stage_bytes, row_pitch, label_off, lse_off;
+  int stages, stage_bytes, block_bytes, label_off, lse_off;   // block = one TMA box in shared memory: CP rows x 128 bytes
   int flags;
   long long ignore_index, dice_ignore;
   int acc_has_ignore;
@@ -79,7 +86,7 @@ template <typename T> struct CsCfg {
   static constexpr int PX = sizeof(T) == 2 ? 2 : 4;
   static constexpr int kPasses = kCsLanePx / PX;
   static constexpr int kWords = PX * (int)sizeof(T) / 4;      // 1 (16-bit) or 4 (fp32)
-  static constexpr int kPadPx = sizeof(T) == 2 ? 8 : 16;      // row padding: the 8 slices x 4 groups of a wavefront hit distinct banks
+  static constexpr int kBoxPx = kCsBoxBytes / (int)sizeof(T);  // pixels per TMA box row: 64 (16-bit) or 32 (fp32)
 };
 template <typename T> struct CsRow {
   uint32_t w[CsCfg<T>::kWords];
@@ -148,44 +155,68 @@ __device__ __forceinline__ CsTile cs_tile(const CsParams& p, long long t, int TP
   return r;
 }
 
-// Producer warp body shared by both directions (REVERSE walks the range back to front).
+// Shared-memory address of (class row, pixel) inside a stage: box = pixel's 128-byte column block, 128B swizzle inside.
+template <typename T> __device__ __forceinline__ unsigned cs_offset(const CsParams& p, int row, int px) {
+  const unsigned byte = (unsigned)px * (unsigned)sizeof(T);
+  const unsigned blk = byte >> 7, inb = byte & 127u;
+  return blk * (unsigned)p.block_bytes + (unsigned)row * 128u + ((((inb >> 4) ^ ((unsigned)row & 7u)) << 4) | (inb & 15u));
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<unsigned long long>(map)),
+               "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+
+// Producer warp body shared by both directions (REVERSE walks the range back to front): lane 0 issues the boxes of a tile.
 template <typename T, bool WITH_LSE, bool REVERSE>
-__device__ __forceinline__ void cs_producer(const CsParams& p, unsigned char* smem, unsigned long long* full_bar,
-                                            unsigned long long* empty_bar, long long t0, long long t1, int TP, int lane) {
+__device__ __forceinline__ void cs_producer(const CsParams& p, const CUtensorMap* map, unsigned char* smem,
+                                            unsigned long long* full_bar, unsigned long long* empty_bar, long long t0,
+                                            long long t1, int TP, int lane) {
+  constexpr int BOXPX = CsCfg<T>::kBoxPx;
   const int C = p.C, NS = p.stages;
   int k = 0;
   for (long long tt = t0; tt < t1; ++tt, ++k) {
     const long long t = REVERSE ? (t1 - 1 - (tt - t0)) : tt;
     const int s = k % NS;
     if (k >= NS) mbar_wait(&empty_bar[s], ((k / NS) - 1) & 1);
-    const CsTile tl = cs_tile(p, t, TP);
-    const unsigned row_bytes = (unsigned)(tl.npx * sizeof(T));
-    const unsigned lab_bytes = (unsigned)(tl.npx * p.label_bytes);
-    const unsigned lse_bytes = WITH_LSE ? (unsigned)(tl.npx * 4) : 0u;
-    unsigned char* stage = smem + (size_t)s * p.stage_bytes;
-    if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (unsigned)C * row_bytes + lab_bytes + lse_bytes);
-    __syncwarp();
-    const char* src = reinterpret_cast<const char*>(p.logits) + ((size_t)tl.n * C * p.HW + tl.px0) * sizeof(T);
-    for (int c = lane; c < C; c += 32)
-      bulk_g2s(stage + (size_t)c * p.row_pitch, src + (size_t)c * p.HW * sizeof(T), row_bytes, &full_bar[s]);
-    if (lane == 0)
+    if (lane == 0) {
+      const CsTile tl = cs_tile(p, t, TP);
+      const int nbox = (tl.npx + BOXPX - 1) / BOXPX;           // boxes that start inside the image (a partial one is zero-filled)
+      const unsigned lab_bytes = (unsigned)(tl.npx * p.label_bytes);
+      const unsigned lse_bytes = WITH_LSE ? (unsigned)(tl.npx * 4) : 0u;
+      unsigned char* stage = smem + (size_t)s * p.stage_bytes;
+      mbar_arrive_expect_tx(&full_bar[s], (unsigned)nbox * (unsigned)C * (unsigned)kCsBoxBytes + lab_bytes + lse_bytes);
+      for (int bx = 0; bx < nbox; ++bx)
+        tma_load_2d(stage + (size_t)bx * p.block_bytes, map, (int)(tl.px0 + (long long)bx * BOXPX), tl.n * C, &full_bar[s]);
       bulk_g2s(stage + p.label_off, reinterpret_cast<const char*>(p.labels) + ((size_t)tl.n * p.HW + tl.px0) * p.label_bytes,
                lab_bytes, &full_bar[s]);
-    if (WITH_LSE && lane == 1)
-      bulk_g2s(stage + p.lse_off, reinterpret_cast<const char*>(p.lse + (size_t)tl.n * p.HW + tl.px0), lse_bytes, &full_bar[s]);
+      if (WITH_LSE)
+        bulk_g2s(stage + p.lse_off, reinterpret_cast<const char*>(p.lse + (size_t)tl.n * p.HW + tl.px0), lse_bytes, &full_bar[s]);
+    }
+    __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
 template <typename T, int CPT, int G>
-__global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel(const CsParams p) {
+__global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel(const CsParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int NWG = kCsGroupWarps, NW = NWG * G;
   constexpr int TP = NWG * kCsWarpPx;
   constexpr int CP = CPT * kCsSlices;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ unsigned char smem_dyn[];
+  // stages are 1024-byte aligned: the 128B swizzle is a function of the shared-memory ADDRESS bits
+  unsigned char* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   __shared__ __align__(8) unsigned long long full_bar[kCsMaxStages], empty_bar[kCsMaxStages];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C = p.C, NS = p.stages, RP = p.row_pitch;
+  const int C = p.C, NS = p.stages;
   const bool dice = (p.flags & B200SEG_WANT_DICE) != 0;
   float* bins = reinterpret_cast<float*>(smem_raw + (size_t)NS * p.stage_bytes);   // [NW][2][C]
   if (tid == 0) {
@@ -194,13 +225,13 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
   }
   // rows C..CP-1 of every stage are never written by the bulk copies: -inf once (exp -> 0, max unaffected)
   {
-    const int words_per_row = (TP * (int)sizeof(T)) / 4;
-    const int pad_words = (CP - C) * words_per_row;
+    constexpr int kBlocks = TP * (int)sizeof(T) / kCsBoxBytes;     // TMA boxes per tile
+    const int pad_words = (CP - C) * (kCsBoxBytes / 4);            // per block: rows C..CP-1 (swizzling permutes inside a row)
     for (int s = 0; s < NS; ++s)
-      for (int i = tid; i < pad_words; i += blockDim.x) {
-        const int r = i / words_per_row, wd = i - r * words_per_row;
-        reinterpret_cast<uint32_t*>(smem_raw + (size_t)s * p.stage_bytes + (size_t)(C + r) * RP)[wd] = neg_inf_word<T>();
-      }
+      for (int bx = 0; bx < kBlocks; ++bx)
+        for (int i = tid; i < pad_words; i += blockDim.x)
+          reinterpret_cast<uint32_t*>(smem_raw + (size_t)s * p.stage_bytes + (size_t)bx * p.block_bytes + (size_t)C * kCsBoxBytes)[i] =
+              neg_inf_word<T>();
     for (int i = tid; i < NW * 2 * C; i += blockDim.x) bins[i] = 0.f;
   }
   __syncthreads();
@@ -211,10 +242,10 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
   int n_valid = 0, n_correct = 0, n_bad = 0, n_acc = 0;
 
   if (warp == NW) {
-    cs_producer<T, false, false>(p, smem_raw, full_bar, empty_bar, t0, t1, TP, lane);
+    cs_producer<T, false, false>(p, &tmap, smem_raw, full_bar, empty_bar, t0, t1, TP, lane);
   } else {
     constexpr int PX = CsCfg<T>::PX, kPasses = CsCfg<T>::kPasses;
-    const int j = lane >> 2, g = lane & 3;
+    const int j = lane & 7, g = lane >> 3;                   // class slice / pixel group
     const int grp = warp / NWG;
     const int pxo = (warp % NWG) * kCsWarpPx;                // first pixel of this warp inside the tile
     float* A_w = bins + (size_t)warp * 2 * C;
@@ -229,8 +260,8 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           float t = acc[i];
-          t += __shfl_xor_sync(0xffffffffu, t, 1);
-          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 8);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
           const int c = i * kCsSlices + j;
           if (g == 0 && c < C) atomicAdd(p.dice_part + ((size_t)n * C + c) * 3 + 1, (double)t);
           acc[i] = 0.f;
@@ -263,18 +294,18 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
 #pragma unroll
       for (int h = 0; h < kPasses; ++h) {
         const int pxh = pxo + h * 4 * PX + g * PX;          // first pixel of this lane in pass h
-        const unsigned char* col = stage + (size_t)j * RP + (size_t)pxh * sizeof(T);   // class 8 i + j: col + i * 8 * RP
+        const unsigned char* col = stage + cs_offset<T>(p, j, pxh);   // class row 8 i + j: col + i * 1024 (same swizzle phase)
         const bool in = pxh < tl.npx;   // npx is a multiple of 16 bytes / sizeof(T) >= PX: a lane's pixels are all in or all out
 
         // sweep 1: the lane's CPT x PX logits (kept packed) and their maximum per pixel
         CsRow<T> zr[CPT];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) zr[i] = cs_load<T>(col + (size_t)i * kCsSlices * RP);
+        for (int i = 0; i < CPT; ++i) zr[i] = cs_load<T>(col + (size_t)i * (kCsSlices * kCsBoxBytes));
         CsRow<T> mx = zr[0];
 #pragma unroll
         for (int i = 1; i < CPT; ++i) cs_max<T>(mx, zr[i]);
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
+        for (int o = 1; o <= 4; o <<= 1) {
           CsRow<T> ot;
 #pragma unroll
           for (int q = 0; q < CsCfg<T>::kWords; ++q) ot.w[q] = __shfl_xor_sync(0xffffffffu, mx.w[q], o);
@@ -298,7 +329,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
           }
         }
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
+        for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
           for (int v = 0; v < PX; ++v) Sh[v] += __shfl_xor_sync(0xffffffffu, Sh[v], o);
         }
@@ -335,7 +366,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
         n_bad += (!ign && !inr);
         n_valid += !ign;
         const int ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);
-        const float zy = to_float<T>(reinterpret_cast<const T*>(stage + (size_t)ycc * RP)[t_px]);
+        const float zy = to_float<T>(*reinterpret_cast<const T*>(stage + cs_offset<T>(p, ycc, t_px)));
         const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
         if (valid && (p.flags & B200SEG_WANT_CE)) {
           const float wt = p.cw ? __ldg(p.cw + ycc) : 1.f;
@@ -365,55 +396,61 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
 // grad_c = p_c (b_c p_c + sub) - onehot_c (p_y da + kk),   sub = kk - dot,   dot = sum_c b_c p_c^2 - da p_y
 //   b_c = 2 god beta[n][c],  da = god alpha[n][y] (Dice-valid pixels),  kk = Gce pw cw[y] (CE-valid pixels)
 template <typename T, int CPT, int G>
-__global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel(const CsParams p) {
+__global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel(const CsParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                                  const __grid_constant__ CUtensorMap tmap_grad) {
   constexpr int NWG = kCsGroupWarps, NW = NWG * G;
   constexpr int TP = NWG * kCsWarpPx;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ unsigned char smem_dyn[];
+  // stages are 1024-byte aligned: the 128B swizzle is a function of the shared-memory ADDRESS bits
+  unsigned char* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   __shared__ __align__(8) unsigned long long full_bar[kCsMaxStages], done_bar[kCsMaxStages], empty_bar[kCsMaxStages];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int C = p.C, NS = p.stages, RP = p.row_pitch;
+  const int C = p.C, NS = p.stages;
   constexpr int CP = CPT * kCsSlices;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&done_bar[s], NWG); mbar_init(&empty_bar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    const int words_per_row = (TP * (int)sizeof(T)) / 4;
-    const int pad_words = (CP - C) * words_per_row;
+    constexpr int kBlocks = TP * (int)sizeof(T) / kCsBoxBytes;     // TMA boxes per tile
+    const int pad_words = (CP - C) * (kCsBoxBytes / 4);            // per block: rows C..CP-1 (swizzling permutes inside a row)
     for (int s = 0; s < NS; ++s)
-      for (int i = tid; i < pad_words; i += blockDim.x) {
-        const int r = i / words_per_row, wd = i - r * words_per_row;
-        reinterpret_cast<uint32_t*>(smem_raw + (size_t)s * p.stage_bytes + (size_t)(C + r) * RP)[wd] = neg_inf_word<T>();
-      }
+      for (int bx = 0; bx < kBlocks; ++bx)
+        for (int i = tid; i < pad_words; i += blockDim.x)
+          reinterpret_cast<uint32_t*>(smem_raw + (size_t)s * p.stage_bytes + (size_t)bx * p.block_bytes + (size_t)C * kCsBoxBytes)[i] =
+              neg_inf_word<T>();
   }
   __syncthreads();
   const long long t0 = (long long)blockIdx.x * p.tiles_per_cta;
   const long long t1 = (t0 + p.tiles_per_cta < p.total_tiles) ? t0 + p.tiles_per_cta : p.total_tiles;
 
   if (warp == NW) {
-    cs_producer<T, true, true>(p, smem_raw, full_bar, empty_bar, t0, t1, TP, lane);
+    cs_producer<T, true, true>(p, &tmap, smem_raw, full_bar, empty_bar, t0, t1, TP, lane);
   } else if (warp == NW + 1) {
-    // store warp: every lane hands its class rows of a finished tile to the bulk-store engine; the stage goes back to the
-    // producer as soon as the engine has READ it
+    // store warp: lane 0 hands the boxes of a finished tile to the TMA store engine; the stage goes back to the producer
+    // as soon as the engine has READ it
+    constexpr int BOXPX = CsCfg<T>::kBoxPx;
     int k = 0;
     for (long long tt = t0; tt < t1; ++tt, ++k) {
       const long long t = t1 - 1 - (tt - t0);
       const int s = k % NS;
       mbar_wait(&done_bar[s], (k / NS) & 1);
-      const CsTile tl = cs_tile(p, t, TP);
-      const unsigned row_bytes = (unsigned)(tl.npx * sizeof(T));
-      unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
-      char* dst = reinterpret_cast<char*>(p.grad) + ((size_t)tl.n * C * p.HW + tl.px0) * sizeof(T);
-      for (int c = lane; c < C; c += 32) bulk_s2g(dst + (size_t)c * p.HW * sizeof(T), stage + (size_t)c * RP, row_bytes);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (lane == 0) {
+        const CsTile tl = cs_tile(p, t, TP);
+        const int nbox = (tl.npx + BOXPX - 1) / BOXPX;
+        unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
+        for (int bx = 0; bx < nbox; ++bx)
+          tma_store_2d(&tmap_grad, (int)(tl.px0 + (long long)bx * BOXPX), tl.n * C, stage + (size_t)bx * p.block_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&empty_bar[s]);
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     constexpr int PX = CsCfg<T>::PX, kPasses = CsCfg<T>::kPasses;
-    const int j = lane >> 2, g = lane & 3;
+    const int j = lane & 7, g = lane >> 3;
     const int grp = warp / NWG;
     const int pxo = (warp % NWG) * kCsWarpPx;
     const bool want_ce = (p.flags & B200SEG_WANT_CE) != 0;
@@ -459,7 +496,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
         if (yy != p.dice_ignore) da = god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 0);
         by = 2.f * god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 1);
         const float lse_own = reinterpret_cast<const float*>(stage + p.lse_off)[t_px];
-        const float zy = to_float<T>(reinterpret_cast<const T*>(stage + (size_t)ycc * RP)[t_px]);
+        const float zy = to_float<T>(*reinterpret_cast<const T*>(stage + cs_offset<T>(p, ycc, t_px)));
         py = ex2(fmaf(zy, kLog2e, -lse_own * kLog2e));
         extra = -fmaf(da, py, kk);
       }
@@ -467,7 +504,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
 #pragma unroll
       for (int h = 0; h < kPasses; ++h) {
         const int pxh = pxo + h * 4 * PX + g * PX;
-        unsigned char* col = stage + (size_t)j * RP + (size_t)pxh * sizeof(T);
+        unsigned char* col = stage + cs_offset<T>(p, j, pxh);
         float nl[PX], D[PX];
 #pragma unroll
         for (int v = 0; v < PX; ++v) {
@@ -477,7 +514,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
         float pr[CPT][PX];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-          const CsRow<T> zr = cs_load<T>(col + (size_t)i * kCsSlices * RP);
+          const CsRow<T> zr = cs_load<T>(col + (size_t)i * (kCsSlices * kCsBoxBytes));
           float z[PX];
           cs_unpack<T>(zr, z);
 #pragma unroll
@@ -490,7 +527,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
 #pragma unroll
         for (int v = 0; v < PX; ++v) D[v] += (j == h * PX + v) ? extra : 0.f;
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
+        for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
           for (int v = 0; v < PX; ++v) D[v] += __shfl_xor_sync(0xffffffffu, D[v], o);
         }
@@ -501,13 +538,13 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
           float gq[PX];
 #pragma unroll
           for (int v = 0; v < PX; ++v) gq[v] = pr[i][v] * fmaf(pr[i][v], b[i], -D[v]);
-          if (i < CPT - 1 || i * kCsSlices + j < C) cs_store<T>(col + (size_t)i * kCsSlices * RP, gq);   // pad rows stay -inf
+          if (i < CPT - 1 || i * kCsSlices + j < C) cs_store<T>(col + (size_t)i * (kCsSlices * kCsBoxBytes), gq);   // pad rows stay -inf
         }
       }
       __syncwarp();
       // one-hot term: the label's class is re-stored by the owner (after the slice lanes, same warp) with -(p_y da + kk)
       if (owner && (da != 0.f || kk != 0.f))
-        reinterpret_cast<T*>(stage + (size_t)ycc * RP)[t_px] = from_float<T>(py * fmaf(py, by, -Down) - fmaf(py, da, kk));
+        *reinterpret_cast<T*>(stage + cs_offset<T>(p, ycc, t_px)) = from_float<T>(py * fmaf(py, by, -Down) - fmaf(py, da, kk));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&done_bar[s]);
@@ -517,7 +554,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
 
 // ------------------------------------------------------------------------------------------------ host side
 struct CsGeom {
-  int cpt, stages, stage_bytes, row_pitch, label_off, lse_off, ctas_per_sm;
+  int cpt, groups, stages, stage_bytes, block_bytes, label_off, lse_off;
   size_t smem_fwd, smem_bwd;
 };
 
@@ -532,21 +569,22 @@ static int cs_cpt_for(int C) {
 static bool cs_geometry(int C, int elem, CsGeom* g) {
   const int cpt = cs_cpt_for(C);
   if (!cpt) return false;
-  constexpr int TP = 8 * kCsWarpPx;
+  constexpr int TP = kCsGroupWarps * kCsWarpPx;
   g->cpt = cpt;
-  g->row_pitch = (TP + (elem == 2 ? 8 : 16)) * elem;   // CsCfg<T>::kPadPx
-  g->label_off = cpt * kCsSlices * g->row_pitch;
+  g->groups = elem == 2 ? 2 : 1;
+  g->block_bytes = cpt * kCsSlices * kCsBoxBytes;                      // CP rows x 128 bytes: a multiple of 1024
+  const int blocks = TP * elem / kCsBoxBytes;
+  g->label_off = blocks * g->block_bytes;
   g->lse_off = g->label_off + TP * 8;
-  g->stage_bytes = g->lse_off + TP * 4;
-  g->ctas_per_sm = 1;
-  const size_t bins = (size_t)kCsGroupWarps * (elem == 2 ? 2 : 1) * 2 * C * sizeof(float);
-  const size_t budget = (size_t)(225 * 1024);
+  g->stage_bytes = ((g->lse_off + TP * 4 + 1023) / 1024) * 1024;      // stages stay 1024-byte aligned (swizzle phase)
+  const size_t bins = (size_t)kCsGroupWarps * g->groups * 2 * C * sizeof(float);
+  const size_t budget = (size_t)(224 * 1024);
   int st = (int)((budget - bins) / g->stage_bytes);
   if (st > kCsMaxStages) st = kCsMaxStages;
   if (st < 2) return false;
   g->stages = st;
-  g->smem_fwd = (size_t)st * g->stage_bytes + bins;
-  g->smem_bwd = (size_t)st * g->stage_bytes;
+  g->smem_fwd = (size_t)st * g->stage_bytes + bins + 1024;   // + alignment slack
+  g->smem_bwd = (size_t)st * g->stage_bytes + 1024;
   return true;
 }
 
@@ -562,34 +600,70 @@ bool cs_supported(const void* logits, const void* labels, const void* lse, const
   return cs_geometry(C, elem, &g);
 }
 
-template <typename T, int CPT, bool BWD> static int cs_launch_t(CsParams p, const CsGeom& g, cudaStream_t st) {
-  constexpr int G = sizeof(T) == 2 ? 2 : 1;   // 16-bit: two consumer groups share one CTA (112 registers per thread)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn cs_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// (N*C, HW) view of an NCHW tensor; box = (128 bytes of pixels) x (C rows), 128B swizzle, out-of-range pixels read as 0
+static int cs_make_map(CUtensorMap* map, const void* base, int logit_dtype, int N, int C, long long HW) {
+  EncodeTiledFn enc = cs_encode_fn();
+  B200SEG_REQUIRE(enc != nullptr, "class-sliced pipeline: cuTensorMapEncodeTiled is not available from this driver");
+  const int elem = logit_bytes(logit_dtype);
+  const CUtensorMapDataType dt = logit_dtype == B200SEG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                               : (logit_dtype == B200SEG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  const cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)N * (cuuint64_t)C};
+  const cuuint64_t strides[1] = {(cuuint64_t)HW * (cuuint64_t)elem};
+  const cuuint32_t box[2] = {(cuuint32_t)(kCsBoxBytes / elem), (cuuint32_t)C};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200SEG_REQUIRE(r == CUDA_SUCCESS, "class-sliced pipeline: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <typename T, int CPT, bool BWD> static int cs_launch_t(CsParams p, const CsGeom& g, int logit_dtype, cudaStream_t st) {
+  constexpr int G = sizeof(T) == 2 ? 2 : 1;   // 16-bit: two consumer groups of 8 warps share one CTA
   constexpr int NW = kCsGroupWarps * G;
-  long long grid = (long long)kSMs * g.ctas_per_sm;
+  long long grid = kSMs;
   if (grid > p.total_tiles) grid = p.total_tiles;
   p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
   grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  CUtensorMap map_in;
+  if (int e = cs_make_map(&map_in, p.logits, logit_dtype, p.N, p.C, p.HW)) return e;
   if constexpr (BWD) {
+    CUtensorMap map_out;
+    if (int e = cs_make_map(&map_out, p.grad, logit_dtype, p.N, p.C, p.HW)) return e;
     auto k = cs_bwd_kernel<T, CPT, G>;
     if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)g.smem_bwd)) return e;
-    k<<<(unsigned)grid, (NW + 2) * 32, g.smem_bwd, st>>>(p);
+    k<<<(unsigned)grid, (NW + 2) * 32, g.smem_bwd, st>>>(p, map_in, map_out);
     count_launch();
     return check_launch("cs_bwd_kernel");
   } else {
     auto k = cs_fwd_kernel<T, CPT, G>;
     if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)g.smem_fwd)) return e;
-    k<<<(unsigned)grid, (NW + 1) * 32, g.smem_fwd, st>>>(p);
+    k<<<(unsigned)grid, (NW + 1) * 32, g.smem_fwd, st>>>(p, map_in);
     count_launch();
     return check_launch("cs_fwd_kernel");
   }
 }
 
-template <typename T, bool BWD> static int cs_launch(const CsParams& p, const CsGeom& g, cudaStream_t st) {
+template <typename T, bool BWD> static int cs_launch(const CsParams& p, const CsGeom& g, int logit_dtype, cudaStream_t st) {
   switch (g.cpt) {
-    case 8: return cs_launch_t<T, 8, BWD>(p, g, st);
-    case 12: return cs_launch_t<T, 12, BWD>(p, g, st);
-    case 16: return cs_launch_t<T, 16, BWD>(p, g, st);
-    case 19: return cs_launch_t<T, 19, BWD>(p, g, st);
+    case 8: return cs_launch_t<T, 8, BWD>(p, g, logit_dtype, st);
+    case 12: return cs_launch_t<T, 12, BWD>(p, g, logit_dtype, st);
+    case 16: return cs_launch_t<T, 16, BWD>(p, g, logit_dtype, st);
+    case 19: return cs_launch_t<T, 19, BWD>(p, g, logit_dtype, st);
   }
   set_error("class-sliced pipeline: unsupported class count %d", p.C);
   return 1;
@@ -599,14 +673,14 @@ template <bool BWD> static int cs_dispatch(CsParams p, int logit_dtype, cudaStre
   CsGeom g;
   const int elem = logit_bytes(logit_dtype);
   B200SEG_REQUIRE(cs_geometry(p.C, elem, &g), "class-sliced pipeline: unsupported shape (C=%d)", p.C);
-  constexpr int TP = 8 * kCsWarpPx;
-  p.stages = g.stages; p.stage_bytes = g.stage_bytes; p.row_pitch = g.row_pitch; p.label_off = g.label_off; p.lse_off = g.lse_off;
+  constexpr int TP = kCsGroupWarps * kCsWarpPx;
+  p.stages = g.stages; p.stage_bytes = g.stage_bytes; p.block_bytes = g.block_bytes; p.label_off = g.label_off; p.lse_off = g.lse_off;
   p.tiles_per_image = (int)((p.HW + TP - 1) / TP);
   p.total_tiles = (long long)p.tiles_per_image * p.N;
   switch (logit_dtype) {
-    case B200SEG_F32: return cs_launch<float, BWD>(p, g, st);
-    case B200SEG_BF16: return cs_launch<__nv_bfloat16, BWD>(p, g, st);
-    case B200SEG_F16: return cs_launch<__half, BWD>(p, g, st);
+    case B200SEG_F32: return cs_launch<float, BWD>(p, g, logit_dtype, st);
+    case B200SEG_BF16: return cs_launch<__nv_bfloat16, BWD>(p, g, logit_dtype, st);
+    case B200SEG_F16: return cs_launch<__half, BWD>(p, g, logit_dtype, st);
   }
   set_error("unsupported logit dtype %d", logit_dtype);
   return 1;

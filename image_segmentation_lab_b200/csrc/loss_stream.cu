@@ -73,15 +73,15 @@ __device__ __forceinline__ Taps make_taps(int Y, int X, int h, int w, float sh, 
   resize_src(sw, X, w, ac, x0, x1, lx);
   Taps t;
   t.o00 = y0 * w + x0; t.o01 = y0 * w + x1; t.o10 = y1 * w + x0; t.o11 = y1 * w + x1;
-  t.h1 = ly; t.h0 = 1.f - ly; t.w1 = lx; t.w0 = 1.f - lx;
+  t.h1 = ly; t.h0 = __fsub_rn(1.f, ly); t.w1 = lx; t.w0 = __fsub_rn(1.f, lx);
   t.w00 = t.h0 * t.w0; t.w01 = t.h0 * t.w1; t.w10 = t.h1 * t.w0; t.w11 = t.h1 * t.w1;
   return t;
 }
-// ATen evaluation order: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+// ATen's expression h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11) with its contraction pinned (common.cuh)
 template <typename T> __device__ __forceinline__ float interp(const T* plane, const Taps& t) {
   float v00 = to_float<T>(plane[t.o00]), v01 = to_float<T>(plane[t.o01]);
   float v10 = to_float<T>(plane[t.o10]), v11 = to_float<T>(plane[t.o11]);
-  return t.h0 * (t.w0 * v00 + t.w1 * v01) + t.h1 * (t.w0 * v10 + t.w1 * v11);
+  return aten_bilerp(t.h0, t.h1, t.w0, t.w1, v00, v01, v10, v11);
 }
 
 template <typename T, int V, int CH, bool UP>
@@ -275,7 +275,6 @@ struct CeBwdParams {
   const float* grad_px;    // per pixel or null
   const unsigned long long* stats;
   void* grad;
-  float* grad_accum;
   int label_dtype;
   int N, C, h, w, H, W;
   int align_corners;
@@ -295,9 +294,11 @@ __device__ __forceinline__ float ce_global_scale(const CeBwdParams& p) {
   return G;
 }
 
-template <typename T, int V, int CH, bool UP>
+// Label-resolution logits only. A resize-fused backward lives in loss_upgen.cuh (deterministic cell-owner sums); the
+// atomicAdd scatter this kernel once carried for other ratios (ATen's own non-deterministic design) is gone: shapes the
+// cell-owner kernel does not take are resized first (csrc/resize.cu, deterministic gather backward).
+template <typename T, int V, int CH>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
-  static_assert(!UP || V == 1, "resize-fused variant is one pixel per thread");
   // reverse launch order: the forward kernel read the batch front to back and its tail is still in the 126 MB L2
   const int n = gridDim.y - 1 - blockIdx.y;
   const int C = p.C;
@@ -335,53 +336,31 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
   }
 
   const T* img = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * hw;
-  if constexpr (UP) {
-    const Taps tp = make_taps((int)(px0 / p.W), (int)(px0 % p.W), p.h, p.w, p.sh, p.sw, p.align_corners != 0);
-    float* acc = p.grad_accum + (size_t)n * C * hw;
-    if (coef[0] == 0.f) return;
-    for (int c = 0; c < C; ++c) {
-      const float z = interp<T>(img + (size_t)c * hw, tp);
-      float g = coef[0] * ex2(fmaf(z, kLog2e, nl[0]));
-      if (c == yc[0]) g -= coef[0];
-      float* a = acc + (size_t)c * hw;
-      atomicAdd(a + tp.o00, tp.w00 * g);
-      atomicAdd(a + tp.o01, tp.w01 * g);
-      atomicAdd(a + tp.o10, tp.w10 * g);
-      atomicAdd(a + tp.o11, tp.w11 * g);
+  T* gq = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW + px0;
+  const T* q = img + px0;
+  for (int c0 = 0; c0 < C; c0 += CH) {
+    RawVec<T, V> raw[CH];
+    const int left = C - c0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (i < left) raw[i] = load_raw<T, V>(q);
+      q += HW;
     }
-  } else {
-    T* gq = reinterpret_cast<T*>(p.grad) + (size_t)n * C * HW + px0;
-    const T* q = img + px0;
-    for (int c0 = 0; c0 < C; c0 += CH) {
-      RawVec<T, V> raw[CH];
-      const int left = C - c0;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i < left) raw[i] = load_raw<T, V>(q);
-        q += HW;
-      }
+    for (int i = 0; i < CH; ++i) {
+      if (i < left) {
+        float g[V], zz[V];
+        unpack_raw<T, V>(raw[i], zz);
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        if (i < left) {
-          float g[V], zz[V];
-          unpack_raw<T, V>(raw[i], zz);
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            g[v] = coef[v] * ex2(fmaf(zz[v], kLog2e, nl[v]));
-            if (c0 + i == yc[v]) g[v] -= coef[v];
-          }
-          store_vec<T, V>(gq, g);
+        for (int v = 0; v < V; ++v) {
+          g[v] = coef[v] * ex2(fmaf(zz[v], kLog2e, nl[v]));
+          if (c0 + i == yc[v]) g[v] -= coef[v];
         }
-        gq += HW;
+        store_vec<T, V>(gq, g);
       }
+      gq += HW;
     }
   }
-}
-
-template <typename T> __global__ void cast_accum_kernel(const float* __restrict__ a, T* __restrict__ o, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) o[i] = from_float<T>(a[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,27 +457,15 @@ template <typename T> static int launch_ce_fwd(const CeFwdParams& p, bool up, bo
   return check_launch("ce_fwd_kernel");
 }
 
-template <typename T> static int launch_ce_bwd(const CeBwdParams& p, bool up, bool vec, cudaStream_t st) {
+template <typename T> static int launch_ce_bwd(const CeBwdParams& p, bool vec, cudaStream_t st) {
   const long long HW = (long long)p.H * p.W;
   constexpr int VV = 16 / (int)sizeof(T);
-  if (up) {
-    const long long nel = (long long)p.N * p.C * p.h * p.w;
-    B200SEG_CUDA(cudaMemsetAsync(p.grad_accum, 0, (size_t)nel * sizeof(float), st));
-    dim3 grid((unsigned)((HW + 255) / 256), p.N);
-    ce_bwd_kernel<T, 1, 8, true><<<grid, 256, 0, st>>>(p);
-    count_launch();
-    if (int e = check_launch("ce_bwd_kernel<UP>")) return e;
-    const int blocks = (int)((nel + 255) / 256 < 4 * kSMs ? (nel + 255) / 256 : 4 * kSMs);
-    cast_accum_kernel<T><<<blocks, 256, 0, st>>>(p.grad_accum, reinterpret_cast<T*>(p.grad), nel);
-    count_launch();
-    return check_launch("cast_accum_kernel");
-  }
   if (vec) {
     dim3 grid((unsigned)((HW / VV + 255) / 256), p.N);
-    ce_bwd_kernel<T, VV, 8, false><<<grid, 256, 0, st>>>(p);
+    ce_bwd_kernel<T, VV, 8><<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid((unsigned)((HW + 255) / 256), p.N);
-    ce_bwd_kernel<T, 1, 8, false><<<grid, 256, 0, st>>>(p);
+    ce_bwd_kernel<T, 1, 8><<<grid, 256, 0, st>>>(p);
   }
   count_launch();
   return check_launch("ce_bwd_kernel");
@@ -539,7 +506,7 @@ int ce_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
   p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;
   p.lse = d->lse; p.grad_out = d->ce_grad_out; p.grad_px = d->ce_grad_px;
   p.stats = reinterpret_cast<const unsigned long long*>(d->stats);
-  p.grad = d->grad_logits; p.grad_accum = d->grad_accum;
+  p.grad = d->grad_logits;
   p.label_dtype = d->label_dtype;
   p.N = d->N; p.C = d->C; p.h = d->h; p.w = d->w; p.H = d->H; p.W = d->W;
   p.align_corners = d->align_corners; p.use_nvalid = d->ce_use_nvalid;
@@ -547,15 +514,16 @@ int ce_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
   p.sh = resize_scale(d->h, d->H, d->align_corners != 0);
   p.sw = resize_scale(d->w, d->W, d->align_corners != 0);
   const bool up = (d->h != d->H) || (d->w != d->W);
-  B200SEG_REQUIRE(!up || d->grad_accum, "loss_bwd: grad_accum scratch is required when (h,w) != (H,W)");
+  B200SEG_REQUIRE(!up, "loss_bwd: logits must be at label resolution — the resize-fused backward is b200seg_loss_fused_fwdbwd "
+                       "(H >= h, W >= w, C <= 32); resize other shapes first (b200seg_resize_bilinear_fwd / _bwd)");
   const long long HW = (long long)d->H * d->W;
   const int VV = 16 / logit_bytes(d->logit_dtype);
-  const bool vec = !up && (HW % VV == 0) && aligned16(d->logits) && aligned16(d->labels) && aligned16(d->lse) &&
+  const bool vec = (HW % VV == 0) && aligned16(d->logits) && aligned16(d->labels) && aligned16(d->lse) &&
                    aligned16(d->grad_logits) && (!p.pw || aligned16(p.pw)) && (!p.grad_px || aligned16(p.grad_px));
   switch (d->logit_dtype) {
-    case B200SEG_F32: return launch_ce_bwd<float>(p, up, vec, st);
-    case B200SEG_BF16: return launch_ce_bwd<__nv_bfloat16>(p, up, vec, st);
-    case B200SEG_F16: return launch_ce_bwd<__half>(p, up, vec, st);
+    case B200SEG_F32: return launch_ce_bwd<float>(p, vec, st);
+    case B200SEG_BF16: return launch_ce_bwd<__nv_bfloat16>(p, vec, st);
+    case B200SEG_F16: return launch_ce_bwd<__half>(p, vec, st);
   }
   set_error("unsupported logit dtype %d", d->logit_dtype);
   return 1;

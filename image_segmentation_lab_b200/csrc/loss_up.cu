@@ -14,6 +14,8 @@
 //   up_combine_kernel  (here)             adds the 4 cells around every low-resolution logit and applies the global scale
 //                                         (upstream gradient, loss_weight, 1/denominator) -> grad_logits
 //   scale_inplace_kernel (here)           late scaling of an already produced gradient (flat single-pass plan)
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200seg {
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(T* __restrict__ x, l
   for (; i < n; i += stride) x[i] = from_float<T>(to_float<T>(x[i]) * s);
 }
 
-static bool up_fast_ok(int C, int h, int w, int H, int W, int ac, int* S_out) {
+// the quad-per-cell kernel of round 1 (loss_upcell.cuh): integer power-of-two scale in [4,32], align_corners=False
+static bool up_pow2_ok(int C, int h, int w, int H, int W, int ac, int* S_out) {
   if (ac) return false;
   if (h <= 0 || w <= 0 || H % h || W % w) return false;
   const int S = H / h;
@@ -63,10 +66,21 @@ static bool up_fast_ok(int C, int h, int w, int H, int W, int ac, int* S_out) {
   *S_out = S;
   return true;
 }
+// the thread-per-cell kernel (loss_upgen.cuh): any up-sampling ratio, both align_corners settings, C <= 32
+static bool up_fast_ok(int C, int h, int w, int H, int W, int ac) {
+  (void)ac;
+  if (h <= 0 || w <= 0 || C < 1 || C > 32) return false;
+  if (H < h || W < w || (H == h && W == w)) return false;
+  return true;
+}
+// B200SEG_UPCELL_OLD=1 keeps the round-1 kernel where it applies (A/B measurements)
+static bool up_use_old(int C, int h, int w, int H, int W, int ac, int* S_out) {
+  const char* e = getenv("B200SEG_UPCELL_OLD");
+  return e && e[0] == '1' && up_pow2_ok(C, h, w, H, W, ac, S_out);
+}
 
 long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {
-  int S;
-  if (!up_fast_ok(C, h, w, H, W, ac, &S)) return 0;
+  if (!up_fast_ok(C, h, w, H, W, ac)) return 0;
   return (long long)N * C * (h + 1) * (w + 1) * 4 * (long long)sizeof(float);
 }
 
@@ -110,12 +124,18 @@ int scale_inplace_dispatch(void* x, int dtype, long long n, const float* g, cuda
 }
 
 template <typename T> int upcell_run(const b200seg_loss_desc* f, float* pb, int S, bool grad, cudaStream_t st);
+template <typename T> int upgen_run(const b200seg_loss_desc* f, float* pb, bool grad, cudaStream_t st);
 
-template <typename T> static int up_run(const b200seg_loss_fused_desc* d, int S, cudaStream_t st) {
+template <typename T> static int up_run(const b200seg_loss_fused_desc* d, cudaStream_t st) {
   const b200seg_loss_desc* f = &d->fwd;
   const bool grad = d->grad_logits != nullptr || d->defer_combine;
   B200SEG_REQUIRE(!grad || d->workspace != nullptr, "loss_fused: workspace is NULL");
-  if (int e = upcell_run<T>(f, reinterpret_cast<float*>(d->workspace), S, grad, st)) return e;
+  int S = 0;
+  if (up_use_old(f->C, f->h, f->w, f->H, f->W, f->align_corners, &S)) {
+    if (int e = upcell_run<T>(f, reinterpret_cast<float*>(d->workspace), S, grad, st)) return e;
+  } else {
+    if (int e = upgen_run<T>(f, reinterpret_cast<float*>(d->workspace), grad, st)) return e;
+  }
   if (!grad || d->defer_combine) return 0;
   return up_combine_dispatch(d->workspace, d->grad_logits, f->logit_dtype, f->N, f->C, f->h, f->w, d->grad_scale_host,
                              d->grad_out, d->use_nvalid, f->stats, st);
@@ -127,14 +147,13 @@ int up_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st) {
   const b200seg_loss_desc* f = &d->fwd;
   const bool up = (f->h != f->H) || (f->w != f->W);
   if (!up) return flat_fused_dispatch(d, st);
-  int S = 0;
-  B200SEG_REQUIRE(up_fast_ok(f->C, f->h, f->w, f->H, f->W, f->align_corners, &S),
-                  "loss_fused: resize-fused single pass needs align_corners=False, an integer power-of-two scale in "
-                  "[4,32] and C <= 32 (query b200seg_loss_fused_workspace_bytes() != 0 first)");
+  B200SEG_REQUIRE(up_fast_ok(f->C, f->h, f->w, f->H, f->W, f->align_corners),
+                  "loss_fused: the resize-fused single pass needs H >= h, W >= w and C <= 32 "
+                  "(query b200seg_loss_fused_workspace_bytes() != 0 first)");
   switch (f->logit_dtype) {
-    case B200SEG_F32: return up_run<float>(d, S, st);
-    case B200SEG_BF16: return up_run<__nv_bfloat16>(d, S, st);
-    case B200SEG_F16: return up_run<__half>(d, S, st);
+    case B200SEG_F32: return up_run<float>(d, st);
+    case B200SEG_BF16: return up_run<__nv_bfloat16>(d, st);
+    case B200SEG_F16: return up_run<__half>(d, st);
   }
   set_error("loss_fused: unsupported logit dtype %d", f->logit_dtype);
   return 1;

@@ -1,6 +1,7 @@
 // Stand-alone resize kernels (reference utils/ops.py:7-26 -> F.interpolate), sm_100a.
 //
-// Forward: one thread per V consecutive output pixels of one (n,c) plane; the four taps come
+// Forward: bit-identical to ATen's upsample_bilinear2d (contraction pinned, see common.cuh). One thread per V
+// consecutive output pixels of one (n,c) plane; the four taps come
 // through the read-only path (each input element is re-read by ~scale^2 neighbours, all L1 hits),
 // the output is written once with 128-bit streaming stores. HBM-bound on the output write.
 // Backward: deterministic GATHER form of the transpose — one thread per input element sums the
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_fwd_kernel(const T* __res
     int y0, y1;
     float ly;
     resize_src(sh, Y, h, ac != 0, y0, y1, ly);
-    const float h1 = ly, h0 = 1.f - ly;
+    const float h1 = ly, h0 = __fsub_rn(1.f, ly);
     const T* r0 = in + ((size_t)nc * h + y0) * w;
     const T* r1 = in + ((size_t)nc * h + y1) * w;
     float o[V];
@@ -34,9 +35,9 @@ __global__ void __launch_bounds__(256) resize_bilinear_fwd_kernel(const T* __res
       int x0, x1;
       float lx;
       resize_src(sw, xv * V + v, w, ac != 0, x0, x1, lx);
-      const float w1 = lx, w0 = 1.f - lx;
-      o[v] = h0 * (w0 * to_float<T>(r0[x0]) + w1 * to_float<T>(r0[x1])) +
-             h1 * (w0 * to_float<T>(r1[x0]) + w1 * to_float<T>(r1[x1]));
+      const float w1 = lx, w0 = __fsub_rn(1.f, lx);
+      // ATen's operations, contraction pinned (common.cuh): bit-identical to F.interpolate
+      o[v] = aten_bilerp(h0, h1, w0, w1, to_float<T>(r0[x0]), to_float<T>(r0[x1]), to_float<T>(r1[x0]), to_float<T>(r1[x1]));
     }
     store_vec<T, V>(out + ((size_t)nc * H + Y) * W + (size_t)xv * V, o);
   }

@@ -8,6 +8,7 @@ logits and with one read of the logits per direction. ``B200DecodeHeadLossMixin`
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .losses._function import LossSpec, run_fused
 from .losses.accuracy import accuracy
 from .losses.cross_entropy_loss import CrossEntropyLoss, _match_dtype
@@ -62,9 +63,15 @@ def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False
             others.append(m)
 
     full = None
-    if up and (fused_dice is not None or others):
-        # dice needs per-class sums of the up-sampled soft-max: materialise once (csrc/resize.cu)
-        full = resize(seg_logit, size=(H, W), mode='bilinear', align_corners=align_corners, warning=False)
+    if up:
+        # The resize-fused single pass (csrc/loss_upgen.cuh) takes CE (+accuracy) for any up-sampling ratio with C <= 32.
+        # Everything else is resized once (csrc/resize.cu: deterministic gather backward — there is no atomicAdd path):
+        # dice needs per-class sums of the up-sampled soft-max, other modules expect label-resolution logits.
+        n, c, h, w = (int(v) for v in seg_logit.shape)
+        fast = (fused_dice is None and not others and fused_ce is not None and fused_ce.single_pass and seg_logit.is_cuda
+                and _lib.load().b200seg_loss_fused_workspace_bytes(n, c, h, w, H, W, int(bool(align_corners))) > 0)
+        if not fast:
+            full = resize(seg_logit, size=(H, W), mode='bilinear', align_corners=align_corners, warning=False)
     src = full if full is not None else seg_logit
 
     out = {}

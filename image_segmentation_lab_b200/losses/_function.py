@@ -5,12 +5,13 @@ It plays the role of the call chain in the reference's ``BaseDecodeHead.losses``
 and of the ATen autograd graph behind it. All arithmetic happens in libb200seg.so; this file only
 allocates buffers, fills descriptors and picks one of three execution plans:
 
-  * ``up_single``   logits at 1/S resolution, CE (+accuracy): forward+backward in one pass
-                    (b200seg_loss_fused_fwdbwd, combine deferred to backward()).
+  * ``up_single``   logits at lower resolution than the labels (any up-sampling ratio, both align_corners settings,
+                    C <= 32), CE (+accuracy): forward+backward in one pass (b200seg_loss_fused_fwdbwd, combine
+                    deferred to backward()).
   * ``flat_single`` logits at label resolution, CE (+accuracy), gradient needed: one pass.
-  * ``two_pass``    everything else (Dice, reduction='none', avg_non_ignore at label resolution,
-                    general resize ratios): b200seg_loss_fwd saves the per-pixel log-sum-exp,
-                    b200seg_loss_bwd re-reads the logits once.
+  * ``two_pass``    everything else at label resolution (Dice, reduction='none', avg_non_ignore): b200seg_loss_fwd saves
+                    the per-pixel log-sum-exp, b200seg_loss_bwd re-reads the logits once (CE + Dice with 32 < C <= 152:
+                    the class-sliced TMA pipeline of csrc/loss_cs.cu, one read of the logits per direction).
 """
 import ctypes as C
 from dataclasses import dataclass
@@ -167,6 +168,11 @@ class FusedLossFunction(torch.autograd.Function):
                         logits_c.data_ptr(), labels.data_ptr(), fd.logit_dtype, fd.label_dtype, Cc, H * W, int(pw is not None)):
                     plan = "flat_single"   # bulk-copy pipeline (any C whose tile fits shared memory) or register tile (C <= 32)
 
+            if up and plan == "two_pass" and needs_grad:
+                # no scatter backward: shapes the resize-fused single pass does not take (C > 32, down-sampling, single_pass
+                # off, reduction='none') are resized first — ops.resize has a deterministic gather backward
+                raise RuntimeError("a gradient through low-resolution logits needs the resize-fused single pass (H >= h, W >= w, "
+                                   "C <= 32, CE with 'mean' / 'sum' reduction); resize first (fused_resize_losses does)")
             loss_px = lse = grad = pb = None
             if plan == "two_pass":
                 if ce_none:
@@ -319,10 +325,6 @@ class FusedLossFunction(torch.autograd.Function):
                 bd.dice_grad_out = gd.data_ptr()
                 bd.dice_coef = coef_p
             bd.grad_logits = out.data_ptr()
-            if (h, w) != (H, W):
-                acc = torch.empty(logits.shape, dtype=torch.float32, device=dev)
-                keep.append(acc)
-                bd.grad_accum = acc.data_ptr()
             if want_dice and (Cc > 32 or tversky):
                 dot = torch.empty((N, H, W), dtype=torch.float32, device=dev)
                 keep.append(dot)

@@ -169,11 +169,12 @@ typedef struct b200seg_loss_bwd_desc {
   const float* dice_coef;           /* (N,C,2) from finalize                                   */
   const float* dice_grad_out;       /* scalar f32 (device) or NULL                             */
   void*   grad_logits;              /* (N,C,h,w) logit_dtype, fully overwritten                */
-  float*  grad_accum;               /* (N,C,h,w) f32 scratch: required when (h,w)!=(H,W)       */
+  float*  reserved_scratch;         /* unused (was the atomicAdd accumulator of the removed scatter backward) */
   float*  scratch_px;               /* (N,H,W) f32 scratch: required for dice with C > 32      */
 } b200seg_loss_bwd_desc;
 
-/* Fused backward: d(loss)/d(logits) in one pass (softmax Jacobian, dice, resize transpose). */
+/* Backward at label resolution ((h,w) == (H,W)): d(loss)/d(logits) in one pass (softmax Jacobian, dice). The resize-fused
+ * backward is b200seg_loss_fused_fwdbwd + _combine; there is no atomicAdd scatter path. */
 int b200seg_loss_bwd(const b200seg_loss_bwd_desc* d, void* stream);
 
 /* 1 if b200seg_loss_fused_fwdbwd can run a label-resolution problem (h == H, w == W) in a single pass: C <= 32 (register

@@ -96,8 +96,10 @@ def test_validation_errors_without_gpu():
     assert lib.b200seg_lovasz_fwd(ctypes.byref(lv), None) != 0
     assert 'avg_factor can not be used' in _lib.last_error()
     assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 0) == 8 * 19 * 65 * 129 * 16
-    assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 1) == 0   # align_corners -> general path
-    assert lib.b200seg_loss_fused_workspace_bytes(8, 150, 64, 64, 512, 512, 0) == 0    # C > 32 -> composite path
+    assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 1) == 8 * 19 * 65 * 129 * 16   # any align_corners
+    assert lib.b200seg_loss_fused_workspace_bytes(2, 19, 65, 129, 513, 1025, 1) == 2 * 19 * 66 * 130 * 16   # any up-sampling ratio
+    assert lib.b200seg_loss_fused_workspace_bytes(8, 150, 64, 64, 512, 512, 0) == 0    # C > 32 -> two-pass path
+    assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 32, 1024, 0) == 0    # down-sampling -> two-pass path
 
 
 def test_sass_is_sm100a():

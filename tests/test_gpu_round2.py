@@ -37,8 +37,10 @@ def test_fp16_gradscaler_gradient_keeps_its_bits(B):
         x = synth_logits(shape, 11, device='cuda').half()
         y = synth_labels((shape[0],) + shape[2:], C, 11, device='cuda', block=8)
         xa = x.clone().requires_grad_(True)
-        la = B.CrossEntropyLoss()(xa, y, ignore_index=255)
-        (la.float() * 65536.0).backward()
+        with torch.autocast('cuda', dtype=torch.float16):   # the loss comes back in float32, as ATen's autocast policy does
+            la = B.CrossEntropyLoss()(xa, y, ignore_index=255)
+        assert la.dtype == torch.float32
+        (la * 65536.0).backward()
         xb = x.float().requires_grad_(True)
         lb = O.cross_entropy_loss_module(xb, y, ignore_index=255)
         (lb * 65536.0).backward()
@@ -211,3 +213,84 @@ def test_class_sliced_pipeline_matches_oracle_and_streaming_kernels(B, dtype):
     b = _ce_dice(B, x, y, {}, {})
     assert rel_err(r['loss_ce'], a[0]) <= 1e-6
     assert torch.equal(a[3], b[3]) or rel_err(a[3].float(), b[3].float()) <= 1e-6   # dice sums are fp64 atomics
+
+
+# ------------------------------------------------------------------------------------------------ thread-per-cell resize-fused CE
+def _up_case(B, shape, size, C, ac, dtype=torch.float32, ce_kw=None, pixel_weight=False, ldt=torch.int64, seed=3, scale=1.0):
+    n = shape[0]
+    x = (synth_logits(shape, seed, dtype=torch.float32, device='cuda') * scale).to(dtype)
+    y = synth_labels((n,) + tuple(size), C, seed, device='cuda', block=5).to(ldt)
+    pw = (torch.rand((n,) + tuple(size), device='cuda') + 0.5) if pixel_weight else None
+    ce_kw = ce_kw or {}
+    xa = x.clone().requires_grad_(True)
+    r = B.fused_resize_losses(xa, y.unsqueeze(1), B.CrossEntropyLoss(**ce_kw), align_corners=ac, ignore_index=255, seg_weight=pw)
+    r['loss_ce'].backward()
+    xo = x.float().requires_grad_(True)
+    full = O.resize(xo, size=size, mode='bilinear', align_corners=ac)
+    kw = dict(ce_kw)
+    lo = O.cross_entropy_loss_module(full, y.long(), weight=pw, ignore_index=255, **kw)
+    lo.backward()
+    acc = O.accuracy(full.detach(), y.long(), ignore_index=255)
+    return (r['loss_ce'].detach(), xa.grad, r['acc_seg']), (lo.detach(), xo.grad, acc)
+
+
+@pytest.mark.parametrize('ac', [False, True])
+def test_resize_fused_any_ratio_single_pass(B, ac):
+    """csrc/loss_upgen.cuh: the resize-fused single pass for ANY up-sampling ratio and both align_corners settings
+    (utils/ops.py:7-26 with align_corners=self.align_corners, decode_head.py:266-269): odd ratios, different ratios per
+    axis, one axis at label resolution, tiny extents, every class count up to 32, weights, label dtypes, 16-bit logits."""
+    from image_segmentation_lab_b200 import _lib
+    lib = _lib.load()
+    cases = [((2, 19, 65, 129), (513, 1025), 19, {}, False, torch.int64, torch.float32),
+             ((2, 19, 64, 128), (512, 1024), 19, {}, False, torch.int64, torch.float32),
+             ((1, 7, 10, 13), (37, 91), 7, dict(class_weight=[0.5 + 0.1 * i for i in range(7)]), True, torch.uint8, torch.float32),
+             ((2, 32, 9, 11), (20, 50), 32, dict(avg_non_ignore=True), False, torch.int32, torch.float32),   # ratio ~2.2 / 4.5
+             ((2, 5, 16, 12), (16, 96), 5, dict(reduction='sum'), False, torch.int64, torch.float32),        # H == h
+             ((1, 3, 1, 1), (9, 7), 3, {}, False, torch.int64, torch.float32),
+             ((2, 21, 17, 23), (130, 180), 21, {}, True, torch.float32, torch.float32),
+             ((2, 19, 33, 65), (257, 513), 19, {}, False, torch.int64, torch.bfloat16),
+             ((2, 19, 16, 32), (256, 512), 19, {}, False, torch.int64, torch.float16)]
+    for shape, size, C, kw, pwt, ldt, dtype in cases:
+        n, c, h, w = shape
+        assert lib.b200seg_loss_fused_workspace_bytes(n, c, h, w, size[0], size[1], int(ac)) > 0
+        got, ref = _up_case(B, shape, size, C, ac, dtype=dtype, ce_kw=kw, pixel_weight=pwt, ldt=ldt)
+        tl, tg = (LOSS_TOL, GRAD_TOL) if dtype == torch.float32 else (HALF_TOL, 2 * HALF_TOL)
+        name = '%s->%s ac=%s %s' % (shape, size, ac, dtype)
+        assert rel_err(got[0], ref[0]) <= tl, (name, rel_err(got[0], ref[0]))
+        assert rel_err(got[1], ref[1]) <= tg, (name, rel_err(got[1], ref[1]))
+        # exact ties between interpolated classes count as correct for the label here, torch.topk picks by its own rule:
+        # allow two pixels on the small shapes
+        npx = n * size[0] * size[1]
+        assert abs(float(got[2]) - float(ref[2])) <= (max(0.02, 200.0 / npx) if dtype == torch.float32 else 0.5), name
+    # steep logits: classes hundreds of nats below the cell maximum -> the direct-evaluation fallback
+    for sc in (20.0, 90.0):
+        got, ref = _up_case(B, (2, 19, 9, 13), (70, 100), 19, ac, scale=sc)
+        assert rel_err(got[0], ref[0]) <= 2e-5 and rel_err(got[1], ref[1]) <= GRAD_TOL, sc
+
+
+def test_resize_fused_general_is_deterministic_and_matches_round1_kernel(B):
+    """No atomics anywhere in the resize-fused backward: bitwise identical gradients run to run for align_corners=True and
+    odd ratios; at power-of-two ratios the thread-per-cell kernel agrees with the round-1 quad-per-cell kernel."""
+    for shape, size, ac in (((3, 19, 33, 65), (257, 513), True), ((2, 19, 30, 40), (97, 131), False)):
+        x = synth_logits(shape, 8, device='cuda')
+        y = synth_labels((shape[0],) + size, 19, 8, device='cuda').unsqueeze(1)
+        grads = []
+        for _ in range(3):
+            xa = x.clone().requires_grad_(True)
+            B.fused_resize_losses(xa, y, B.CrossEntropyLoss(), align_corners=ac, ignore_index=255)['loss_ce'].backward()
+            grads.append(xa.grad.clone())
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    x = synth_logits((4, 19, 32, 64), 8, device='cuda')
+    y = synth_labels((4, 256, 512), 19, 8, device='cuda').unsqueeze(1)
+    res = []
+    for old in ('0', '1'):
+        os.environ['B200SEG_UPCELL_OLD'] = old
+        try:
+            xa = x.clone().requires_grad_(True)
+            r = B.fused_resize_losses(xa, y, B.CrossEntropyLoss(), ignore_index=255)
+            r['loss_ce'].backward()
+            res.append((r['loss_ce'].detach().clone(), xa.grad.clone(), r['acc_seg'].clone()))
+        finally:
+            del os.environ['B200SEG_UPCELL_OLD']
+    assert rel_err(res[0][0], res[1][0]) <= 2e-6 and rel_err(res[0][1], res[1][1]) <= 1e-5
+    assert abs(float(res[0][2]) - float(res[1][2])) <= 1e-3

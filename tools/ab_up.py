@@ -68,3 +68,4 @@ if __name__ == '__main__':
     run(8, 19, 32, 64, 16)
     run(8, 8, 64, 128, 8)
     run(8, 32, 64, 128, 8)
+    run(8, 19, 64, 128, 8, dtype=torch.float16)
