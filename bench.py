@@ -474,7 +474,10 @@ def flatten_workloads(line, extras):
     put('c4_fwd_bwd_ms', extras, 'C4_voc_fp32_ce', 'fwd_bwd', 'ms')
     put('c4_fwd_bwd_frac', extras, 'C4_voc_fp32_ce', 'fwd_bwd', 'roofline', 'frac')
     put('c4_fwd_frac', extras, 'C4_voc_fp32_ce', 'fwd', 'roofline', 'frac')
+    put('c2_ac_false_eager_ms', extras, 'C2_align_corners_false_eager', 'fwd_bwd', 'ms')
     put('c2_ac_true_ms', extras, 'C2_align_corners_true', 'fwd_bwd', 'ms')
+    put('c2_c150_ns_per_px_class', extras, 'C2_like_c150_64to512', 'fwd_bwd', 'ns_per_px_class')
+    put('c2_ac_true_ns_per_px_class', extras, 'C2_align_corners_true', 'fwd_bwd', 'ns_per_px_class')
     put('c2_c150_general_ms', extras, 'C2_like_c150_64to512', 'fwd_bwd', 'ms')
     put('c5i_ms', extras, 'C5i_miou_label_maps', 'ms')
     put('c5i_frac', extras, 'C5i_miou_label_maps', 'roofline', 'frac')
@@ -685,7 +688,7 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     cw = torch.linspace(0.5, 1.5, 150).tolist()
     bench_losses('C3_ade20k_bf16_ce_dice', (16, 150, 512, 512), torch.bfloat16,
                  [B.CrossEntropyLoss(class_weight=cw), B.DiceLoss(loss_weight=3.0)], iters=10,
-                 plan='ce_fwd_kernel(+one-hot dice sums) + dice_sumsq_kernel + finalize; dice_dot_kernel + dice_grad_kernel')
+                 plan='cs_fwd_kernel + finalize; cs_bwd_kernel (class-sliced tensor-map TMA pipeline: one read of the logits per direction)')
     bench_losses('C4_voc_fp32_ce', (32, 21, 512, 512), torch.float32, B.CrossEntropyLoss(), iters=20, single=True,
                  plan='ce_bulk_kernel (cp.async.bulk load warp / consumers / store warp): forward+backward in one pass')
     bench_losses('C3_ade20k_bf16_ce_only', (16, 150, 512, 512), torch.bfloat16, B.CrossEntropyLoss(class_weight=cw), iters=10,
@@ -694,6 +697,39 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     ce2.single_pass = False
     bench_losses('C4_voc_fp32_ce_two_pass', (32, 21, 512, 512), torch.float32, ce2, iters=10,
                  plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
+
+    # ---- resize-fused CE beyond the headline shape: align_corners=True (thread-per-cell kernel, csrc/loss_upgen.cuh) and
+    # 150 classes at 1/8 resolution (C > 32: resized once by csrc/resize.cu, then the label-resolution kernels; both
+    # deterministic — there is no atomicAdd backward)
+    def bench_up(name, shape, size, ac, iters=20, plan=''):
+        n, c, hh, ww = shape
+        xs = [make_logits(shape, 700 + i, device=dev).requires_grad_(True) for i in range(2)]
+        ys = [make_labels((n,) + size, c, 700 + i, 255, device=dev).unsqueeze(1) for i in range(2)]
+        ce = B.CrossEntropyLoss()
+
+        def fb(i):
+            x = xs[i & 1]
+            x.grad = None
+            B.fused_resize_losses(x, ys[i & 1], ce, align_corners=ac, ignore_index=255)['loss_ce'].backward()
+
+        for i in range(3):
+            fb(i)
+        ms = timed_events(fb, iters)
+        px = n * size[0] * size[1]
+        out[name] = {'logits': list(shape), 'label_hw': list(size), 'align_corners': ac, 'pixels': px,
+                     'fwd_bwd': dict(ms=ms, mpix_s=px / ms / 1e3, ns_per_px_class=ms * 1e6 / (px * c), plan=plan)}
+        del xs, ys
+        torch.cuda.empty_cache()
+
+    try:
+        bench_up('C2_align_corners_false_eager', (8, 19, 64, 128), (512, 1024), False,
+                 plan='headline shape through eager launches (no CUDA graph), for comparison with the two lines below')
+        bench_up('C2_align_corners_true', (8, 19, 64, 128), (512, 1024), True,
+                 plan='up_gen_kernel (thread per cell, any ratio) + up_combine + finalize')
+        bench_up('C2_like_c150_64to512', (8, 150, 64, 64), (512, 512), False, iters=10,
+                 plan='resize_bilinear_fwd -> ce_fwd + ce_bwd at label resolution -> resize_bilinear_bwd (deterministic gather)')
+    except Exception as e:
+        out['C2_align_corners_true'] = {'error': repr(e)}
 
     # ---- "next" row f4': LovaszLoss at the config-2 label resolution (19 class segments of 4 M pixels each)
     try:
@@ -758,7 +794,31 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     out['C5ii_miou_from_logits'] = {'images': n_l, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
                                     'roofline': roof(px * (Cn * 4 + 4), ms), 'algorithmic_bytes': px * (Cn * 4 + 4),
                                     'note': 'all 500 images (79.7 GB of fp32 logits), fused arg-max + areas, one launch'}
-    del logits, lbase, gl, gt_all
+    del logits, lbase
+    torch.cuda.empty_cache()
+
+    # ---- "next" row f2: the validation rescale fused into the arg-max — logits at 1/8 resolution (1,19,128,256) against
+    # 1024x2048 ground truth, 500 images, one launch; the (1,19,1024,2048) rescaled logits are never written
+    try:
+        lo = [make_logits((1, Cn, 128, 256), 950 + i, device=dev) for i in range(8)]
+        lows = [lo[i % 8].clone() for i in range(n_l)]
+        tabr = B.prepare_images(lows, gl, Cn, from_logits=True)
+
+        def sweep3(i):
+            B.area_totals_device(tabr, None, Cn, 255)
+
+        sweep3(0)
+        ms = timed_events(sweep3, 3)
+        px = n_l * 1024 * 2048
+        algo = px * 4 + n_l * Cn * 128 * 256 * 4
+        out['C5_resized_lowres_logits'] = {'images': n_l, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
+                                           'roofline': roof(algo, ms), 'algorithmic_bytes': algo,
+                                           'note': 'fused bilinear rescale (ATen arithmetic, bit-exact) + arg-max + areas from 1/8-resolution '
+                                                   'logits; issue bound (19 interpolations per output pixel), not HBM bound'}
+        del lows, lo, tabr
+    except Exception as e:
+        out['C5_resized_lowres_logits'] = {'error': repr(e)}
+    del gl, gt_all
     torch.cuda.empty_cache()
     return out
 

@@ -144,9 +144,10 @@ SYMBOLS = [
     ("b200seg_loss_fused_fwdbwd", C.c_int, [C.POINTER(LossFusedDesc), _p]),
     ("b200seg_loss_fused_combine", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _f, _p, _i32, _p, _p]),
     ("b200seg_scale_inplace", C.c_int, [_p, _i32, _i64, _p, _p]),
-    ("b200seg_resize_bilinear_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
-    ("b200seg_resize_bilinear_bwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
-    ("b200seg_resize_nearest_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    ("b200seg_resize_bilinear_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _f, _p]),
+    ("b200seg_resize_bilinear_bwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _f, _p]),
+    ("b200seg_resize_nearest_fwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _f, _f, _p]),
+    ("b200seg_resize_nearest_bwd", C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _f, _f, _p]),
     ("b200seg_confusion_labels", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _i32, _p]),
     ("b200seg_confusion_logits", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p, _i32, _p]),
     ("b200seg_confusion_logits_resized", C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p, _i32, _p]),

@@ -38,6 +38,8 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
 }
 
 __device__ __forceinline__ long long smem_label(const unsigned char* row, int dt, int t) {
+  if (dt == B200SEG_L_I64) return reinterpret_cast<const long long*>(row)[t];   // the two common cases first: one compare
+  if (dt == B200SEG_L_U8) return (long long)row[t];
   switch (dt) {
     case B200SEG_L_U8: return (long long)row[t];
     case B200SEG_L_I16: return (long long)reinterpret_cast<const short*>(row)[t];

@@ -52,6 +52,12 @@ constexpr int kCsWarpPx = 16;     // pixels per consumer warp per tile (4 groups
 constexpr int kCsGroupWarps = 8;  // consumer warps per tile (a "group"); a CTA runs G groups on alternating tiles
 constexpr int kCsMaxStages = 6;
 constexpr int kCsBoxBytes = 128;   // inner extent of a TMA box = one swizzle row
+constexpr int kCsBig = (int)0x80000000;     // a label that does not fit int32: never a class, never ignored
+constexpr int kCsNever = (int)0x80000001;   // an ignore value no decoded label can take
+__device__ __forceinline__ int cs_label32(const unsigned char* row, int dt, int t) {
+  const long long v = smem_label(row, dt, t);
+  return (v == (long long)(int)v && (int)v != kCsNever) ? (int)v : kCsBig;
+}
 
 struct CsParams {
   const void* logits;
@@ -72,9 +78,9 @@ struct CsParams {
   long long total_tiles, tiles_per_cta;
   int stages, stage_bytes, block_bytes, label_off, lse_off;   // block = one TMA box in shared memory: CP rows x 128 bytes
   int flags;
-  long long ignore_index, dice_ignore;
+  int ignore32, dice_ignore32;       // ignore values squashed to int32 (kCsNever when they do not fit: never matches)
   int acc_has_ignore;
-  long long acc_ignore;
+  int acc_ignore32;
   float ce_scale_host;
   int ce_use_nvalid;
 };
@@ -147,13 +153,31 @@ struct CsTile {
   int n, npx;
   long long px0;
 };
-__device__ __forceinline__ CsTile cs_tile(const CsParams& p, long long t, int TP) {
-  CsTile r;
-  r.n = (int)(t / p.tiles_per_image);
-  r.px0 = (t - (long long)r.n * p.tiles_per_image) * TP;
-  r.npx = (int)((p.HW - r.px0 < TP) ? p.HW - r.px0 : TP);
-  return r;
-}
+// Walks a CTA's tile range forward (or backward) in steps of `step` tiles without a division per tile.
+struct CsWalker {
+  int n, tin, tpi, step, TP;
+  long long HW;
+  __device__ __forceinline__ void init(const CsParams& p, long long t_first, int step_, int TP_) {
+    tpi = p.tiles_per_image; step = step_; TP = TP_; HW = p.HW;
+    n = (int)(t_first / tpi);
+    tin = (int)(t_first - (long long)n * tpi);
+  }
+  __device__ __forceinline__ CsTile tile() const {
+    CsTile r;
+    r.n = n;
+    r.px0 = (long long)tin * TP;
+    r.npx = (int)((HW - r.px0 < TP) ? HW - r.px0 : TP);
+    return r;
+  }
+  __device__ __forceinline__ void forward() {
+    tin += step;
+    while (tin >= tpi) { tin -= tpi; ++n; }
+  }
+  __device__ __forceinline__ void backward() {
+    tin -= step;
+    while (tin < 0) { tin += tpi; --n; }
+  }
+};
 
 // Shared-memory address of (class row, pixel) inside a stage: box = pixel's 128-byte column block, 128B swizzle inside.
 template <typename T> __device__ __forceinline__ unsigned cs_offset(const CsParams& p, int row, int px) {
@@ -182,13 +206,14 @@ __device__ __forceinline__ void cs_producer(const CsParams& p, const CUtensorMap
                                             long long t1, int TP, int lane) {
   constexpr int BOXPX = CsCfg<T>::kBoxPx;
   const int C = p.C, NS = p.stages;
-  int k = 0;
-  for (long long tt = t0; tt < t1; ++tt, ++k) {
-    const long long t = REVERSE ? (t1 - 1 - (tt - t0)) : tt;
+  CsWalker wk;
+  wk.init(p, REVERSE ? t1 - 1 : t0, 1, TP);
+  const int nt = (int)(t1 - t0);
+  for (int k = 0; k < nt; ++k) {
     const int s = k % NS;
     if (k >= NS) mbar_wait(&empty_bar[s], ((k / NS) - 1) & 1);
     if (lane == 0) {
-      const CsTile tl = cs_tile(p, t, TP);
+      const CsTile tl = wk.tile();
       const int nbox = (tl.npx + BOXPX - 1) / BOXPX;           // boxes that start inside the image (a partial one is zero-filled)
       const unsigned lab_bytes = (unsigned)(tl.npx * p.label_bytes);
       const unsigned lse_bytes = WITH_LSE ? (unsigned)(tl.npx * 4) : 0u;
@@ -201,6 +226,7 @@ __device__ __forceinline__ void cs_producer(const CsParams& p, const CUtensorMap
       if (WITH_LSE)
         bulk_g2s(stage + p.lse_off, reinterpret_cast<const char*>(p.lse + (size_t)tl.n * p.HW + tl.px0), lse_bytes, &full_bar[s]);
     }
+    if (REVERSE) wk.backward(); else wk.forward();
     __syncwarp();
   }
 }
@@ -280,10 +306,11 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
       }
     };
 
-    for (int k = grp; k < (int)(t1 - t0); k += G) {     // group grp consumes tiles grp, grp + G, ... of the CTA's range
-      const long long t = t0 + k;
+    CsWalker wk;
+    wk.init(p, t0 + grp, G, TP);
+    for (int k = grp; k < (int)(t1 - t0); k += G, wk.forward()) {   // group grp consumes tiles grp, grp + G, ... of the CTA's range
       const int s = k % NS;
-      const CsTile tl = cs_tile(p, t, TP);
+      const CsTile tl = wk.tile();
       if (tl.n != n_cur) {
         if (n_cur >= 0) flush_image(n_cur);
         n_cur = tl.n;
@@ -359,13 +386,13 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
       if (j < 4 && t_px < tl.npx) {
         const float m_own = pick4(m, j), S_own = pick4(S, j);
         const float lse = m_own + fast_log(S_own);
-        const long long yy = smem_label(stage + p.label_off, p.label_dtype, t_px);
-        const bool ign = (yy == p.ignore_index);
-        const bool inr = (yy >= 0 && yy < (long long)C);
+        const int yy = cs_label32(stage + p.label_off, p.label_dtype, t_px);
+        const bool ign = (yy == p.ignore32);
+        const bool inr = (unsigned)yy < (unsigned)C;
         const bool valid = !ign && inr;
         n_bad += (!ign && !inr);
         n_valid += !ign;
-        const int ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);
+        const int ycc = yy < 0 ? 0 : (yy >= C ? C - 1 : yy);
         const float zy = to_float<T>(*reinterpret_cast<const T*>(stage + cs_offset<T>(p, ycc, t_px)));
         const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
         if (valid && (p.flags & B200SEG_WANT_CE)) {
@@ -373,11 +400,11 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
           const float pwv = p.pw ? __ldg(p.pw + gpx) : 1.f;
           loss_acc = fmaf(wt * pwv, lse - zy, loss_acc);
         }
-        const bool av = p.acc_has_ignore ? (yy != p.acc_ignore) : true;
+        const bool av = p.acc_has_ignore ? (yy != p.acc_ignore32) : true;
         n_acc += av;
         n_correct += (av && inr && zy == m_own);
         if (dice) {
-          const bool dv = (yy != p.dice_ignore);                       // valid_mask
+          const bool dv = (yy != p.dice_ignore32);                     // valid_mask
           cls = ycc;                                                   // one-hot of the CLAMPED label (dice_loss.py:119-122)
           pyv = dv ? ex2((zy - lse) * kLog2e) : 0.f;
         }
@@ -430,13 +457,14 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
     // store warp: lane 0 hands the boxes of a finished tile to the TMA store engine; the stage goes back to the producer
     // as soon as the engine has READ it
     constexpr int BOXPX = CsCfg<T>::kBoxPx;
-    int k = 0;
-    for (long long tt = t0; tt < t1; ++tt, ++k) {
-      const long long t = t1 - 1 - (tt - t0);
+    CsWalker wk;
+    wk.init(p, t1 - 1, 1, TP);
+    const int nt = (int)(t1 - t0);
+    for (int k = 0; k < nt; ++k, wk.backward()) {
       const int s = k % NS;
       mbar_wait(&done_bar[s], (k / NS) & 1);
       if (lane == 0) {
-        const CsTile tl = cs_tile(p, t, TP);
+        const CsTile tl = wk.tile();
         const int nbox = (tl.npx + BOXPX - 1) / BOXPX;
         unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
         for (int bx = 0; bx < nbox; ++bx)
@@ -466,10 +494,11 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
     }
     float b[CPT];
     int n_cur = -1;
-    for (int k = grp; k < (int)(t1 - t0); k += G) {
-      const long long t = t1 - 1 - k;
+    CsWalker wk;
+    wk.init(p, t1 - 1 - grp, G, TP);
+    for (int k = grp; k < (int)(t1 - t0); k += G, wk.backward()) {
       const int s = k % NS;
-      const CsTile tl = cs_tile(p, t, TP);
+      const CsTile tl = wk.tile();
       if (tl.n != n_cur) {
         n_cur = tl.n;
 #pragma unroll
@@ -488,12 +517,12 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
       const int t_px = pxo + (j / PX) * 4 * PX + g * PX + (j % PX);
       const bool owner = (j < 4) && t_px < tl.npx;
       if (owner) {
-        const long long yy = smem_label(stage + p.label_off, p.label_dtype, t_px);
-        const bool valid = (yy != p.ignore_index) && yy >= 0 && yy < (long long)C;
-        ycc = yy < 0 ? 0 : (yy >= (long long)C ? C - 1 : (int)yy);
+        const int yy = cs_label32(stage + p.label_off, p.label_dtype, t_px);
+        const bool valid = (yy != p.ignore32) && (unsigned)yy < (unsigned)C;
+        ycc = yy < 0 ? 0 : (yy >= C ? C - 1 : yy);
         const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
         if (want_ce && valid) kk = Gce * (p.pw ? __ldg(p.pw + gpx) : 1.f) * (p.cw ? __ldg(p.cw + ycc) : 1.f);
-        if (yy != p.dice_ignore) da = god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 0);
+        if (yy != p.dice_ignore32) da = god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 0);
         by = 2.f * god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 1);
         const float lse_own = reinterpret_cast<const float*>(stage + p.lse_off)[t_px];
         const float zy = to_float<T>(*reinterpret_cast<const T*>(stage + cs_offset<T>(p, ycc, t_px)));
@@ -686,6 +715,8 @@ template <bool BWD> static int cs_dispatch(CsParams p, int logit_dtype, cudaStre
   return 1;
 }
 
+static int cs_fit32(long long v) { return (v >= -2147483647LL && v <= 2147483647LL) ? (int)v : kCsNever; }
+
 int cs_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   CsParams p = {};
   p.logits = d->logits; p.labels = d->labels; p.pw = d->pixel_weight; p.cw = d->ce_class_weight;
@@ -695,8 +726,8 @@ int cs_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
   p.label_dtype = d->label_dtype; p.label_bytes = label_bytes(d->label_dtype);
   p.N = d->N; p.C = d->C; p.HW = (long long)d->H * d->W;
   p.flags = d->flags;
-  p.ignore_index = d->ignore_index; p.dice_ignore = d->dice_ignore_index;
-  p.acc_has_ignore = d->acc_has_ignore; p.acc_ignore = d->acc_ignore_index;
+  p.ignore32 = cs_fit32(d->ignore_index); p.dice_ignore32 = cs_fit32(d->dice_ignore_index);
+  p.acc_has_ignore = d->acc_has_ignore; p.acc_ignore32 = cs_fit32(d->acc_ignore_index);
   return cs_dispatch<false>(p, d->logit_dtype, st);
 }
 
@@ -710,7 +741,7 @@ int cs_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
   p.label_dtype = d->label_dtype; p.label_bytes = label_bytes(d->label_dtype);
   p.N = d->N; p.C = d->C; p.HW = (long long)d->H * d->W;
   p.flags = d->flags;
-  p.ignore_index = d->ignore_index; p.dice_ignore = d->dice_ignore_index;
+  p.ignore32 = cs_fit32(d->ignore_index); p.dice_ignore32 = cs_fit32(d->dice_ignore_index);
   p.ce_scale_host = d->ce_scale_host; p.ce_use_nvalid = d->ce_use_nvalid;
   return cs_dispatch<true>(p, d->logit_dtype, st);
 }

@@ -73,10 +73,15 @@ static bool up_fast_ok(int C, int h, int w, int H, int W, int ac) {
   if (H < h || W < w || (H == h && W == w)) return false;
   return true;
 }
-// B200SEG_UPCELL_OLD=1 keeps the round-1 kernel where it applies (A/B measurements)
+// Which kernel: the quad-per-cell kernel measures faster at power-of-two scales up to 8 with align_corners=False (config 2:
+// 80 vs 89 us), the thread-per-cell kernel at 16 and 32 (68 vs 76 us) and is the only one for everything else.
+// B200SEG_UPCELL=old|gen forces one of them where both apply (A/B measurements).
 static bool up_use_old(int C, int h, int w, int H, int W, int ac, int* S_out) {
-  const char* e = getenv("B200SEG_UPCELL_OLD");
-  return e && e[0] == '1' && up_pow2_ok(C, h, w, H, W, ac, S_out);
+  if (!up_pow2_ok(C, h, w, H, W, ac, S_out)) return false;
+  const char* e = getenv("B200SEG_UPCELL");
+  if (e && e[0] == 'o') return true;
+  if (e && e[0] == 'g') return false;
+  return *S_out <= 8;
 }
 
 long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {

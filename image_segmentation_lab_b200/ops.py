@@ -1,7 +1,8 @@
 """``resize`` / ``Upsample`` / ``add_prefix`` with the reference's signatures (utils/ops.py:7-69).
 
 ``resize`` is a thin wrapper over F.interpolate in the reference; here bilinear and nearest run on
-csrc/resize.cu (forward, and a deterministic gather backward for bilinear). The decode-head hot call
+csrc/resize.cu (forward bit-identical to ATen's CUDA kernels, deterministic gather backwards, size= or
+scale_factor= including fractional factors). The decode-head hot call
 (decode_head.py:266-269) should not use this at all — ``fused_resize_losses`` never materialises the
 up-sampled logits — but validation rescaling and inference still need the real tensor.
 """
@@ -29,33 +30,56 @@ def _out_size(input, size, scale_factor):
             int(math.floor(float(input.shape[3]) * float(scale_factor[1]))))
 
 
-class _ResizeBilinear(torch.autograd.Function):
+def _kernel_scales(scale_factor):
+    """ATen's compute_scales_value: with scale_factor= (and recompute_scale_factor unset) the source-index scale is
+    (float)(1.0 / scale_factor) instead of in / out. 0 = derive from the sizes."""
+    if scale_factor is None:
+        return 0.0, 0.0
+    sf = scale_factor if isinstance(scale_factor, (tuple, list)) else (scale_factor, scale_factor)
+    return float(torch.tensor(1.0 / float(sf[0]), dtype=torch.float32)), float(torch.tensor(1.0 / float(sf[1]), dtype=torch.float32))
+
+
+class _Resize(torch.autograd.Function):
+    """F.interpolate(mode='bilinear' | 'nearest') on csrc/resize.cu: the bilinear forward is bit-identical to ATen's CUDA
+    kernel (FMA contraction pinned), both backwards are deterministic gathers (ATen scatters with atomicAdd)."""
+
     @staticmethod
-    def forward(ctx, x, H, W, align_corners):
+    def forward(ctx, x, H, W, mode, align_corners, scales):
         lib = _lib.load()
         x = x.contiguous()
         N, Cc, h, w = x.shape
         out = torch.empty((N, Cc, H, W), dtype=x.dtype, device=x.device)
+        sh, sw = scales
         with torch.cuda.device(x.device):
-            _lib.check(lib.b200seg_resize_bilinear_fwd(x.data_ptr(), out.data_ptr(), _lib.LOGIT_DTYPES[x.dtype], N * Cc,
-                                                       h, w, H, W, int(bool(align_corners)), _lib.stream_ptr(x.device)))
-        ctx.geom = (N, Cc, h, w, H, W, bool(align_corners))
+            if mode == 'bilinear':
+                _lib.check(lib.b200seg_resize_bilinear_fwd(x.data_ptr(), out.data_ptr(), _lib.LOGIT_DTYPES[x.dtype], N * Cc, h, w, H,
+                                                           W, int(bool(align_corners)), sh, sw, _lib.stream_ptr(x.device)))
+            else:
+                _lib.check(lib.b200seg_resize_nearest_fwd(x.data_ptr(), out.data_ptr(), _lib.LOGIT_DTYPES[x.dtype], N * Cc, h, w, H, W,
+                                                          sh, sw, _lib.stream_ptr(x.device)))
+        ctx.geom = (N, Cc, h, w, H, W, mode, bool(align_corners), sh, sw)
         return out
 
     @staticmethod
     def backward(ctx, go):
         lib = _lib.load()
-        N, Cc, h, w, H, W, ac = ctx.geom
+        N, Cc, h, w, H, W, mode, ac, sh, sw = ctx.geom
         go = go.contiguous()
         gi = torch.empty((N, Cc, h, w), dtype=go.dtype, device=go.device)
         with torch.cuda.device(go.device):
-            _lib.check(lib.b200seg_resize_bilinear_bwd(go.data_ptr(), gi.data_ptr(), _lib.LOGIT_DTYPES[go.dtype], N * Cc,
-                                                       h, w, H, W, int(ac), _lib.stream_ptr(go.device)))
-        return gi, None, None, None
+            if mode == 'bilinear':
+                _lib.check(lib.b200seg_resize_bilinear_bwd(go.data_ptr(), gi.data_ptr(), _lib.LOGIT_DTYPES[go.dtype], N * Cc, h, w, H,
+                                                           W, int(ac), sh, sw, _lib.stream_ptr(go.device)))
+            else:
+                _lib.check(lib.b200seg_resize_nearest_bwd(go.data_ptr(), gi.data_ptr(), _lib.LOGIT_DTYPES[go.dtype], N * Cc, h, w, H, W,
+                                                          sh, sw, _lib.stream_ptr(go.device)))
+        return gi, None, None, None, None, None
 
 
 def resize(input, size=None, scale_factor=None, mode='nearest', align_corners=None, warning=True):
-    """Same arguments, warning and result as the reference (utils/ops.py:7-26)."""
+    """Same arguments, warning and result as the reference (utils/ops.py:7-26) for mode 'bilinear' and 'nearest' (the
+    modes the segmentation path uses: decode_head.py:266-269,301-318, encoder_decoder.py:94-97,247-251); other modes of
+    F.interpolate (bicubic, area, ...) are not on that path and raise NotImplementedError."""
     if warning:
         if size is not None and align_corners:
             input_h, input_w = tuple(int(x) for x in input.shape[2:])
@@ -71,28 +95,13 @@ def resize(input, size=None, scale_factor=None, mode='nearest', align_corners=No
     if input.dtype not in _lib.LOGIT_DTYPES:
         raise TypeError('resize: float32, bfloat16 or float16 input expected, got %s' % input.dtype)
     H, W = _out_size(input, size, scale_factor)
-    if scale_factor is not None:
-        # With scale_factor F.interpolate uses 1/scale_factor (not in/out) as the source-index scale; the two
-        # agree only when in*scale_factor is integral, which is the only case taken here.
-        sf = scale_factor if isinstance(scale_factor, (tuple, list)) else (scale_factor, scale_factor)
-        if abs(input.shape[2] * float(sf[0]) - H) > 1e-6 or abs(input.shape[3] * float(sf[1]) - W) > 1e-6:
-            raise NotImplementedError('resize: pass size= (a scale_factor with a fractional output size changes '
-                                      'ATen\'s source-index scale)')
+    scales = _kernel_scales(scale_factor)
     if mode == 'bilinear':
-        return _ResizeBilinear.apply(input, H, W, bool(align_corners))
+        return _Resize.apply(input, H, W, 'bilinear', bool(align_corners), scales)
     if mode == 'nearest':
         if align_corners is not None:
             raise ValueError('align_corners option can only be set with the interpolating modes')
-        if input.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError('resize(mode="nearest") has no backward on this path')
-        lib = _lib.load()
-        x = input.contiguous()
-        N, Cc, h, w = x.shape
-        out = torch.empty((N, Cc, H, W), dtype=x.dtype, device=x.device)
-        with torch.cuda.device(x.device):
-            _lib.check(lib.b200seg_resize_nearest_fwd(x.data_ptr(), out.data_ptr(), _lib.LOGIT_DTYPES[x.dtype], N * Cc,
-                                                      h, w, H, W, _lib.stream_ptr(x.device)))
-        return out
+        return _Resize.apply(input, H, W, 'nearest', False, scales)
     raise NotImplementedError('resize: mode %r is not on the segmentation hot path (bilinear / nearest only)' % (mode,))
 
 

@@ -294,15 +294,21 @@ typedef struct b200seg_lovasz_bwd_desc {
 } b200seg_lovasz_bwd_desc;
 int b200seg_lovasz_bwd(const b200seg_lovasz_bwd_desc* d, void* stream);
 
-/* Bilinear resize, ATen semantics (torch/include/ATen/native/UpSample.h:271-312,442-476). */
+/* Bilinear resize, ATen semantics (torch/include/ATen/native/UpSample.h:271-312,442-476); the forward is bit-identical to
+ * F.interpolate on CUDA (FMA contraction pinned). scale_h / scale_w: > 0 = the source-index scale to use instead of in/out —
+ * F.interpolate(scale_factor=s) uses (float)(1.0 / s) (compute_scales_value); <= 0 = from the sizes. Ignored when
+ * align_corners != 0, as ATen does. */
 int b200seg_resize_bilinear_fwd(const void* in, void* out, int32_t dtype, int32_t NC, int32_t h, int32_t w,
-                                int32_t H, int32_t W, int32_t align_corners, void* stream);
+                                int32_t H, int32_t W, int32_t align_corners, float scale_h, float scale_w, void* stream);
 /* Deterministic transpose (gather form): grad_in (NC,h,w) <- grad_out (NC,H,W). */
 int b200seg_resize_bilinear_bwd(const void* grad_out, void* grad_in, int32_t dtype, int32_t NC, int32_t h,
-                                int32_t w, int32_t H, int32_t W, int32_t align_corners, void* stream);
-/* Nearest resize (F.interpolate default mode of utils/ops.py:7-26). */
+                                int32_t w, int32_t H, int32_t W, int32_t align_corners, float scale_h, float scale_w,
+                                void* stream);
+/* Nearest resize (F.interpolate default mode of utils/ops.py:7-26) and its deterministic gather backward. */
 int b200seg_resize_nearest_fwd(const void* in, void* out, int32_t dtype, int32_t NC, int32_t h, int32_t w,
-                               int32_t H, int32_t W, void* stream);
+                               int32_t H, int32_t W, float scale_h, float scale_w, void* stream);
+int b200seg_resize_nearest_bwd(const void* grad_out, void* grad_in, int32_t dtype, int32_t NC, int32_t h, int32_t w,
+                               int32_t H, int32_t W, float scale_h, float scale_w, void* stream);
 
 /* One image of an evaluation batch. */
 typedef struct b200seg_image {

@@ -283,14 +283,45 @@ def test_resize_fused_general_is_deterministic_and_matches_round1_kernel(B):
     x = synth_logits((4, 19, 32, 64), 8, device='cuda')
     y = synth_labels((4, 256, 512), 19, 8, device='cuda').unsqueeze(1)
     res = []
-    for old in ('0', '1'):
-        os.environ['B200SEG_UPCELL_OLD'] = old
+    for old in ('gen', 'old'):
+        os.environ['B200SEG_UPCELL'] = old
         try:
             xa = x.clone().requires_grad_(True)
             r = B.fused_resize_losses(xa, y, B.CrossEntropyLoss(), ignore_index=255)
             r['loss_ce'].backward()
             res.append((r['loss_ce'].detach().clone(), xa.grad.clone(), r['acc_seg'].clone()))
         finally:
-            del os.environ['B200SEG_UPCELL_OLD']
+            del os.environ['B200SEG_UPCELL']
     assert rel_err(res[0][0], res[1][0]) <= 2e-6 and rel_err(res[0][1], res[1][1]) <= 1e-5
     assert abs(float(res[0][2]) - float(res[1][2])) <= 1e-3
+
+
+def test_resize_scale_factor_and_nearest_backward(B):
+    """utils/ops.py:7-26 passes size= / scale_factor= and any mode through to F.interpolate: fractional scale factors (the
+    source-index scale becomes 1 / scale_factor, not in / out) and the nearest mode with a gradient."""
+    F = torch.nn.functional
+    x = torch.randn(2, 3, 11, 14, device='cuda')
+    for sf in (2, 1.5, (2.5, 1.7), 0.6):
+        for ac in (False, True):
+            xa = x.clone().requires_grad_(True)
+            xb = x.clone().requires_grad_(True)
+            ya = B.resize(xa, scale_factor=sf, mode='bilinear', align_corners=ac, warning=False)
+            yb = F.interpolate(xb, scale_factor=sf, mode='bilinear', align_corners=ac)
+            assert ya.shape == yb.shape and torch.equal(ya, yb), (sf, ac)
+            go = torch.randn_like(yb)
+            ya.backward(go)
+            yb.backward(go)
+            assert rel_err(xa.grad, xb.grad) <= 1e-5, (sf, ac)
+        xa = x.clone().requires_grad_(True)
+        xb = x.clone().requires_grad_(True)
+        ya = B.resize(xa, scale_factor=sf)              # default mode: nearest
+        yb = F.interpolate(xb, scale_factor=sf)
+        assert torch.equal(ya, yb), sf
+        go = torch.randn_like(yb)
+        ya.backward(go)
+        yb.backward(go)
+        assert rel_err(xa.grad, xb.grad) <= 1e-5, sf
+    y = B.resize(x, size=(23, 9))
+    assert torch.equal(y, F.interpolate(x, size=(23, 9)))
+    with pytest.raises(NotImplementedError):
+        B.resize(x, size=(20, 20), mode='bicubic')
