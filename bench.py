@@ -336,6 +336,26 @@ def b200_main(args):
                 yd[j].copy_(yh[j], non_blocking=True)
                 arrived[j].record(copy_stream)
 
+        # the step itself is captured once per device buffer set through the public API (fused_resize_losses + backward),
+        # as the device-resident loop does: per step the host issues two copies, one graph replay and one D2H read
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for j in range(2):
+                xd[j].grad = None
+                B.fused_resize_losses(xd[j], yd[j], ce, align_corners=False, ignore_index=ign)['loss_ce'].backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs, losses = [], []
+        for j in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                xd[j].grad = None
+                r = B.fused_resize_losses(xd[j], yd[j], ce, align_corners=False, ignore_index=ign)
+                r['loss_ce'].backward()
+            graphs.append(g)
+            losses.append(r['loss_ce'])
+
         def run(steps):
             issue_copy(0)
             for k in range(steps):
@@ -343,10 +363,8 @@ def b200_main(args):
                 if k + 1 < steps:
                     issue_copy(k + 1)      # buffer (k+1)&1 was released by the .item() of step k-1
                 torch.cuda.current_stream().wait_event(arrived[j])
-                xd[j].grad = None
-                r = B.fused_resize_losses(xd[j], yd[j], ce, align_corners=False, ignore_index=ign)
-                r['loss_ce'].backward()
-                host_loss.append(r['loss_ce'].item())  # D2H read of the step's result (synchronises, as parse_losses does)
+                graphs[j].replay()
+                host_loss.append(losses[j].item())  # D2H read of the step's result (synchronises, as parse_losses does)
 
         run(4)
         vals = []
@@ -434,8 +452,9 @@ def b200_main(args):
                     'repeats_mpix_s': [round(v, 1) for v in e2e_runs],
                     'int64_host_labels_value': e2e_i64_value, 'int64_host_labels_h2d_bytes_per_step': h2d_i64,
                     'note': 'pinned host fp32 logits + uint8 label maps (as a pipeline delivers masks; read directly by the '
-                            'kernels) copied every step on a copy stream, double-buffered; loss read back every step; '
-                            'median of 3 repeats. int64_host_labels_value = same loop with int64 host labels (8x label bytes)'},
+                            'kernels) copied every step on a copy stream into double-buffered device inputs; the step '
+                            '(fused_resize_losses + backward) replayed from a CUDA graph captured through the public API; loss read '
+                            'back every step; median of 3 repeats. int64_host_labels_value = same loop with int64 host labels'},
             'gpu_launches': int(launches_per_step * K),
             'launches_per_step': int(launches_per_step),
             'roofline': roof,
@@ -474,7 +493,7 @@ def flatten_workloads(line, extras):
     put('c4_fwd_bwd_ms', extras, 'C4_voc_fp32_ce', 'fwd_bwd', 'ms')
     put('c4_fwd_bwd_frac', extras, 'C4_voc_fp32_ce', 'fwd_bwd', 'roofline', 'frac')
     put('c4_fwd_frac', extras, 'C4_voc_fp32_ce', 'fwd', 'roofline', 'frac')
-    put('c2_ac_false_eager_ms', extras, 'C2_align_corners_false_eager', 'fwd_bwd', 'ms')
+    put('c2_ac_false_ms', extras, 'C2_align_corners_false', 'fwd_bwd', 'ms')
     put('c2_ac_true_ms', extras, 'C2_align_corners_true', 'fwd_bwd', 'ms')
     put('c2_c150_ns_per_px_class', extras, 'C2_like_c150_64to512', 'fwd_bwd', 'ns_per_px_class')
     put('c2_ac_true_ns_per_px_class', extras, 'C2_align_corners_true', 'fwd_bwd', 'ns_per_px_class')
@@ -699,8 +718,8 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
                  plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
 
     # ---- resize-fused CE beyond the headline shape: align_corners=True (thread-per-cell kernel, csrc/loss_upgen.cuh) and
-    # 150 classes at 1/8 resolution (C > 32: resized once by csrc/resize.cu, then the label-resolution kernels; both
-    # deterministic — there is no atomicAdd backward)
+    # 150 classes at 1/8 resolution (C > 32: the class-tiled plan of the same file); both deterministic — there is no
+    # atomicAdd backward. Each step is replayed from a CUDA graph, as the headline is.
     def bench_up(name, shape, size, ac, iters=20, plan=''):
         n, c, hh, ww = shape
         xs = [make_logits(shape, 700 + i, device=dev).requires_grad_(True) for i in range(2)]
@@ -712,9 +731,22 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
             x.grad = None
             B.fused_resize_losses(x, ys[i & 1], ce, align_corners=ac, ignore_index=255)['loss_ce'].backward()
 
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(2):
+                fb(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs = []
+        for i in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fb(i)
+            graphs.append(g)
         for i in range(3):
-            fb(i)
-        ms = timed_events(fb, iters)
+            graphs[i & 1].replay()
+        ms = timed_events(lambda i: graphs[i & 1].replay(), iters)
         px = n * size[0] * size[1]
         out[name] = {'logits': list(shape), 'label_hw': list(size), 'align_corners': ac, 'pixels': px,
                      'fwd_bwd': dict(ms=ms, mpix_s=px / ms / 1e3, ns_per_px_class=ms * 1e6 / (px * c), plan=plan)}
@@ -722,12 +754,12 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
         torch.cuda.empty_cache()
 
     try:
-        bench_up('C2_align_corners_false_eager', (8, 19, 64, 128), (512, 1024), False,
-                 plan='headline shape through eager launches (no CUDA graph), for comparison with the two lines below')
+        bench_up('C2_align_corners_false', (8, 19, 64, 128), (512, 1024), False,
+                 plan='the headline shape measured the same way as the two lines below (2 input sets, CUDA-graph replay)')
         bench_up('C2_align_corners_true', (8, 19, 64, 128), (512, 1024), True,
                  plan='up_gen_kernel (thread per cell, any ratio) + up_combine + finalize')
         bench_up('C2_like_c150_64to512', (8, 150, 64, 64), (512, 512), False, iters=10,
-                 plan='resize_bilinear_fwd -> ce_fwd + ce_bwd at label resolution -> resize_bilinear_bwd (deterministic gather)')
+                 plan='class-tiled thread-per-cell plan: up_gen_kernel (forward, all classes) + up_gen_bwd_tile_kernel x 5 tiles + up_combine')
     except Exception as e:
         out['C2_align_corners_true'] = {'error': repr(e)}
 

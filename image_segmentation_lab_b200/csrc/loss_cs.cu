@@ -52,6 +52,7 @@ constexpr int kCsWarpPx = 16;     // pixels per consumer warp per tile (4 groups
 constexpr int kCsGroupWarps = 8;  // consumer warps per tile (a "group"); a CTA runs G groups on alternating tiles
 constexpr int kCsMaxStages = 6;
 constexpr int kCsBoxBytes = 128;   // inner extent of a TMA box = one swizzle row
+constexpr int kCsMaxClasses = 152;          // 8 slices x 19 classes
 constexpr int kCsBig = (int)0x80000000;     // a label that does not fit int32: never a class, never ignored
 constexpr int kCsNever = (int)0x80000001;   // an ignore value no decoded label can take
 __device__ __forceinline__ int cs_label32(const unsigned char* row, int dt, int t) {
@@ -245,6 +246,8 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
   const int C = p.C, NS = p.stages;
   const bool dice = (p.flags & B200SEG_WANT_DICE) != 0;
   float* bins = reinterpret_cast<float*>(smem_raw + (size_t)NS * p.stage_bytes);   // [NW][2][C]
+  __shared__ float cw_s[kCsMaxClasses];                                           // CE class weights (1 when absent)
+  for (int c = tid; c < C; c += blockDim.x) cw_s[c] = p.cw ? __ldg(p.cw + c) : 1.f;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -338,12 +341,12 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
           for (int q = 0; q < CsCfg<T>::kWords; ++q) ot.w[q] = __shfl_xor_sync(0xffffffffu, mx.w[q], o);
           cs_max<T>(mx, ot);
         }
-        float mh[PX], nm[PX], Sh[PX];
+        float mh[PX], nm[PX], Sh[PX], Sb[PX];
         cs_unpack<T>(mx, mh);
 #pragma unroll
-        for (int v = 0; v < PX; ++v) { nm[v] = -mh[v] * kLog2e; Sh[v] = 0.f; }
+        for (int v = 0; v < PX; ++v) { nm[v] = -mh[v] * kLog2e; Sh[v] = 0.f; Sb[v] = 0.f; }
 
-        // sweep 2: exponentials (kept) and their sum
+        // sweep 2: exponentials (kept) and their sum (two partial sums per pixel: shorter dependent FADD chains)
         float e[CPT][PX];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
@@ -352,9 +355,12 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
 #pragma unroll
           for (int v = 0; v < PX; ++v) {
             e[i][v] = ex2(fmaf(z[v], kLog2e, nm[v]));
-            Sh[v] += e[i][v];
+            if (i & 1) Sb[v] += e[i][v];
+            else Sh[v] += e[i][v];
           }
         }
+#pragma unroll
+        for (int v = 0; v < PX; ++v) Sh[v] += Sb[v];
 #pragma unroll
         for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
         const float zy = to_float<T>(*reinterpret_cast<const T*>(stage + cs_offset<T>(p, ycc, t_px)));
         const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
         if (valid && (p.flags & B200SEG_WANT_CE)) {
-          const float wt = p.cw ? __ldg(p.cw + ycc) : 1.f;
+          const float wt = cw_s[ycc];
           const float pwv = p.pw ? __ldg(p.pw + gpx) : 1.f;
           loss_acc = fmaf(wt * pwv, lse - zy, loss_acc);
         }
@@ -431,9 +437,14 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
   // stages are 1024-byte aligned: the 128B swizzle is a function of the shared-memory ADDRESS bits
   unsigned char* const smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   __shared__ __align__(8) unsigned long long full_bar[kCsMaxStages], done_bar[kCsMaxStages], empty_bar[kCsMaxStages];
+  // per-image Dice coefficients of the image a consumer group is working on ([alpha | 2 beta], scaled by the upstream
+  // gradient) and the CE class weights: the per-pixel scalar work reads them from shared memory, not through L2
+  __shared__ float coef_s[G][2][kCsMaxClasses];
+  __shared__ float cw_s[kCsMaxClasses];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C, NS = p.stages;
   constexpr int CP = CPT * kCsSlices;
+  for (int c = tid; c < C; c += blockDim.x) cw_s[c] = p.cw ? __ldg(p.cw + c) : 1.f;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&done_bar[s], NWG); mbar_init(&empty_bar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -500,11 +511,20 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
       const int s = k % NS;
       const CsTile tl = wk.tile();
       if (tl.n != n_cur) {
+        // new image: the group's 8 warps reload its coefficient table (two named barriers; once or twice per CTA)
         n_cur = tl.n;
+        const int gt = tid - grp * (NWG * 32);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NWG * 32) : "memory");
+        for (int c = gt; c < C; c += NWG * 32) {
+          const float2 ab = __ldg(reinterpret_cast<const float2*>(p.dice_coef) + (size_t)tl.n * C + c);
+          coef_s[grp][0][c] = god * ab.x;
+          coef_s[grp][1][c] = 2.f * god * ab.y;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NWG * 32) : "memory");
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           const int c = i * kCsSlices + j;
-          b[i] = c < C ? 2.f * god * __ldg(p.dice_coef + ((size_t)tl.n * C + c) * 2 + 1) : 0.f;
+          b[i] = c < C ? coef_s[grp][1][c] : 0.f;
         }
       }
       mbar_wait(&full_bar[s], (k / NS) & 1);
@@ -521,9 +541,9 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
         const bool valid = (yy != p.ignore32) && (unsigned)yy < (unsigned)C;
         ycc = yy < 0 ? 0 : (yy >= C ? C - 1 : yy);
         const size_t gpx = (size_t)tl.n * p.HW + tl.px0 + t_px;
-        if (want_ce && valid) kk = Gce * (p.pw ? __ldg(p.pw + gpx) : 1.f) * (p.cw ? __ldg(p.cw + ycc) : 1.f);
-        if (yy != p.dice_ignore32) da = god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 0);
-        by = 2.f * god * __ldg(p.dice_coef + ((size_t)tl.n * C + ycc) * 2 + 1);
+        if (want_ce && valid) kk = Gce * (p.pw ? __ldg(p.pw + gpx) : 1.f) * cw_s[ycc];
+        if (yy != p.dice_ignore32) da = coef_s[grp][0][ycc];
+        by = coef_s[grp][1][ycc];
         const float lse_own = reinterpret_cast<const float*>(stage + p.lse_off)[t_px];
         const float zy = to_float<T>(*reinterpret_cast<const T*>(stage + cs_offset<T>(p, ycc, t_px)));
         py = ex2(fmaf(zy, kLog2e, -lse_own * kLog2e));
@@ -534,11 +554,12 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
       for (int h = 0; h < kPasses; ++h) {
         const int pxh = pxo + h * 4 * PX + g * PX;
         unsigned char* col = stage + cs_offset<T>(p, j, pxh);
-        float nl[PX], D[PX];
+        float nl[PX], D[PX], Db[PX];
 #pragma unroll
         for (int v = 0; v < PX; ++v) {
           nl[v] = -reinterpret_cast<const float*>(stage + p.lse_off)[pxh + v] * kLog2e;
           D[v] = 0.f;
+          Db[v] = 0.f;
         }
         float pr[CPT][PX];
 #pragma unroll
@@ -549,9 +570,12 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
 #pragma unroll
           for (int v = 0; v < PX; ++v) {
             pr[i][v] = ex2(fmaf(z[v], kLog2e, nl[v]));
-            D[v] = fmaf(pr[i][v] * b[i], pr[i][v], D[v]);
+            if (i & 1) Db[v] = fmaf(pr[i][v] * b[i], pr[i][v], Db[v]);   // two partial sums: shorter dependent chains
+            else D[v] = fmaf(pr[i][v] * b[i], pr[i][v], D[v]);
           }
         }
+#pragma unroll
+        for (int v = 0; v < PX; ++v) D[v] += Db[v];
         // the owner adds -(da p_y + kk): after the tree every lane of the pixel holds D = dot - kk = -sub
 #pragma unroll
         for (int v = 0; v < PX; ++v) D[v] += (j == h * PX + v) ? extra : 0.f;

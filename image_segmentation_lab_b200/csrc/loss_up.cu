@@ -66,10 +66,11 @@ static bool up_pow2_ok(int C, int h, int w, int H, int W, int ac, int* S_out) {
   *S_out = S;
   return true;
 }
-// the thread-per-cell kernel (loss_upgen.cuh): any up-sampling ratio, both align_corners settings, C <= 32
+// the thread-per-cell kernels (loss_upgen.cuh): any up-sampling ratio, both align_corners settings; C <= 32 in one launch,
+// up to 512 classes as one forward launch + one backward launch per tile of 32 classes
 static bool up_fast_ok(int C, int h, int w, int H, int W, int ac) {
   (void)ac;
-  if (h <= 0 || w <= 0 || C < 1 || C > 32) return false;
+  if (h <= 0 || w <= 0 || C < 1 || C > 512) return false;
   if (H < h || W < w || (H == h && W == w)) return false;
   return true;
 }
@@ -86,7 +87,8 @@ static bool up_use_old(int C, int h, int w, int H, int W, int ac, int* S_out) {
 
 long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {
   if (!up_fast_ok(C, h, w, H, W, ac)) return 0;
-  return (long long)N * C * (h + 1) * (w + 1) * 4 * (long long)sizeof(float);
+  // corner sums PB (N,C,h+1,w+1) float4; for C > 32 (class-tiled plan) also the (N,H,W) f32 log2-sum-exp map
+  return (long long)N * C * (h + 1) * (w + 1) * 4 * (long long)sizeof(float) + (C > 32 ? (long long)N * H * W * (long long)sizeof(float) : 0);
 }
 
 template <typename T>
@@ -153,7 +155,7 @@ int up_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st) {
   const bool up = (f->h != f->H) || (f->w != f->W);
   if (!up) return flat_fused_dispatch(d, st);
   B200SEG_REQUIRE(up_fast_ok(f->C, f->h, f->w, f->H, f->W, f->align_corners),
-                  "loss_fused: the resize-fused single pass needs H >= h, W >= w and C <= 32 "
+                  "loss_fused: the resize-fused single pass needs H >= h, W >= w and C <= 512 "
                   "(query b200seg_loss_fused_workspace_bytes() != 0 first)");
   switch (f->logit_dtype) {
     case B200SEG_F32: return up_run<float>(d, st);

@@ -45,6 +45,8 @@ struct UpGenParams {
   const float* cw;
   unsigned long long* stats;
   float* pb;
+  float* lse2;        // (N,H,W) per-pixel log2-sum-exp of the interpolated logits: written by the forward-only launch of
+                      // the class-tiled plan (C > 32), read by its backward launches; NULL otherwise
   int label_dtype, label_bytes;
   int has_w;
   int N, C, h, w, H, W;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
 
   // ---- the cell's 4 corner logits: the RG threads of the cell split the classes; scaled by log2 e and offset by the
   // cell's maximum once the latter is known
+  float M2cell = 0.f;
   {
     const int plane = p.h * p.w;
     const T* pl = reinterpret_cast<const T*>(p.logits) + (size_t)n * C * (size_t)plane;
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
     }
     for (int off = 1; off < RG; off <<= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, off));
     const float nM2 = -M * kLog2e;
+    M2cell = M * kLog2e;
     for (int c = rg; c < C; c += RG) {
       const float4 v = CORN[c * cpc + cell];
       CORN[c * cpc + cell] = make_float4(fmaf(v.x, kLog2e, nM2), fmaf(v.y, kLog2e, nM2), (v.z - v.x) * kLog2e, (v.w - v.y) * kLog2e);
@@ -257,8 +261,12 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
         // the product chain (relative error <= 2^-20: four ex2.approx factors), so the test allows 2^-19 — an exact or
         // near tie with another class counts as correct for the label (torch.topk's choice among ties is unspecified)
         const float ey = ex2(zy2 - moff[j]);
-        loss_acc = fmaf(wt, (moff[j] + lg2(s[j])) - zy2, loss_acc);
+        const float lse2_rel = moff[j] + lg2(s[j]);
+        loss_acc = fmaf(wt, lse2_rel - zy2, loss_acc);
         n_correct += (acc_ok && inr && !ign && ey >= m[j] * 0.99999809265f);
+        if constexpr (!GRAD) {
+          if (p.lse2 && ok) p.lse2[img_px + (size_t)(roff + (unsigned)(Xc + j))] = M2cell + lse2_rel;
+        }
         if constexpr (GRAD) {
           a[j] = wt * fast_rcp(s[j]);
           bl[j] = a[j] * lamj;
@@ -341,6 +349,188 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
   cta_flush_stats(loss_acc * kLn2, n_valid, n_correct, n_bad, n_acc, p.stats);
 }
 
+// ------------------------------------------------------------------------------------------------ class-tiled backward
+// C > 32: a thread's private corner sums for ALL classes do not fit shared memory (16 C bytes per thread), so the plan is
+// split: one forward-only launch of up_gen_kernel over all classes (loss, accuracy, and the per-pixel log2-sum-exp into
+// `lse2`), then this kernel once per tile of kUpTile classes (grid.y): soft-max probabilities of the tile's classes from
+// the saved lse2 — p = 2^(z2 - lse2) — the same chain / corner-sum machinery, the tile's slice of PB. Deterministic.
+constexpr int kUpTile = 32;
+
+template <typename T, int PXC, int LK, int THR>
+__global__ void __launch_bounds__(THR) up_gen_bwd_tile_kernel(const UpGenParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int C = p.C;
+  const int RG = p.RG;
+  const int cpc = THR >> p.logRG;
+  float4* CORN = reinterpret_cast<float4*>(smem_raw);             // [kUpTile][cpc]
+  float4* OH = CORN + (size_t)kUpTile * cpc;                      // [kUpTile][THR]
+  const int c0 = blockIdx.y * kUpTile;
+  const int ct = min(kUpTile, C - c0);
+  const int rg = tid & (RG - 1);
+  const int cell = tid >> p.logRG;
+  const unsigned cid_raw = blockIdx.x * (unsigned)cpc + (unsigned)cell;
+  const bool cell_ok = cid_raw < (unsigned)p.cells;
+  const unsigned cid = cell_ok ? cid_raw : (unsigned)p.cells - 1u;
+  const unsigned t0 = cid / (unsigned)(p.w + 1);
+  const int r = (int)(cid - t0 * (unsigned)(p.w + 1));
+  const int n = (int)(t0 / (unsigned)(p.h + 1));
+  const int b = (int)(t0 - (unsigned)n * (unsigned)(p.h + 1));
+  const bool ac = p.ac != 0;
+
+  float M2t;
+  bool chain_ok;
+  {
+    const int plane = p.h * p.w;
+    const T* pl = reinterpret_cast<const T*>(p.logits) + ((size_t)n * C + c0) * (size_t)plane;
+    const int ya = b - 1 < 0 ? 0 : b - 1, yb = b > p.h - 1 ? p.h - 1 : b;
+    const int xa = r - 1 < 0 ? 0 : r - 1, xb = r > p.w - 1 ? p.w - 1 : r;
+    const int o00 = ya * p.w + xa, o01 = ya * p.w + xb, o10 = yb * p.w + xa, o11 = yb * p.w + xb;
+    float M = -3.0e38f, mn = 3.0e38f;
+    for (int c = rg; c < ct; c += RG) {
+      const T* q = pl + (size_t)c * plane;
+      const float v00 = to_float<T>(__ldg(q + o00)), v01 = to_float<T>(__ldg(q + o01));
+      const float v10 = to_float<T>(__ldg(q + o10)), v11 = to_float<T>(__ldg(q + o11));
+      M = fmaxf(fmaxf(M, fmaxf(v00, v01)), fmaxf(v10, v11));
+      mn = fminf(fminf(mn, fminf(v00, v01)), fminf(v10, v11));
+      CORN[c * cpc + cell] = make_float4(v00, v01, v10, v11);
+    }
+    for (int off = 1; off < RG; off <<= 1) {
+      M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, off));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    }
+    M2t = M * kLog2e;
+    // the chain (and the per-pixel factor 2^(M2t - lse2) <= 2^(M2t - min)) stays in the normal range
+    chain_ok = (M - mn) * kLog2e <= 120.f;
+    const float nM2 = -M2t;
+    for (int c = rg; c < ct; c += RG) {
+      const float4 v = CORN[c * cpc + cell];
+      CORN[c * cpc + cell] = make_float4(fmaf(v.x, kLog2e, nM2), fmaf(v.y, kLog2e, nM2), (v.z - v.x) * kLog2e, (v.w - v.y) * kLog2e);
+    }
+    for (int c = 0; c < ct; ++c) OH[c * THR + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+  }
+  const float4* corn = CORN + cell;
+
+  const int Yb0 = up_band_start(p.sh, b, p.h, p.H, ac), Yb1 = up_band_start(p.sh, b + 1, p.h, p.H, ac);
+  const int X0 = up_band_start(p.sw, r, p.w, p.W, ac), X1 = up_band_start(p.sw, r + 1, p.w, p.W, ac);
+  const int rows_per = (Yb1 - Yb0 + RG - 1) >> p.logRG;
+  const int Yr0 = Yb0 + rg * rows_per;
+  const int Yr1 = cell_ok ? min(Yb1, Yr0 + rows_per) : Yr0;
+  const bool xreg = (r > 0 && r < p.w);
+  const float sx = xreg ? p.sw : 0.f;
+  const float lx0 = xreg ? (X0 < X1 ? up_lambda(p.sw, X0, r - 1, ac) : 0.f) : (r == 0 ? 1.f : 0.f);
+  const bool yreg = (b > 0 && b < p.h);
+  const float ly_clamped = (b == 0) ? 1.f : 0.f;
+  const int dt = p.label_dtype;
+  const int lb = LK == 0 ? 8 : (LK == 1 ? 1 : p.label_bytes);
+  const size_t img_px = (size_t)n * p.H * p.W;
+  const char* labimg = reinterpret_cast<const char*>(p.labels) + img_px * lb;
+  const float* lseimg = p.lse2 + img_px;
+
+#pragma unroll 1
+  for (int Y = Yr0; Y < Yr1; ++Y) {
+    const float ly = yreg ? up_lambda(p.sh, Y, b - 1, ac) : ly_clamped;
+    const float ly0 = 1.f - ly;
+    const unsigned roff = (unsigned)Y * (unsigned)p.W;
+#pragma unroll 1
+    for (int Xc = X0; Xc < X1; Xc += PXC) {
+      const int npx = min(PXC, X1 - Xc);
+      RawLabel raw[PXC];
+      float off2[PXC];
+#pragma unroll
+      for (int j = 0; j < PXC; ++j) {
+        const unsigned px = roff + (unsigned)(Xc + min(j, npx - 1));
+        raw[j] = load_raw_label<LK>(labimg, dt, px);
+        off2[j] = M2t - __ldg(lseimg + px);           // z2_rel + off2 = z2 - lse2 <= 0
+      }
+      const float lam0 = fmaf((float)(Xc - X0), sx, lx0);
+      const bool fast = chain_ok && ((npx == PXC) || (sx == 0.f));
+      float a[PXC], bl[PXC], wts[PXC];
+#pragma unroll
+      for (int j = 0; j < PXC; ++j) {
+        const bool ok = cell_ok && j < npx;
+        const int ydec = decode_label<LK>(raw[j], dt);
+        const int yy = ok ? ydec : p.ignore32;
+        const bool ign = (yy == p.ignore32);
+        const bool inr = (unsigned)yy < (unsigned)C;
+        const int yc = inr && !ign ? yy : 0;
+        const bool use = ok && inr && !ign;
+        float wt = use ? 1.f : 0.f;
+        if (p.has_w) wt = pixel_weight(p.cw, p.pw, use, yc, img_px + (size_t)(roff + (unsigned)(Xc + min(j, npx - 1))));
+        const float lamj = fmaf((float)(fast ? j : min(j, npx - 1)), sx, lam0);
+        wts[j] = wt;
+        a[j] = fast ? wt * ex2(off2[j]) : wt;          // direct evaluation folds off2 into the exponent instead
+        bl[j] = a[j] * lamj;
+        const int yl = yc - c0;
+        if (use && (unsigned)yl < (unsigned)ct) {     // one-hot term, for labels of this tile
+          const float u = wt * lamj, v = wt - u;
+          float4* oh = OH + yl * THR + tid;
+          float4 o = *oh;
+          o.x = fmaf(ly - 1.f, v, o.x);
+          o.y = fmaf(ly - 1.f, u, o.y);
+          o.z = fmaf(-ly, v, o.z);
+          o.w = fmaf(-ly, u, o.w);
+          *oh = o;
+        }
+      }
+      if (fast) {
+#pragma unroll 2
+        for (int c = 0; c < ct; ++c) {
+          const float4 q = corn[c * cpc];
+          const float L2 = fmaf(ly, q.z, q.x), D2 = fmaf(ly, q.w, q.y) - L2;
+          float e[PXC];
+          up_chain<PXC>(ex2(fmaf(lam0, D2, L2)), ex2(D2 * sx), e);
+          float gs = 0.f, gb = 0.f;
+#pragma unroll
+          for (int j = 0; j < PXC; ++j) { gs = fmaf(e[j], a[j], gs); gb = fmaf(e[j], bl[j], gb); }
+          const float ga = gs - gb;
+          float4* oh = OH + c * THR + tid;
+          float4 o = *oh;
+          o.x = fmaf(ly0, ga, o.x);
+          o.y = fmaf(ly0, gb, o.y);
+          o.z = fmaf(ly, ga, o.z);
+          o.w = fmaf(ly, gb, o.w);
+          *oh = o;
+        }
+      } else {
+        for (int c = 0; c < ct; ++c) {
+          const float4 q = corn[c * cpc];
+          const float L2 = fmaf(ly, q.z, q.x), D2 = fmaf(ly, q.w, q.y) - L2;
+          float gs = 0.f, gb = 0.f;
+#pragma unroll
+          for (int j = 0; j < PXC; ++j) {
+            const float ev = wts[j] != 0.f ? ex2(fmaf(fmaf((float)min(j, npx - 1), sx, lam0), D2, L2) + off2[j]) : 0.f;
+            gs = fmaf(ev, a[j], gs);
+            gb = fmaf(ev, bl[j], gb);
+          }
+          const float ga = gs - gb;
+          float4* oh = OH + c * THR + tid;
+          float4 o = *oh;
+          o.x = fmaf(ly0, ga, o.x);
+          o.y = fmaf(ly0, gb, o.y);
+          o.z = fmaf(ly, ga, o.z);
+          o.w = fmaf(ly, gb, o.w);
+          *oh = o;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (cell_ok) {
+    const int col0 = tid - rg;
+    for (int c = rg; c < ct; c += RG) {
+      float4 o = OH[c * THR + col0];
+      for (int k = 1; k < RG; ++k) {
+        const float4 t = OH[c * THR + col0 + k];
+        o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+      }
+      float4* dst = reinterpret_cast<float4*>(p.pb) + (((size_t)n * C + c0 + c) * (p.h + 1) + b) * (p.w + 1) + r;
+      *dst = o;
+    }
+  }
+}
+
 // resident CTAs per SM from the shared-memory footprint (228 KB per SM, 1 KB reserved per CTA) and the register file
 template <int THR> static int upgen_resident_warps(int C, int logRG, bool grad) {
   const size_t smem = upgen_smem_bytes<THR>(C, logRG, grad) + 1024 + 640;
@@ -354,6 +544,32 @@ template <int THR> static int upgen_resident_warps(int C, int logRG, bool grad) 
 
 template <typename T, int PXC, bool GRAD, int LK> static int launch_upgen_lk(UpGenParams p, cudaStream_t st) {
   constexpr int THR = 32;
+  if (p.C > kUpTile) {
+    // class-tiled plan: the corner logits of ALL classes sit in shared memory per CELL (16 C bytes), so 4 threads share a cell
+    p.logRG = 2;
+    p.RG = 4;
+    const long long cells_per_cta = THR >> p.logRG;
+    const long long grid = (p.cells + cells_per_cta - 1) / cells_per_cta;
+    {
+      const size_t smem = upgen_smem_bytes<THR>(p.C, p.logRG, false);
+      auto k = up_gen_kernel<T, PXC, false, LK, THR>;
+      if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)smem)) return e;
+      k<<<(unsigned)grid, THR, smem, st>>>(p);
+      count_launch();
+      if (int e = check_launch("up_gen_kernel")) return e;
+    }
+    if (GRAD) {
+      const size_t smem = upgen_smem_bytes<THR>(kUpTile, p.logRG, true);
+      auto k = up_gen_bwd_tile_kernel<T, PXC, LK, THR>;
+      if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)smem)) return e;
+      dim3 g2((unsigned)grid, (unsigned)((p.C + kUpTile - 1) / kUpTile));
+      k<<<g2, THR, smem, st>>>(p);
+      count_launch();
+      return check_launch("up_gen_bwd_tile_kernel");
+    }
+    return 0;
+  }
+  p.lse2 = nullptr;
   // row groups: enough threads for >= 2 waves of resident warps, and the fewest idle slots in the last wave
   int best = 0;
   double best_eff = -1.0;
@@ -390,6 +606,8 @@ template <typename T> int upgen_run(const b200seg_loss_desc* f, float* pb, bool 
   p.logits = f->logits; p.labels = f->labels; p.pw = f->pixel_weight; p.cw = f->ce_class_weight;
   p.stats = reinterpret_cast<unsigned long long*>(f->stats);
   p.pb = pb;
+  // workspace layout: PB (N,C,h+1,w+1) float4, then — class-tiled plan only — the (N,H,W) per-pixel log2-sum-exp
+  p.lse2 = (grad && f->C > kUpTile) ? pb + (size_t)f->N * f->C * (f->h + 1) * (f->w + 1) * 4 : nullptr;
   p.label_dtype = f->label_dtype; p.label_bytes = label_bytes(f->label_dtype);
   p.has_w = (p.cw != nullptr) || (p.pw != nullptr);
   p.N = f->N; p.C = f->C; p.h = f->h; p.w = f->w; p.H = f->H; p.W = f->W;

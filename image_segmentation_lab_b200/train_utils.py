@@ -31,8 +31,9 @@ def parse_losses(losses, lazy=False):
 
     names = list(log_vars.keys())
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    # torch.full is a device-side fill (a host tensor copied to the GPU here would break CUDA-graph capture of the step)
     vec = torch.stack([log_vars[k].detach().to(torch.float32).reshape(()) for k in names] +
-                      [torch.tensor(float(len(names)), device=loss.device)])
+                      [torch.full((), float(len(names)), dtype=torch.float32, device=loss.device)])
     if world > 1:
         dist.all_reduce(vec)
     if lazy:

@@ -41,12 +41,16 @@ def main():
     lo, hi = D.shard_range(n_img, rank, world)
     preds = [torch.randint(0, 19, (96, 160), generator=torch.Generator().manual_seed(900 + i)).to(dev) for i in range(lo, hi)]
     gts = [synth_labels((1, 96, 160), 19, 900 + i, block=8)[0].float().to(dev) for i in range(lo, hi)]
+    # parse_losses under NCCL: one all-reduce for every logged variable of the step, rank mean as the reference
+    # (utils/train_utils.py:56-72)
+    _, logged = B.parse_losses({'loss_ce': r['loss_ce'].detach(), 'loss_dice': r['loss_dice'].detach(), 'acc_seg': r['acc_seg']})
     tot = B.area_totals_device(preds, gts, 19, 255)
     tot = D.all_reduce_areas({'areas': tot})['areas']
     torch.cuda.synchronize()
     if rank == 0:
         torch.save({'loss_ce': float(loss_ce), 'loss_dice': float(loss_dice), 'acc_seg': float(acc),
-                    'grad': torch.cat(g_all, 0).cpu(), 'areas': tot.cpu()}, os.environ['MGPU_OUT'])
+                    'grad': torch.cat(g_all, 0).cpu(), 'areas': tot.cpu(), 'logged': dict(logged),
+                    'local_loss_ce': float(r['loss_ce'])}, os.environ['MGPU_OUT'])
     dist.barrier()
     dist.destroy_process_group()
 

@@ -98,7 +98,8 @@ def test_validation_errors_without_gpu():
     assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 0) == 8 * 19 * 65 * 129 * 16
     assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 512, 1024, 1) == 8 * 19 * 65 * 129 * 16   # any align_corners
     assert lib.b200seg_loss_fused_workspace_bytes(2, 19, 65, 129, 513, 1025, 1) == 2 * 19 * 66 * 130 * 16   # any up-sampling ratio
-    assert lib.b200seg_loss_fused_workspace_bytes(8, 150, 64, 64, 512, 512, 0) == 0    # C > 32 -> two-pass path
+    assert lib.b200seg_loss_fused_workspace_bytes(8, 150, 64, 64, 512, 512, 0) == 8 * 150 * 65 * 65 * 16 + 8 * 512 * 512 * 4   # class-tiled
+    assert lib.b200seg_loss_fused_workspace_bytes(8, 600, 64, 64, 512, 512, 0) == 0    # C > 512 -> resize first
     assert lib.b200seg_loss_fused_workspace_bytes(8, 19, 64, 128, 32, 1024, 0) == 0    # down-sampling -> two-pass path
 
 
