@@ -25,7 +25,7 @@
 // and offset by the cell's maximum (every interpolated logit is a convex combination of its corners, so z <= 0).
 // Each cell's sums go once to PB[n][c][band][run] (float4); up_combine_kernel (loss_up.cu) adds the 4 cells around every
 // logit. A chunk falls back to DIRECT evaluation (FFMA + MUFU per class-pixel, exact per-pixel maxima) when the chain is
-// not applicable: a partially filled chunk, a class more than 120 log2-units below the cell maximum at either tap
+// not applicable: a partially filled chunk at a ratio below PXC - 1, a class more than 120 log2-units below the cell maximum at either tap
 // (its chain would leave the normal range), or an underflowing sum.
 //
 // Top-1: the label's class is the arg-max iff its exponential reaches the pixel's maximum exponential up to the chain's
@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
       float s[PXC], m[PXC], moff[PXC];
 #pragma unroll
       for (int j = 0; j < PXC; ++j) { s[j] = 0.f; m[j] = 0.f; moff[j] = 0.f; }
-      bool fast = (npx == PXC) || (sx == 0.f);
+      // a partially filled chunk still takes the chain when the lambdas of its masked tail stay <= 2 (then, with every
+      // tap >= -120 below the maximum, the tail's exponentials stay finite; their weights a[j] are 0)
+      bool fast = (npx == PXC) || (sx * (float)(PXC - 1) <= 1.f);
       if (fast) {
         // ---- forward sweep, geometric chain
         float minend = 0.f;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
         }
         bool okc = minend >= -120.f;
 #pragma unroll
-        for (int j = 0; j < PXC; ++j) okc = okc && (s[j] > 1e-30f) && (s[j] < 3.0e38f);
+        for (int j = 0; j < PXC; ++j) okc = okc && (j >= npx || ((s[j] > 1e-30f) && (s[j] < 3.0e38f)));
         fast = okc;
       }
       if (!fast) {
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(THR) up_gen_bwd_tile_kernel(const UpGenParams 
         off2[j] = M2t - __ldg(lseimg + px);           // z2_rel + off2 = z2 - lse2 <= 0
       }
       const float lam0 = fmaf((float)(Xc - X0), sx, lx0);
-      const bool fast = chain_ok && ((npx == PXC) || (sx == 0.f));
+      const bool fast = chain_ok && ((npx == PXC) || (sx * (float)(PXC - 1) <= 1.f));
       float a[PXC], bl[PXC], wts[PXC];
 #pragma unroll
       for (int j = 0; j < PXC; ++j) {
