@@ -6,8 +6,9 @@
 Headline workload (config.workload, BASELINE.json configs[1]): FCN-style head at Cityscapes shape — fp32 logits
 (8,19,64,128) bilinearly resized to 512x1024 labels, cross-entropy with ignore_index=255, forward AND backward, plus
 the in-loop top-1 accuracy. A "step" is one such batch per GPU; a pixel is a label-resolution pixel. Under
-torchrun every rank runs the same per-GPU batch (weak scaling, images are independent) and the only exchange is
-one all-reduce of the 8-double statistics vector per step on a side stream.
+torchrun every rank runs the same per-GPU batch (weak scaling, images are independent) and the only exchange is the
+all-reduce of the steps' 8-double statistics vectors (logging only), packed and issued once per ring cycle of 8 steps on a
+side stream (--allreduce-every 1 issues it every step).
 
   value         device-resident throughput: CUDA-graph replays of the step over a ring of input sets larger than L2,
                 timed with CUDA events on the launching stream, max over ranks.
@@ -199,11 +200,13 @@ def timed_events(fn, iters, stream=None):
 
 
 class GraphRing:
-    """A step captured once per input set (the ring is larger than L2) and replayed; under torchrun ONE all-reduce of
-    the step's 8-double statistics vector rides on a side stream, ordered by events, off the compute stream."""
+    """A step captured once per input set (the ring is larger than L2) and replayed; under torchrun the steps' 8-double
+    statistics vectors (logging only: the gradient's denominator is known a priori) are all-reduced ONCE PER RING CYCLE —
+    `every` steps packed into one buffer, one NCCL call on a side stream ordered by events, off the compute stream."""
 
-    def __init__(self, step, n_sets, dev, world, dist):
+    def __init__(self, step, n_sets, dev, world, dist, every=None):
         self.R, self.world, self.dist, self.dev = n_sets, world, dist, dev
+        self.every = n_sets if every is None else max(1, min(int(every), n_sets))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -219,23 +222,36 @@ class GraphRing:
             self.graphs.append(g)
         self.stats = [o['_stats'] for o in self.outs]
         self.comm = torch.cuda.Stream(device=dev)
-        self.slot_free = [torch.cuda.Event() for _ in range(n_sets)]
-        self.ready = [torch.cuda.Event() for _ in range(n_sets)]
+        self.ready = torch.cuda.Event()
+        self.packed = torch.cuda.Event()       # the side stream has read the cycle's statistics: their slots may be rewritten
+        self.pending = []                      # ring slots whose statistics have not been reduced yet
+        self.collectives = 0
+
+    def _reduce_pending(self):
+        if not self.pending:
+            return
+        cur = torch.cuda.current_stream()
+        self.ready.record(cur)
+        self.comm.wait_event(self.ready)
+        with torch.cuda.stream(self.comm):
+            buf = torch.cat([self.stats[i] for i in self.pending])
+            self.packed.record(self.comm)
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM)
+        cur.wait_event(self.packed)
+        self.pending = []
+        self.collectives += 1
 
     def run_step(self, k):
         i = k % self.R
-        cur = torch.cuda.current_stream()
-        if self.world > 1:
-            cur.wait_event(self.slot_free[i])
         self.graphs[i].replay()
-        if self.world > 1:  # one 64-byte all-reduce per step, off the compute stream
-            self.ready[i].record(cur)
-            self.comm.wait_event(self.ready[i])
-            with torch.cuda.stream(self.comm):
-                self.dist.all_reduce(self.stats[i], op=self.dist.ReduceOp.SUM)
-                self.slot_free[i].record(self.comm)
+        if self.world > 1:
+            self.pending.append(i)
+            if len(self.pending) >= self.every:
+                self._reduce_pending()
 
     def drain(self):
+        if self.world > 1:
+            self._reduce_pending()             # a partial cycle is reduced inside the timed region
         torch.cuda.current_stream().wait_stream(self.comm)
 
     def timed(self, K, W):
@@ -310,9 +326,10 @@ def b200_main(args):
     torch.cuda.synchronize()
     launches_per_step = B.launch_count() - c0
 
-    ring = GraphRing(step, R, dev, world, dist)
+    ring = GraphRing(step, R, dev, world, dist, every=args.allreduce_every)
     ms_step = ring.timed(K, W)
     value = world * px_step / (ms_step * 1e-3) / 1e6
+    ar_every = ring.every
 
     # ---- e2e: host inputs, H2D + step + D2H every step, through the public API. The copies of step k+1 are issued on a
     # copy stream before step k's kernels (double-buffered device inputs), as a DataLoader with pin_memory +
@@ -428,7 +445,7 @@ def b200_main(args):
         del xs, ys
         torch.cuda.empty_cache()
         try:
-            c4 = c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W)
+            c4 = c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W, args.allreduce_every)
         except Exception as ex:
             c4 = {'error': repr(ex)}
         sharded = c5_sharded(B, D, dist, dev, rank, world, peak, peak_kind)
@@ -444,8 +461,8 @@ def b200_main(args):
             'config': dict(workload_config(), l2='ring of %d input sets (%.0f MB) > 126 MB L2; one CUDA graph per set' % (
                 R, R * (N * Cc * h * w * 4 + N * H * Wd * 8) / 1e6),
                 cpu_affinity='GPU-local NUMA node (NVML)' if numa_bound else 'inherited',
-                collective='1 all_reduce(8 doubles)/step on a side stream'
-                if world > 1 else 'none (single GPU)'),
+                collective=('1 all_reduce per %d steps: the steps\' 8-double statistics vectors (logging only) packed into one '
+                            'buffer, on a side stream' % ar_every) if world > 1 else 'none (single GPU)'),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'steps': e2e_steps, 'host_label_dtype': 'uint8',
@@ -579,7 +596,7 @@ def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
     return out
 
 
-def c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W):
+def c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W, ar_every=None):
     """BASELINE config 4 (PSPNet head at Pascal VOC shape: 21 classes, 512x512, fp32 CE fwd+bwd, batch 32) data-parallel
     over the ranks: STRONG = the 32 images split over the GPUs, WEAK = 32 images on every GPU. CUDA-graph replay over a ring
     of input sets larger than L2, one all-reduce of the statistics vector per step on a side stream."""
@@ -599,7 +616,7 @@ def c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W):
             r['loss_ce'].backward()
             return r
 
-        ring = GraphRing(step, R, dev, world, dist)
+        ring = GraphRing(step, R, dev, world, dist, every=ar_every)
         ms = ring.timed(K, W)
         px = n_loc * world * Hh * Ww
         algo = 2 * n_loc * world * Cn * Hh * Ww * 4 + px * 8          # single pass: read + write logits, read labels
@@ -610,8 +627,8 @@ def c4_data_parallel(B, dist, dev, rank, world, peak, peak_kind, K, W):
                                   'peak_kind': peak_kind}}
         del ring, xs, ys
         torch.cuda.empty_cache()
-    out['note'] = ('ce_bulk_kernel + finalize per step from a CUDA graph; 1 all_reduce(8 doubles)/step on a side stream; '
-                   'strong = 32/G images per GPU, weak = 32 per GPU')
+    out['note'] = ('ce_bulk_kernel + finalize per step from a CUDA graph; the steps\' statistics vectors all-reduced once per ring '
+                   'cycle on a side stream; strong = 32/G images per GPU, weak = 32 per GPU')
     return out
 
 
@@ -862,6 +879,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--allreduce-every', type=int, default=None,
+                    help='steps per all-reduce of the logging statistics under torchrun (default: the ring size, 8; 1 = every step)')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_main(args)

@@ -210,9 +210,11 @@ __device__ __forceinline__ void cs_producer(const CsParams& p, const CUtensorMap
   CsWalker wk;
   wk.init(p, REVERSE ? t1 - 1 : t0, 1, TP);
   const int nt = (int)(t1 - t0);
-  for (int k = 0; k < nt; ++k) {
-    const int s = k % NS;
-    if (k >= NS) mbar_wait(&empty_bar[s], ((k / NS) - 1) & 1);
+  StageRing ring;
+  ring.init(0, NS, 1);
+  for (int k = 0; k < nt; ++k, ring.advance()) {
+    const int s = ring.s;
+    if (k >= NS) mbar_wait(&empty_bar[s], ring.ph ^ 1);
     if (lane == 0) {
       const CsTile tl = wk.tile();
       const int nbox = (tl.npx + BOXPX - 1) / BOXPX;           // boxes that start inside the image (a partial one is zero-filled)
@@ -311,14 +313,16 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
 
     CsWalker wk;
     wk.init(p, t0 + grp, G, TP);
-    for (int k = grp; k < (int)(t1 - t0); k += G, wk.forward()) {   // group grp consumes tiles grp, grp + G, ... of the CTA's range
-      const int s = k % NS;
+    StageRing ring;
+    ring.init(grp, NS, G);
+    for (int k = grp; k < (int)(t1 - t0); k += G, wk.forward(), ring.advance()) {   // group grp consumes tiles grp, grp + G, ...
+      const int s = ring.s;
       const CsTile tl = wk.tile();
       if (tl.n != n_cur) {
         if (n_cur >= 0) flush_image(n_cur);
         n_cur = tl.n;
       }
-      mbar_wait(&full_bar[s], (k / NS) & 1);
+      mbar_wait(&full_bar[s], ring.ph);
       const unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
       float m[4], S[4];                                     // per pixel of this lane (all 4, both passes)
 #pragma unroll
@@ -471,9 +475,11 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
     CsWalker wk;
     wk.init(p, t1 - 1, 1, TP);
     const int nt = (int)(t1 - t0);
-    for (int k = 0; k < nt; ++k, wk.backward()) {
-      const int s = k % NS;
-      mbar_wait(&done_bar[s], (k / NS) & 1);
+    StageRing ring;
+    ring.init(0, NS, 1);
+    for (int k = 0; k < nt; ++k, wk.backward(), ring.advance()) {
+      const int s = ring.s;
+      mbar_wait(&done_bar[s], ring.ph);
       if (lane == 0) {
         const CsTile tl = wk.tile();
         const int nbox = (tl.npx + BOXPX - 1) / BOXPX;
@@ -507,8 +513,10 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
     int n_cur = -1;
     CsWalker wk;
     wk.init(p, t1 - 1 - grp, G, TP);
-    for (int k = grp; k < (int)(t1 - t0); k += G, wk.backward()) {
-      const int s = k % NS;
+    StageRing ring;
+    ring.init(grp, NS, G);
+    for (int k = grp; k < (int)(t1 - t0); k += G, wk.backward(), ring.advance()) {
+      const int s = ring.s;
       const CsTile tl = wk.tile();
       if (tl.n != n_cur) {
         // new image: the group's 8 warps reload its coefficient table (two named barriers; once or twice per CTA)
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 2) * 32, 1) cs_bwd_kernel
           b[i] = c < C ? coef_s[grp][1][c] : 0.f;
         }
       }
-      mbar_wait(&full_bar[s], (k / NS) & 1);
+      mbar_wait(&full_bar[s], ring.ph);
       unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
 
       // per-pixel scalars of the pixel this lane owns (lane j < 4: pass j / PX, v = j % PX): issued first, consumed

@@ -30,6 +30,16 @@ def main():
         for _ in range(reps):
             x.grad = None
             B.fused_resize_losses(x, y, ce, ignore_index=255)['loss_ce'].backward()
+    if 'c2' in which:   # round 2: the thread-per-cell kernels — align_corners=True, and 150 classes (class-tiled plan)
+        ce = B.CrossEntropyLoss()
+        for _ in range(reps):
+            x.grad = None
+            B.fused_resize_losses(x, y, ce, align_corners=True, ignore_index=255)['loss_ce'].backward()
+        x150 = bench.make_logits((2, 150, 64, 64), 1, device=dev).requires_grad_(True)
+        y150 = bench.make_labels((2, 512, 512), 150, 1, device=dev).unsqueeze(1)
+        for _ in range(reps):
+            x150.grad = None
+            B.fused_resize_losses(x150, y150, ce, ignore_index=255)['loss_ce'].backward()
     if 'c3' in which:
         x = bench.make_logits((4, 150, 512, 512), 2, dtype=torch.bfloat16, device=dev).requires_grad_(True)
         y = bench.make_labels((4, 512, 512), 150, 2, device=dev).unsqueeze(1)
@@ -57,6 +67,9 @@ def main():
         logits = [bench.make_logits((1, 19, 1024, 2048), 60 + i, device=dev) for i in range(8)]
         for _ in range(reps):
             B.areas_device(logits, gts[:8], 19, 255, from_logits=True)
+        lows = [bench.make_logits((1, 19, 128, 256), 70 + i, device=dev) for i in range(8)]   # f2: rescale fused into the arg-max
+        for _ in range(reps):
+            B.areas_device(lows, gts[:8], 19, 255, from_logits=True)
     if 'lovasz' in which:   # Lovasz-Softmax at the config-2 label resolution, 4 classes' worth of segments
         x = bench.make_logits((8, 4, 512, 1024), 4, device=dev).requires_grad_(True)
         y = bench.make_labels((8, 512, 1024), 4, 4, device=dev)
