@@ -175,7 +175,10 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
-    if not os.path.exists(path) or (not _build.is_current() and os.environ.get("B200SEG_NO_REBUILD") != "1"):
+    alt = os.environ.get("B200SEG_LIB_PATH")     # an alternative build of the same sources (A/B measurements of compile-time variants)
+    if alt:
+        path = alt
+    elif not os.path.exists(path) or (not _build.is_current() and os.environ.get("B200SEG_NO_REBUILD") != "1"):
         try:
             _build.build_library()
         except Exception as e:  # no nvcc: use a prebuilt .so if there is one, else fail loudly
