@@ -67,9 +67,11 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
   if (warp == kBulkConsumers / 32) {
     // ===================== producer warp: one bulk copy per class row + one for the labels, NS tiles ahead
     int k = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
-      const int s = k % NS;
-      if (k >= NS) mbar_wait(&empty_bar[s], ((k / NS) - 1) & 1);
+    StageRing ring;
+    ring.init(0, NS, 1);
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k, ring.advance()) {
+      const int s = ring.s;
+      if (k >= NS) mbar_wait(&empty_bar[s], ring.ph ^ 1);
       const int n = (int)(tile / p.tiles_per_image);
       const long long px0 = (tile - (long long)n * p.tiles_per_image) * kBulkPx;
       const int npx = (int)((HW - px0 < kBulkPx) ? HW - px0 : kBulkPx);
@@ -88,10 +90,12 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
   } else if (warp == kBulkConsumers / 32 + 1) {
     // ===================== store warp: one bulk store per class row once all consumers are done with the tile; a stage
     // goes back to the producer when the stores of the tile BEFORE have finished reading it (one tile of slack)
-    int k = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
-      const int s = k % NS;
-      mbar_wait(&done_bar[s], (k / NS) & 1);
+    int k = 0, prev_s = 0;
+    StageRing ring;
+    ring.init(0, NS, 1);
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k, prev_s = ring.s, ring.advance()) {
+      const int s = ring.s;
+      mbar_wait(&done_bar[s], ring.ph);
       const int n = (int)(tile / p.tiles_per_image);
       const long long px0 = (tile - (long long)n * p.tiles_per_image) * kBulkPx;
       const int npx = (int)((HW - px0 < kBulkPx) ? HW - px0 : kBulkPx);
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (k >= 1) {
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          mbar_arrive(&empty_bar[(k - 1) % NS]);
+          mbar_arrive(&empty_bar[prev_s]);
         }
       }
       __syncwarp();
@@ -115,9 +119,11 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
     const float Gs = p.ce_scale_host * (p.ce_grad_out ? __ldg(p.ce_grad_out) : 1.f);
     struct __align__(sizeof(T) * V) Pack { T v[V]; };
     int k = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
-      const int s = k % NS;
-      mbar_wait(&full_bar[s], (k / NS) & 1);
+    StageRing ring;
+    ring.init(0, NS, 1);
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k, ring.advance()) {
+      const int s = ring.s;
+      mbar_wait(&full_bar[s], ring.ph);
       const int n = (int)(tile / p.tiles_per_image);
       const long long px0 = (tile - (long long)n * p.tiles_per_image) * kBulkPx;
       const int npx = (int)((HW - px0 < kBulkPx) ? HW - px0 : kBulkPx);
