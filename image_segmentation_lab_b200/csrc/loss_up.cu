@@ -21,6 +21,11 @@
 namespace b200seg {
 
 // grad[n][c][y][x] = G * (cell(y,x).c11 + cell(y,x+1).c10 + cell(y+1,x).c01 + cell(y+1,x+1).c00)
+// Every cell is read from L2 exactly once: a warp owns 31 consecutive columns x 8 rows of one (n,c) plane; lane l loads
+// the cells of column x0 + l row by row (coalesced float4), its right neighbour's cell arrives by shuffle, and the row
+// above stays in registers. (The first version read the 4 cells of every logit separately: 4x the L2 traffic for the
+// 20 MB corner buffer, 10.8 us at config 2.)
+constexpr int kCombineRows = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) up_combine_kernel(const float* __restrict__ pb, T* __restrict__ grad, int NC, int h,
                                                          int w, float scale_host, const float* grad_out, int use_nvalid,
@@ -31,19 +36,33 @@ __global__ void __launch_bounds__(256) up_combine_kernel(const float* __restrict
     const double nv = (double)(long long)stats[B200SEG_ST_N_VALID];
     G = (float)((double)G / (nv + 1.1920928955078125e-07));
   }
-  const long long total = (long long)NC * h * w;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % w);
-    const long long t = idx / w;
-    const int y = (int)(t % h);
-    const long long nc = t / h;
+  const int lane = threadIdx.x & 31;
+  const int xt = (w + 30) / 31, yt = (h + kCombineRows - 1) / kCombineRows;
+  const long long tasks = (long long)NC * yt * xt;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long t = warp0; t < tasks; t += nwarps) {
+    const int tx = (int)(t % xt);
+    const long long r = t / xt;
+    const int ty = (int)(r % yt);
+    const long long nc = r / yt;
+    const int x = tx * 31 + lane;                 // cell column of this lane; logit column too for lanes 0..30
+    const int y0 = ty * kCombineRows;
+    const int ny = min(kCombineRows, h - y0);
     const float4* cells = reinterpret_cast<const float4*>(pb) + nc * (long long)(h + 1) * (w + 1);
-    const float4 c00 = cells[(long long)y * (w + 1) + x];            // cell (b=y,   r=x)   -> corner (1,1) = .w
-    const float4 c01 = cells[(long long)y * (w + 1) + x + 1];        // cell (b=y,   r=x+1) -> corner (1,0) = .z
-    const float4 c10 = cells[(long long)(y + 1) * (w + 1) + x];      // cell (b=y+1, r=x)   -> corner (0,1) = .y
-    const float4 c11 = cells[(long long)(y + 1) * (w + 1) + x + 1];  // cell (b=y+1, r=x+1) -> corner (0,0) = .x
-    grad[idx] = from_float<T>(G * ((c00.w + c01.z) + (c10.y + c11.x)));
+    const bool cin = x <= w;                      // cell columns run 0..w
+    float4 up = cin ? __ldg(cells + (long long)y0 * (w + 1) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float up_r_z = __shfl_down_sync(0xffffffffu, up.z, 1);
+    for (int i = 0; i < ny; ++i) {
+      const int y = y0 + i;
+      const float4 dn = cin ? __ldg(cells + (long long)(y + 1) * (w + 1) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float dn_r_x = __shfl_down_sync(0xffffffffu, dn.x, 1);
+      const float dn_r_z = __shfl_down_sync(0xffffffffu, dn.z, 1);
+      // cell (y,x).c11 = up.w | cell (y,x+1).c10 = right neighbour's up.z | cell (y+1,x).c01 = dn.y | cell (y+1,x+1).c00 = right dn.x
+      if (lane < 31 && x < w) grad[(nc * h + y) * (long long)w + x] = from_float<T>(G * ((up.w + up_r_z) + (dn.y + dn_r_x)));
+      up = dn;
+      up_r_z = dn_r_z;
+    }
   }
 }
 
@@ -94,8 +113,8 @@ long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {
 template <typename T>
 static int up_combine_t(const void* ws, void* grad, int N, int C, int h, int w, float scale_host, const float* grad_out,
                         int use_nvalid, const uint64_t* stats, cudaStream_t st) {
-  const long long total = (long long)N * C * h * w;
-  long long blocks = (total + 255) / 256;
+  const long long tasks = (long long)N * C * ((h + kCombineRows - 1) / kCombineRows) * ((w + 30) / 31);   // one per warp
+  long long blocks = (tasks + 7) / 8;
   if (blocks > kSMs * 8) blocks = kSMs * 8;
   if (blocks < 1) blocks = 1;
   up_combine_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(ws), reinterpret_cast<T*>(grad),

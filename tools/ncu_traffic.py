@@ -33,7 +33,9 @@ def short_name(full):
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     src = sys.argv[3] if len(sys.argv) > 3 else rep
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    # a report, or its `ncu -i X.ncu-rep --page raw --csv` dump made on the GPU box (reports with source exceed the 64 MiB
+    # that travel back)
+    raw = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
 
