@@ -51,17 +51,18 @@ __global__ void __launch_bounds__(256) up_combine_kernel(const float* __restrict
     const int ny = min(kCombineRows, h - y0);
     const float4* cells = reinterpret_cast<const float4*>(pb) + nc * (long long)(h + 1) * (w + 1);
     const bool cin = x <= w;                      // cell columns run 0..w
-    float4 up = cin ? __ldg(cells + (long long)y0 * (w + 1) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float up_r_z = __shfl_down_sync(0xffffffffu, up.z, 1);
-    for (int i = 0; i < ny; ++i) {
-      const int y = y0 + i;
-      const float4 dn = cin ? __ldg(cells + (long long)(y + 1) * (w + 1) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float dn_r_x = __shfl_down_sync(0xffffffffu, dn.x, 1);
-      const float dn_r_z = __shfl_down_sync(0xffffffffu, dn.z, 1);
+    // all rows of the strip are requested before the first is used (9 independent 16-byte loads in flight per lane)
+    float4 c[kCombineRows + 1];
+#pragma unroll
+    for (int i = 0; i <= kCombineRows; ++i)
+      c[i] = (cin && i <= ny) ? __ldg(cells + (long long)(y0 + i) * (w + 1) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kCombineRows; ++i) {
       // cell (y,x).c11 = up.w | cell (y,x+1).c10 = right neighbour's up.z | cell (y+1,x).c01 = dn.y | cell (y+1,x+1).c00 = right dn.x
-      if (lane < 31 && x < w) grad[(nc * h + y) * (long long)w + x] = from_float<T>(G * ((up.w + up_r_z) + (dn.y + dn_r_x)));
-      up = dn;
-      up_r_z = dn_r_z;
+      const float up_r_z = __shfl_down_sync(0xffffffffu, c[i].z, 1);
+      const float dn_r_x = __shfl_down_sync(0xffffffffu, c[i + 1].x, 1);
+      if (i < ny && lane < 31 && x < w)
+        grad[(nc * h + y0 + i) * (long long)w + x] = from_float<T>(G * ((c[i].w + up_r_z) + (c[i + 1].y + dn_r_x)));
     }
   }
 }
