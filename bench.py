@@ -222,23 +222,32 @@ class GraphRing:
             self.graphs.append(g)
         self.stats = [o['_stats'] for o in self.outs]
         self.comm = torch.cuda.Stream(device=dev)
-        self.ready = torch.cuda.Event()
-        self.packed = torch.cuda.Event()       # the side stream has read the cycle's statistics: their slots may be rewritten
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]   # the all-reduce that last used packed buffer 0 / 1 has finished
+        self.bufs = [torch.zeros(n_sets * self.stats[0].numel(), dtype=self.stats[0].dtype, device=dev) for _ in range(2)]
+        self.cycle = 0
         self.pending = []                      # ring slots whose statistics have not been reduced yet
         self.collectives = 0
 
     def _reduce_pending(self):
+        """Packs the pending steps' statistics on the COMPUTE stream (one small cat) and hands the packed buffer to the
+        side stream for the all-reduce; two packed buffers alternate, so the compute stream only ever waits for a
+        collective issued two cycles earlier."""
         if not self.pending:
             return
         cur = torch.cuda.current_stream()
-        self.ready.record(cur)
-        self.comm.wait_event(self.ready)
+        b = self.cycle & 1
+        cur.wait_event(self.done[b])
+        n = len(self.pending) * self.stats[0].numel()
+        buf = self.bufs[b][:n]
+        torch.cat([self.stats[i] for i in self.pending], out=buf)
+        self.ready[b].record(cur)
+        self.comm.wait_event(self.ready[b])
         with torch.cuda.stream(self.comm):
-            buf = torch.cat([self.stats[i] for i in self.pending])
-            self.packed.record(self.comm)
             self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM)
-        cur.wait_event(self.packed)
+            self.done[b].record(self.comm)
         self.pending = []
+        self.cycle += 1
         self.collectives += 1
 
     def run_step(self, k):

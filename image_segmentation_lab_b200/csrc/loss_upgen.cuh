@@ -25,7 +25,7 @@
 // and offset by the cell's maximum (every interpolated logit is a convex combination of its corners, so z <= 0).
 // Each cell's sums go once to PB[n][c][band][run] (float4); up_combine_kernel (loss_up.cu) adds the 4 cells around every
 // logit. A chunk falls back to DIRECT evaluation (FFMA + MUFU per class-pixel, exact per-pixel maxima) when the chain is
-// not applicable: a partially filled chunk at a ratio below PXC - 1, a class more than 120 log2-units below the cell maximum at either tap
+// not applicable: a partially filled chunk at a ratio below PXC - 1, a class more than 100 log2-units below the cell maximum at either tap
 // (its chain would leave the normal range), or an underflowing sum.
 //
 // Top-1: the label's class is the arg-max iff its exponential reaches the pixel's maximum exponential up to the chain's
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
 #pragma unroll
       for (int j = 0; j < PXC; ++j) { s[j] = 0.f; m[j] = 0.f; moff[j] = 0.f; }
       // a partially filled chunk still takes the chain when the lambdas of its masked tail stay <= 2 (then, with every
-      // tap >= -120 below the maximum, the tail's exponentials stay finite; their weights a[j] are 0)
+      // tap >= -100 below the maximum, the tail's exponentials stay finite; their weights a[j] are 0)
       bool fast = (npx == PXC) || (sx * (float)(PXC - 1) <= 1.f);
       if (fast) {
         // ---- forward sweep, geometric chain
@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
 #pragma unroll
           for (int j = 0; j < PXC; ++j) { s[j] += e[j]; m[j] = fmaxf(m[j], e[j]); }
         }
-        bool okc = minend >= -120.f;
+        // taps within 100 log2-units of the cell maximum: the chain stays in the normal range and the Horner partial sums of
+        // the backward sweep (<= weight / E0) stay finite
+        bool okc = minend >= -100.f;
 #pragma unroll
         for (int j = 0; j < PXC; ++j) okc = okc && (j >= npx || ((s[j] > 1e-30f) && (s[j] < 3.0e38f)));
         fast = okc;
@@ -298,11 +300,14 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
           for (int c = 0; c < C; ++c) {
             const float4 q = corn[c * cpc];
             const float L2 = fmaf(ly, q.z, q.x), D2 = fmaf(ly, q.w, q.y) - L2;
-            float e[PXC];
-            up_chain<PXC>(ex2(fmaf(lam0, D2, L2)), ex2(D2 * sx), e);
-            float gs = 0.f, gb = 0.f;
+            // sum_j a_j E0 R^j = E0 * A(R): the row's weighted sums are two polynomials in R (coefficients a_j >= 0 and
+            // a_j lambda_j >= 0, no cancellation) evaluated by Horner's rule — 2 (PXC - 1) FFMA instead of the product chain
+            // plus 2 PXC FFMA
+            const float E0 = ex2(fmaf(lam0, D2, L2)), R = ex2(D2 * sx);
+            float pa = a[PXC - 1], pb = bl[PXC - 1];
 #pragma unroll
-            for (int j = 0; j < PXC; ++j) { gs = fmaf(e[j], a[j], gs); gb = fmaf(e[j], bl[j], gb); }
+            for (int j = PXC - 2; j >= 0; --j) { pa = fmaf(pa, R, a[j]); pb = fmaf(pb, R, bl[j]); }
+            const float gs = E0 * pa, gb = E0 * pb;
             const float ga = gs - gb;
             float4* oh = OH + c * THR + tid;
             float4 o = *oh;
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(THR) up_gen_bwd_tile_kernel(const UpGenParams 
     }
     M2t = M * kLog2e;
     // the chain (and the per-pixel factor 2^(M2t - lse2) <= 2^(M2t - min)) stays in the normal range
-    chain_ok = (M - mn) * kLog2e <= 120.f;
+    chain_ok = (M - mn) * kLog2e <= 100.f;
     const float nM2 = -M2t;
     for (int c = rg; c < ct; c += RG) {
       const float4 v = CORN[c * cpc + cell];
@@ -487,11 +492,11 @@ __global__ void __launch_bounds__(THR) up_gen_bwd_tile_kernel(const UpGenParams 
         for (int c = 0; c < ct; ++c) {
           const float4 q = corn[c * cpc];
           const float L2 = fmaf(ly, q.z, q.x), D2 = fmaf(ly, q.w, q.y) - L2;
-          float e[PXC];
-          up_chain<PXC>(ex2(fmaf(lam0, D2, L2)), ex2(D2 * sx), e);
-          float gs = 0.f, gb = 0.f;
+          const float E0 = ex2(fmaf(lam0, D2, L2)), R = ex2(D2 * sx);     // Horner form of sum_j a_j E0 R^j (see up_gen_kernel)
+          float pa = a[PXC - 1], pb = bl[PXC - 1];
 #pragma unroll
-          for (int j = 0; j < PXC; ++j) { gs = fmaf(e[j], a[j], gs); gb = fmaf(e[j], bl[j], gb); }
+          for (int j = PXC - 2; j >= 0; --j) { pa = fmaf(pa, R, a[j]); pb = fmaf(pb, R, bl[j]); }
+          const float gs = E0 * pa, gb = E0 * pb;
           const float ga = gs - gb;
           float4* oh = OH + c * THR + tid;
           float4 o = *oh;

@@ -176,7 +176,10 @@ def test_class_sliced_pipeline_matches_oracle_and_streaming_kernels(B, dtype):
              ((1, 100, 32, 32), dict(avg_non_ignore=True), dict(ignore_index=3, class_weight=[0.7] * 100), False, torch.int32, 8.0),
              ((2, 70, 16, 24), dict(reduction='sum'), dict(smooth=2.0), False, torch.float32, 1.0),
              ((2, 150, 24, 40), dict(class_weight=torch.linspace(0.5, 1.5, 150).tolist()), dict(loss_weight=3.0), True, torch.int64, 1.0),
-             ((1, 33, 8, 16), {}, dict(), False, torch.int64, 1.0)]
+             ((1, 33, 8, 16), {}, dict(), False, torch.int64, 1.0),
+             # H*W = 136 / 168: the last tile's TMA box is only partly inside the image (out-of-range columns read as 0)
+             ((2, 40, 8, 17), {}, dict(), False, torch.int64, 1.0),
+             ((1, 150, 12, 14), dict(class_weight=torch.linspace(0.5, 1.5, 150).tolist()), dict(loss_weight=3.0), True, torch.int64, 1.0)]
     tol_l, tol_g = (LOSS_TOL, GRAD_TOL) if dtype == torch.float32 else (HALF_TOL, 2 * HALF_TOL)
     for shape, ce_kw, dice_kw, with_pw, ldt, scale in cases:
         n, c, h, w = shape
