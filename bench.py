@@ -14,7 +14,7 @@ side stream (--allreduce-every 1 issues it every step).
                 timed with CUDA events on the launching stream, max over ranks.
   e2e           the same step through the public API with HOST inputs: pinned H2D of logits + labels every step,
                 fused_resize_losses + backward, D2H read of the loss.
-  roofline      the dominant kernel (up_cell_kernel) timed alone with CUDA events: algorithmic bytes / time vs the
+  roofline      the dominant kernel (up_gen_kernel) timed alone with CUDA events: algorithmic bytes / time vs the
                 measured HBM copy peak (MEASURED_PEAKS.json).
   cpu_baseline  the oracle (the reference's ATen chain restated, oracle/oracle.py) on the host cores, bounded sample.
   workloads     extra single-GPU results for BASELINE configs 3, 4 and 5 (HBM-bound shapes), each with its roofline.
@@ -543,7 +543,7 @@ def flatten_workloads(line, extras):
 
 
 def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind):
-    """up_cell_kernel alone: b200seg_loss_fused_fwdbwd(defer_combine=1) launches exactly that kernel."""
+    """The resize-fused CE kernel (up_gen_kernel) alone: b200seg_loss_fused_fwdbwd(defer_combine=1) launches exactly it."""
     import ctypes as C
     dev = xs[0].device
     R = len(xs)
@@ -579,22 +579,22 @@ def kernel_roofline(lib, _lib, xs, ys, N, Cc, h, w, H, Wd, ign, peak, peak_kind)
     algo = 2 * N * Cc * h * w * s + N * H * Wd * 8          # logits read + gradient written + int64 labels read
     achieved = algo / (ms * 1e-3) / 1e9
     traffic, warp_inst, src = None, None, None
-    for name in ('traffic_r2.json', 'traffic_r1g.json'):   # DRAM bytes / warp instructions per launch from the committed ncu capture
+    for name in ('traffic_r2d.json', 'traffic_r2.json'):   # DRAM bytes / warp instructions per launch from the committed ncu capture
         try:
             with open(os.path.join(ROOT, 'profiles', name)) as fh:
                 ks = json.load(fh)['kernels']
-            k = next(v for kk, v in ks.items() if kk.startswith('up_cell_kernel<float, 5, 1'))
+            k = next(v for kk, v in ks.items() if kk.startswith('up_gen_kernel<float, 8, 1'))
             traffic, warp_inst, src = k['dram_bytes'], k['warp_inst'], 'profiles/' + name
             break
         except Exception:
             continue
-    out = {'bound': 'hbm', 'kernel': 'up_cell_kernel<float,CPT=5,GRAD,64 threads,int64 labels>', 'achieved': achieved, 'peak': peak,
+    out = {'bound': 'hbm', 'kernel': 'up_gen_kernel<float,PXC=8,GRAD,int64 labels,32 threads>', 'achieved': achieved, 'peak': peak,
            'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
            'traffic_source': (src + ' (ncu --set full capture of the same kernel and shape; not measured in this run)') if src else None,
            'peak_kind': peak_kind, 'ms_per_launch': ms,
            'algorithmic_bytes_per_launch': algo,
            'note': 'not HBM bound: with the logits at 1/8 resolution the only full-resolution tensor touched is the label map '
-                   '(33.6 of the 43.5 MB), while every output pixel owes C exponentials (MUFU) and ~11 issue slots per class; '
+                   '(33.6 of the 43.5 MB), while every output pixel owes ~9 issue slots per class plus ~100 of per-pixel scalar work; '
                    'see issue_frac and DESIGN.md. The HBM-bound kernels of the path are the c3_/c4_/c5 keys'}
     if warp_inst:
         sm_clock = 1.965e9

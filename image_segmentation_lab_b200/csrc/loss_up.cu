@@ -94,15 +94,14 @@ static bool up_fast_ok(int C, int h, int w, int H, int W, int ac) {
   if (H < h || W < w || (H == h && W == w)) return false;
   return true;
 }
-// Which kernel: the quad-per-cell kernel measures faster at power-of-two scales up to 8 with align_corners=False (config 2:
-// 80 vs 89 us), the thread-per-cell kernel at 16 and 32 (68 vs 76 us) and is the only one for everything else.
-// B200SEG_UPCELL=old|gen forces one of them where both apply (A/B measurements).
+// Which kernel: the thread-per-cell kernel (loss_upgen.cuh) everywhere — after the Horner-form backward sweep it measures
+// 77.8 us at config 2 against 80.1 us for the quad-per-cell kernel of round 1 (loss_upcell.cuh), 60.9 vs 75.8 us at scale
+// 16, 145.5 vs 147.4 us at scale 4, and it is the only one for other ratios / align_corners=True / C > 32.
+// B200SEG_UPCELL=old runs the round-1 kernel where it applies (A/B measurements, tests).
 static bool up_use_old(int C, int h, int w, int H, int W, int ac, int* S_out) {
   if (!up_pow2_ok(C, h, w, H, W, ac, S_out)) return false;
   const char* e = getenv("B200SEG_UPCELL");
-  if (e && e[0] == 'o') return true;
-  if (e && e[0] == 'g') return false;
-  return *S_out <= 8;
+  return e && e[0] == 'o';
 }
 
 long long up_fused_workspace(int N, int C, int h, int w, int H, int W, int ac) {
