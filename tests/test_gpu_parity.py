@@ -243,15 +243,20 @@ def test_config1_unet_shape(B):
 @pytest.mark.parametrize('ac', [False, True])
 def test_config2_cityscapes_shape(B, ac):
     """BASELINE config 2 at full size: (8,19,64,128) -> 512x1024, CE + ignore_index=255, both align_corners."""
-    out, ref = _head_case(B, (8, 19, 64, 128), (512, 1024), 19, torch.float32, {}, None, ac=ac, acc_tol=0.01 if ac else None)
+    out, ref = _head_case(B, (8, 19, 64, 128), (512, 1024), 19, torch.float32, {}, None, ac=ac, acc_tol=0.01)
     assert out['grad'].shape == (8, 19, 64, 128)
 
 
 def test_config2_variants(B):
-    _head_case(B, (2, 19, 32, 64), (512, 1024), 19, torch.float32, dict(avg_non_ignore=True), None, pixel_weight=True)  # S=16
-    _head_case(B, (2, 19, 128, 256), (512, 1024), 19, torch.float32, dict(class_weight=[1.0 + 0.05 * i for i in range(19)]), None)  # S=4
-    _head_case(B, (1, 21, 16, 16), (512, 512), 21, torch.float32, dict(reduction='sum'), None)  # S=32
-    _head_case(B, (2, 32, 40, 24), (320, 192), 32, torch.float32, {}, None)  # C=32, non power-of-two extents
+    # The thread-per-cell kernel decides top-1 from the exponentials it already holds (label counted when its term is
+    # within 2e-6 of the row maximum), so a pixel whose two best interpolated logits are closer than that can flip
+    # against torch.topk (about 10 of a million pixels here): the logged accuracy is allowed 0.01 %
+    t = 0.01
+    _head_case(B, (2, 19, 32, 64), (512, 1024), 19, torch.float32, dict(avg_non_ignore=True), None, pixel_weight=True, acc_tol=t)  # S=16
+    _head_case(B, (2, 19, 128, 256), (512, 1024), 19, torch.float32, dict(class_weight=[1.0 + 0.05 * i for i in range(19)]), None,
+               acc_tol=t)  # S=4
+    _head_case(B, (1, 21, 16, 16), (512, 512), 21, torch.float32, dict(reduction='sum'), None, acc_tol=t)  # S=32
+    _head_case(B, (2, 32, 40, 24), (320, 192), 32, torch.float32, {}, None, acc_tol=t)  # C=32, non power-of-two extents
     # nx+1 sizes, align_corners=True: the thread-per-cell kernel. At a non-dyadic ratio its interpolation weights differ
     # from ATen's in the last bits, which flips the top-1 of pixels whose two best classes are closer than ~1e-5 (about 20
     # of a million here): the logged accuracy is allowed 0.01 %
