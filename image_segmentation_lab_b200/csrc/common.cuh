@@ -384,6 +384,23 @@ __device__ __forceinline__ void cta_flush_stats(float loss, int n_valid, int n_c
   }
 }
 
+// The same for a CTA of ONE warp: no shared-memory hop, no barrier.
+__device__ __forceinline__ void warp_flush_stats(float loss, int n_valid, int n_correct, int n_bad, int n_acc,
+                                                 unsigned long long* stats) {
+  loss = warp_sum(loss);
+  n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+  n_correct = __reduce_add_sync(0xffffffffu, n_correct);
+  n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(reinterpret_cast<double*>(stats + B200SEG_ST_CE_SUM), (double)loss);
+    atomicAdd(stats + B200SEG_ST_N_VALID, (unsigned long long)n_valid);
+    if (n_bad) atomicAdd(stats + B200SEG_ST_N_BAD, (unsigned long long)n_bad);
+    atomicAdd(stats + B200SEG_ST_N_CORRECT, (unsigned long long)n_correct);
+    atomicAdd(stats + B200SEG_ST_N_ACC, (unsigned long long)n_acc);
+  }
+}
+
 // One-hot Dice sums of one pixel per lane into this warp's class bins: lanes holding the same class are found with one
 // MATCH.ANY, their p_y are added with one integer REDUX in Q23 fixed point (p_y <= 1, 32 lanes: no overflow; rounding
 // 6e-8 per term, unbiased), and the group's lowest lane does the two shared-memory updates. cls < 0 = nothing to add.
