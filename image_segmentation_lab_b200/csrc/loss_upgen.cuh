@@ -38,6 +38,8 @@
 // Bound: instruction issue; HBM traffic is the label map.
 // Algorithmic bytes per launch: 2*N*C*h*w*s + N*H*W*L.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_upcell.cuh"   // RawLabel / decode_label / lg2 / pixel_weight / kLn2
 
@@ -80,6 +82,7 @@ struct UpGenParams {
   UpFastDiv div_w1, div_h1;   // division by w + 1 / h + 1
   int ignore32;       // ignore_index as int32 (kNeverLabel if it does not fit: never matches)
   int acc_ignore32;   // accuracy's ignore_index, kNeverLabel when it has none
+  int dbg;
 };
 
 // ---- shared memory by 32-bit shared-window address. (With generic pointers into the dynamic segment the compiler re-derived
@@ -362,11 +365,13 @@ __device__ __forceinline__ void up_write_cell(const UpGenParams& p, const UpCell
     const int c2 = c + RGC;
     const bool two = c2 < ct;
     const unsigned oa = col0 + (unsigned)c * (unsigned)(THR * 16), ob = col0 + (unsigned)(two ? c2 : c) * (unsigned)(THR * 16);
+    // the RGC threads of a cell read different classes (512 bytes apart: the same banks), so thread rg starts at column rg:
+    // conflict-free, and still a fixed summation order per class
     float4 t[RGC], t2[RGC];
 #pragma unroll
-    for (int k = 0; k < RGC; ++k) t[k] = lds4(oa + (unsigned)k * 16u);
+    for (int k = 0; k < RGC; ++k) t[k] = lds4(oa + (unsigned)((k + g.rg) & (RGC - 1)) * 16u);
 #pragma unroll
-    for (int k = 0; k < RGC; ++k) t2[k] = lds4(ob + (unsigned)k * 16u);
+    for (int k = 0; k < RGC; ++k) t2[k] = lds4(ob + (unsigned)((k + g.rg) & (RGC - 1)) * 16u);
     float4 o = t[0], o2 = t2[0];
 #pragma unroll
     for (int k = 1; k < RGC; ++k) {
@@ -387,6 +392,39 @@ template <int LK> static __device__ __noinline__ int up_count_bad(const char* la
     n += (yy != ignore32 && (unsigned)yy >= (unsigned)C);
   }
   return n;
+}
+
+// ---- the PXC labels of a chunk. The kernel is bound by the L1 / shared-memory data pipe, and 8-byte label loads scattered
+// over the rows and cells of a warp cost it ~23 wavefronts per request: a full chunk is fetched with 16-byte loads (int64:
+// two labels, uint8: four) whenever its first label is suitably aligned, a quarter / half of the requests.
+template <int PXC, int LK>
+__device__ __forceinline__ void up_load_labels(const char* labimg, int dt, unsigned px0, int npx, RawLabel (&raw)[PXC]) {
+  if constexpr (LK == 0) {
+    const char* a = labimg + (size_t)px0 * 8;
+    if (npx == PXC && (reinterpret_cast<size_t>(a) & 15) == 0) {
+#pragma unroll
+      for (int k = 0; k < PXC / 2; ++k) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a) + k);
+        raw[2 * k].lo = v.x; raw[2 * k].hi = v.y;
+        raw[2 * k + 1].lo = v.z; raw[2 * k + 1].hi = v.w;
+      }
+      return;
+    }
+  }
+  if constexpr (LK == 1) {
+    const char* a = labimg + px0;
+    if (npx == PXC && (reinterpret_cast<size_t>(a) & 3) == 0) {
+#pragma unroll
+      for (int k = 0; k < PXC / 4; ++k) {
+        const unsigned v = __ldg(reinterpret_cast<const unsigned*>(a) + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { raw[4 * k + i].lo = (v >> (8 * i)) & 0xffu; raw[4 * k + i].hi = 0; }
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PXC; ++j) raw[j] = load_raw_label<LK>(labimg, dt, px0 + (unsigned)min(j, npx - 1));
 }
 
 struct UpAcc {
@@ -490,7 +528,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
   const unsigned corn = sm0 + (unsigned)g.cell * 16u;
   const unsigned oh_col = oh_base + (unsigned)tid * 16u;
   if constexpr (GRAD) {
-    for (int c = 0; c < Cp4; ++c) sts4(oh_col + (unsigned)c * (unsigned)(THR * 16), make_float4(0.f, 0.f, 0.f, 0.f));
+    if (!(p.dbg & 1)) for (int c = 0; c < Cp4; ++c) sts4(oh_col + (unsigned)c * (unsigned)(THR * 16), make_float4(0.f, 0.f, 0.f, 0.f));
   }
   __syncwarp();
   const float M2cell = M * kLog2e;
@@ -518,8 +556,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
       const int npx = min(PXC, g.X1 - Xc);
       // ---- labels of the chunk, issued before the class sweep (consumed after it)
       RawLabel raw[PXC];
-#pragma unroll
-      for (int j = 0; j < PXC; ++j) raw[j] = load_raw_label<LK>(labimg, dt, roff + (unsigned)(Xc + min(j, npx - 1)));
+      up_load_labels<PXC, LK>(labimg, dt, roff + (unsigned)Xc, npx, raw);
       const float lam0 = fmaf((float)(Xc - g.X0), sx, g.lx0);
       float wts[PXC];
 #pragma unroll
@@ -633,7 +670,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
 
   if constexpr (GRAD) {
     __syncwarp();
-    if (g.ok) {
+    if (g.ok && !(p.dbg & 2)) {
       if (RG == 4) up_write_cell<4, THR>(p, g, tid, oh_base, 0, C);
       else if (RG == 2) up_write_cell<2, THR>(p, g, tid, oh_base, 0, C);
       else up_write_cell<1, THR>(p, g, tid, oh_base, 0, C);
@@ -809,7 +846,8 @@ template <typename T, int PXC, bool GRAD, int LK> static int launch_upgen_lk(UpG
   }
   p.logRG = best;
   p.RG = 1 << best;
-  const size_t smem = upgen_smem_bytes<THR>(p.C, p.logRG, GRAD);
+  size_t smem = upgen_smem_bytes<THR>(p.C, p.logRG, GRAD);
+  if (const char* e = getenv("B200SEG_UPGEN_EXTRA_SMEM")) smem += (size_t)atoi(e);   // occupancy experiments
   auto k = up_gen_kernel<T, PXC, GRAD, LK, THR>;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)smem)) return e;
   const long long cells_per_cta = THR >> p.logRG;
@@ -841,6 +879,7 @@ template <typename T> int upgen_run(const b200seg_loss_desc* f, float* pb, bool 
   p.inv_sh = p.sh > 0.f ? 1.f / p.sh : 0.f;
   p.inv_sw = p.sw > 0.f ? 1.f / p.sw : 0.f;
   p.RG = 1; p.logRG = 0;
+  p.dbg = getenv("B200SEG_DBG") ? atoi(getenv("B200SEG_DBG")) : 0;
   p.cells = (long long)f->N * (f->h + 1) * (f->w + 1);
   p.div_w1 = up_fastdiv((unsigned)(f->w + 1));
   p.div_h1 = up_fastdiv((unsigned)(f->h + 1));
