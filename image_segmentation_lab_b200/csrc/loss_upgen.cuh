@@ -38,8 +38,6 @@
 // Bound: instruction issue; HBM traffic is the label map.
 // Algorithmic bytes per launch: 2*N*C*h*w*s + N*H*W*L.
 #pragma once
-#include <cstdlib>
-
 #include "common.cuh"
 #include "loss_upcell.cuh"   // RawLabel / decode_label / lg2 / pixel_weight / kLn2
 
@@ -82,7 +80,6 @@ struct UpGenParams {
   UpFastDiv div_w1, div_h1;   // division by w + 1 / h + 1
   int ignore32;       // ignore_index as int32 (kNeverLabel if it does not fit: never matches)
   int acc_ignore32;   // accuracy's ignore_index, kNeverLabel when it has none
-  int dbg;
 };
 
 // ---- shared memory by 32-bit shared-window address. (With generic pointers into the dynamic segment the compiler re-derived
@@ -528,7 +525,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
   const unsigned corn = sm0 + (unsigned)g.cell * 16u;
   const unsigned oh_col = oh_base + (unsigned)tid * 16u;
   if constexpr (GRAD) {
-    if (!(p.dbg & 1)) for (int c = 0; c < Cp4; ++c) sts4(oh_col + (unsigned)c * (unsigned)(THR * 16), make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int c = 0; c < Cp4; ++c) sts4(oh_col + (unsigned)c * (unsigned)(THR * 16), make_float4(0.f, 0.f, 0.f, 0.f));
   }
   __syncwarp();
   const float M2cell = M * kLog2e;
@@ -670,7 +667,7 @@ __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
 
   if constexpr (GRAD) {
     __syncwarp();
-    if (g.ok && !(p.dbg & 2)) {
+    if (g.ok) {
       if (RG == 4) up_write_cell<4, THR>(p, g, tid, oh_base, 0, C);
       else if (RG == 2) up_write_cell<2, THR>(p, g, tid, oh_base, 0, C);
       else up_write_cell<1, THR>(p, g, tid, oh_base, 0, C);
@@ -846,8 +843,7 @@ template <typename T, int PXC, bool GRAD, int LK> static int launch_upgen_lk(UpG
   }
   p.logRG = best;
   p.RG = 1 << best;
-  size_t smem = upgen_smem_bytes<THR>(p.C, p.logRG, GRAD);
-  if (const char* e = getenv("B200SEG_UPGEN_EXTRA_SMEM")) smem += (size_t)atoi(e);   // occupancy experiments
+  const size_t smem = upgen_smem_bytes<THR>(p.C, p.logRG, GRAD);
   auto k = up_gen_kernel<T, PXC, GRAD, LK, THR>;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), (int)smem)) return e;
   const long long cells_per_cta = THR >> p.logRG;
@@ -879,7 +875,6 @@ template <typename T> int upgen_run(const b200seg_loss_desc* f, float* pb, bool 
   p.inv_sh = p.sh > 0.f ? 1.f / p.sh : 0.f;
   p.inv_sw = p.sw > 0.f ? 1.f / p.sw : 0.f;
   p.RG = 1; p.logRG = 0;
-  p.dbg = getenv("B200SEG_DBG") ? atoi(getenv("B200SEG_DBG")) : 0;
   p.cells = (long long)f->N * (f->h + 1) * (f->w + 1);
   p.div_w1 = up_fastdiv((unsigned)(f->w + 1));
   p.div_h1 = up_fastdiv((unsigned)(f->h + 1));
