@@ -56,6 +56,12 @@ def main():
         rd, wr = col(r, 'dram__bytes_read.sum'), col(r, 'dram__bytes_write.sum')
         kernels[name] = {'dram_bytes_read': rd, 'dram_bytes_write': wr, 'dram_bytes': rd + wr,
                          'ncu_us': col(r, 'gpu__time_duration.sum'), 'warp_inst': col(r, 'smsp__inst_executed.sum', False)}
+        # the two units a non-HBM-bound kernel can sit on instead: the L1 / shared-memory data pipe and the issue slots
+        for key, metric in (('l1_data_pipe_pct', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'),
+                            ('issue_active_pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                            ('registers', 'launch__registers_per_thread')):
+            if metric in hdr:
+                kernels[name][key] = col(r, metric, False)
     with open(out, 'w') as fh:
         json.dump({'source': src, 'kernels': kernels}, fh, indent=1)
     print('wrote', out, list(kernels))
