@@ -6,11 +6,12 @@
 // never materialised in either direction, instead of the reference's ~10 passes over it (utils/ops.py:26,
 // cross_entropy_loss.py:56-61, accuracy.py:41 and their autograd backwards).
 //
-// Scope: logits at 1/S resolution, S a power of two in [4,32], align_corners=False (the decode-head call,
-// models/decode_heads/decode_head.py:266-269), C <= 32. Other ratios take the general kernels of loss_stream.cu.
+// Scope: logits at lower resolution than the labels (H >= h, W >= w), any ratio, both align_corners settings, C <= 512.
 //
-//   up_cell_kernel     (loss_upcell.cuh)  the single pass; writes each (band, run) cell's 4 corner gradient sums to
-//                                         PB[n][c][band][run] (float4), deterministic, no atomics
+//   up_gen_kernel      (loss_upgen.cuh)   the single pass (thread per cell on packed fp32 math); writes each (band, run)
+//                                         cell's 4 corner gradient sums to PB[n][c][band][run] (float4), deterministic,
+//                                         no atomics. C > 32: forward launch + up_gen_bwd_tile_kernel per 32 classes
+//   up_cell_kernel     (loss_upcell.cuh)  its round-1 predecessor (quad per cell, power-of-two scales): B200SEG_UPCELL=old
 //   up_combine_kernel  (here)             adds the 4 cells around every low-resolution logit and applies the global scale
 //                                         (upstream gradient, loss_weight, 1/denominator) -> grad_logits
 //   scale_inplace_kernel (here)           late scaling of an already produced gradient (flat single-pass plan)
@@ -94,9 +95,8 @@ static bool up_fast_ok(int C, int h, int w, int H, int W, int ac) {
   if (H < h || W < w || (H == h && W == w)) return false;
   return true;
 }
-// Which kernel: the thread-per-cell kernel (loss_upgen.cuh) everywhere — after the Horner-form backward sweep it measures
-// 77.8 us at config 2 against 80.1 us for the quad-per-cell kernel of round 1 (loss_upcell.cuh), 60.9 vs 75.8 us at scale
-// 16, 145.5 vs 147.4 us at scale 4, and it is the only one for other ratios / align_corners=True / C > 32.
+// Which kernel: the thread-per-cell kernel (loss_upgen.cuh) everywhere — 52.6 us at config 2 against 80.1 us for the
+// quad-per-cell kernel of round 1 (loss_upcell.cuh), and the only one for other ratios / align_corners=True / C > 32.
 // B200SEG_UPCELL=old runs the round-1 kernel where it applies (A/B measurements, tests).
 static bool up_use_old(int C, int h, int w, int H, int W, int ac, int* S_out) {
   if (!up_pow2_ok(C, h, w, H, W, ac, S_out)) return false;
