@@ -320,6 +320,27 @@ template <int V> __device__ __forceinline__ void load_labels(const void* p, int 
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (sm_90+)
+// A kernel launched with launch_pdl() may be scheduled while its predecessor in the stream is still draining; it must
+// call pdl_wait() before touching anything the predecessor wrote (no-op for a plain launch). A predecessor that calls
+// pdl_launch_dependents() lets that scheduling begin early; without it the dependents start when it exits.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------- reductions
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const CeBwdParams p) {
 // finalize: statistics -> scalars (models/losses/utils.py:48-80, accuracy.py:51-60, dice_loss.py:31-58)
 __global__ void __launch_bounds__(1024) finalize_kernel(const b200seg_finalize_desc d) {
   __shared__ double sred[32];
+  pdl_wait();      // scheduled under the tail of the loss kernel (programmatic dependent launch)
   const double eps = 1.1920928955078125e-07;  // torch.finfo(torch.float32).eps
   if (threadIdx.x == 0) {
     const double sum = *reinterpret_cast<const double*>(d.stats + B200SEG_ST_CE_SUM);
@@ -532,7 +533,7 @@ int ce_bwd_dispatch(const b200seg_loss_bwd_desc* d, cudaStream_t st) {
 int finalize_dispatch(const b200seg_finalize_desc* d, cudaStream_t st) {
   // one CTA; 1024 threads when there are thousands of (sample, class) Dice terms to walk (fp64 divisions), else 256
   const int threads = (d->dice_part != nullptr && (long long)d->N * d->C > 512) ? 1024 : 256;
-  finalize_kernel<<<1, threads, 0, st>>>(*d);
+  launch_pdl(finalize_kernel, dim3(1), dim3(threads), 0, st, *d);
   count_launch();
   return check_launch("finalize_kernel");
 }

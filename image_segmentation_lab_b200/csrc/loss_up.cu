@@ -31,6 +31,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) up_combine_kernel(const float* __restrict__ pb, T* __restrict__ grad, int NC, int h,
                                                          int w, float scale_host, const float* grad_out, int use_nvalid,
                                                          const unsigned long long* stats) {
+  pdl_wait();
   float G = scale_host;
   if (grad_out) G *= __ldg(grad_out);
   if (use_nvalid) {
@@ -117,9 +118,9 @@ static int up_combine_t(const void* ws, void* grad, int N, int C, int h, int w, 
   long long blocks = (tasks + 7) / 8;
   if (blocks > kSMs * 8) blocks = kSMs * 8;
   if (blocks < 1) blocks = 1;
-  up_combine_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(ws), reinterpret_cast<T*>(grad),
-                                                        N * C, h, w, scale_host, grad_out, use_nvalid,
-                                                        reinterpret_cast<const unsigned long long*>(stats));
+  launch_pdl(up_combine_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<const float*>(ws),
+             reinterpret_cast<T*>(grad), N * C, h, w, scale_host, grad_out, use_nvalid,
+             reinterpret_cast<const unsigned long long*>(stats));
   count_launch();
   return check_launch("up_combine_kernel");
 }

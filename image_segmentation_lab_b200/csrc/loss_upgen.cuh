@@ -512,6 +512,7 @@ __device__ __forceinline__ bool up_pixel_pass(const UpGenParams& p, const RawLab
 template <typename T, int PXC, bool GRAD, int LK, int THR>
 __global__ void __launch_bounds__(THR) up_gen_kernel(const UpGenParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();   // finalize may be scheduled as soon as SM resources free up; it waits for this grid itself
   const unsigned sm0 = (unsigned)__cvta_generic_to_shared(smem_raw);
   const int tid = threadIdx.x;
   const int C = p.C;
