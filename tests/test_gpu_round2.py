@@ -274,6 +274,70 @@ def test_resize_fused_any_ratio_single_pass(B, ac):
         assert rel_err(got[0], ref[0]) <= 2e-5 and rel_err(got[1], ref[1]) <= GRAD_TOL, sc
 
 
+def test_resize_fused_paths_of_the_packed_kernel(B):
+    """Code paths the packed-math kernel added (csrc/loss_upgen.cuh): class counts that need 0..3 pad classes, every row-group
+    count (1, 2, 4 threads per cell), labels outside [0, C) counted in the statistics and treated as ignored, long runs
+    of ignored pixels inside a chunk (the run-merged one-hot update), uint8 labels at all four alignments of a chunk, and
+    horizontal logit differences steep enough for R^(PXC/2) to overflow (cell-level fallback)."""
+    from image_segmentation_lab_b200 import _lib
+    # class counts: pads 3, 2, 1, 0; tiny class counts
+    for C in (1, 2, 3, 4, 17, 18, 20, 31):
+        got, ref = _up_case(B, (2, C, 12, 20), (96, 160), C, False, seed=C)
+        if C == 1:      # the reference's loss and gradient are exactly 0: absolute bounds (the chain rounds at 2^-23)
+            assert float(got[0].abs()) <= 1e-6 and float(got[1].abs().max()) <= 1e-9
+            continue
+        assert rel_err(got[0], ref[0]) <= LOSS_TOL and rel_err(got[1], ref[1]) <= GRAD_TOL, C
+    # row groups: scale 2 (1 thread per cell), scale 4 (2), scale 8 and 16 (4); a single cell column / row
+    for shape, size in (((1, 19, 40, 50), (80, 100)), ((1, 19, 40, 50), (160, 200)), ((1, 19, 20, 24), (160, 192)),
+                        ((1, 19, 6, 8), (96, 128)), ((1, 5, 1, 9), (16, 72)), ((1, 5, 9, 1), (72, 16))):
+        for ac in (False, True):
+            got, ref = _up_case(B, shape, size, shape[1], ac, seed=11)
+            assert rel_err(got[0], ref[0]) <= LOSS_TOL and rel_err(got[1], ref[1]) <= GRAD_TOL, (shape, size, ac)
+    # uint8 labels whose rows start at every alignment (W = 157: rows shift by 1 byte), int64 rows at odd offsets (W odd)
+    for ldt in (torch.uint8, torch.int64):
+        got, ref = _up_case(B, (2, 19, 10, 20), (80, 157), 19, False, ldt=ldt, seed=5)
+        assert rel_err(got[0], ref[0]) <= LOSS_TOL and rel_err(got[1], ref[1]) <= GRAD_TOL, ldt
+    # labels outside [0, C): counted, and ignored by the loss, its gradient and the accuracy numerator
+    x = synth_logits((2, 19, 16, 32), 21, device='cuda')
+    y = synth_labels((2, 128, 256), 19, 21, device='cuda')
+    y_bad = y.clone()
+    y_bad[:, 10:30, 40:44] = 77
+    y_bad[1, 100, :] = -3
+    n_bad = int(((y_bad != 255) & ((y_bad < 0) | (y_bad >= 19))).sum())
+    xa = x.clone().requires_grad_(True)
+    r = B.fused_resize_losses(xa, y_bad.unsqueeze(1), B.CrossEntropyLoss(), ignore_index=255, return_stats=True)
+    r['loss_ce'].backward()
+    assert int(r['_stats'][_lib.LOG_N_BAD]) == n_bad and n_bad > 0
+    y_ign = torch.where((y_bad < 0) | ((y_bad >= 19) & (y_bad != 255)), torch.full_like(y_bad, 255), y_bad)
+    xo = x.clone().requires_grad_(True)
+    full = O.resize(xo, size=(128, 256), mode='bilinear', align_corners=False)
+    lo = O.cross_entropy_loss_module(full, y_ign, ignore_index=255)
+    lo.backward()
+    assert rel_err(r['loss_ce'].detach(), lo.detach()) <= LOSS_TOL and rel_err(xa.grad, xo.grad) <= GRAD_TOL
+    # a label map that is mostly ignore_index, with isolated valid pixels (runs of length 1 between ignored stretches)
+    y_sparse = torch.full_like(y, 255)
+    y_sparse[:, ::3, ::5] = y[:, ::3, ::5]
+    xa = x.clone().requires_grad_(True)
+    r = B.fused_resize_losses(xa, y_sparse.unsqueeze(1), B.CrossEntropyLoss(avg_non_ignore=True), ignore_index=255)
+    r['loss_ce'].backward()
+    xo = x.clone().requires_grad_(True)
+    lo = O.cross_entropy_loss_module(O.resize(xo, size=(128, 256), mode='bilinear', align_corners=False), y_sparse, ignore_index=255,
+                                     avg_non_ignore=True)
+    lo.backward()
+    assert rel_err(r['loss_ce'].detach(), lo.detach()) <= LOSS_TOL and rel_err(xa.grad, xo.grad) <= GRAD_TOL
+    # neighbouring logits 60 nats apart along x at scale ~1.5: R^(PXC/2) leaves the normal range -> cell-level fallback
+    xs = synth_logits((1, 6, 8, 40), 4, device='cuda')
+    xs[:, :, :, ::2] += 60.0
+    ys = synth_labels((1, 12, 60), 6, 4, device='cuda')
+    xa = xs.clone().requires_grad_(True)
+    r = B.fused_resize_losses(xa, ys.unsqueeze(1), B.CrossEntropyLoss(), ignore_index=255)
+    r['loss_ce'].backward()
+    xo = xs.clone().requires_grad_(True)
+    lo = O.cross_entropy_loss_module(O.resize(xo, size=(12, 60), mode='bilinear', align_corners=False), ys, ignore_index=255)
+    lo.backward()
+    assert torch.isfinite(r['loss_ce']) and rel_err(r['loss_ce'].detach(), lo.detach()) <= 2e-5 and rel_err(xa.grad, xo.grad) <= GRAD_TOL
+
+
 def test_resize_fused_general_is_deterministic_and_matches_round1_kernel(B):
     """No atomics anywhere in the resize-fused backward: bitwise identical gradients run to run for align_corners=True and
     odd ratios; at power-of-two ratios the thread-per-cell kernel agrees with the round-1 quad-per-cell kernel."""
