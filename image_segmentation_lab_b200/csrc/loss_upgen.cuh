@@ -233,7 +233,7 @@ template <typename T> struct UpCornerLoad {
 #pragma unroll
     for (int u = 0; u < kUpLoadBatch; ++u) {
       const int c = cb + u * RG;
-      const unsigned co = (unsigned)(c < ct ? c : cb) * plane;
+      const unsigned co = (unsigned)(c < ct ? c : 0) * plane;       // idle slots re-read class 0 (always in range)
       v[u][0] = to_float<T>(__ldg(lg + (o00 + co)));
       v[u][1] = to_float<T>(__ldg(lg + (o01 + co)));
       v[u][2] = to_float<T>(__ldg(lg + (o10 + co)));
