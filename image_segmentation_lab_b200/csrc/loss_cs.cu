@@ -345,26 +345,40 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
           for (int q = 0; q < CsCfg<T>::kWords; ++q) ot.w[q] = __shfl_xor_sync(0xffffffffu, mx.w[q], o);
           cs_max<T>(mx, ot);
         }
-        float mh[PX], nm[PX], Sh[PX], Sb[PX];
+        float mh[PX], Sh[PX];
         cs_unpack<T>(mx, mh);
+        // sweeps 2 and 3 work on PIXEL PAIRS with the packed fp32 forms (FFMA2 / FADD2 / FMUL2: one issue slot for two
+        // pixels; same rounding as the scalar forms) — the forward is issue bound
+        constexpr int PP = PX / 2;
+        float2 nm2[PP], Sa2[PP], Sb2[PP];
+        const float2 l2e = make_float2(kLog2e, kLog2e);
 #pragma unroll
-        for (int v = 0; v < PX; ++v) { nm[v] = -mh[v] * kLog2e; Sh[v] = 0.f; Sb[v] = 0.f; }
+        for (int q = 0; q < PP; ++q) {
+          nm2[q] = make_float2(-mh[2 * q] * kLog2e, -mh[2 * q + 1] * kLog2e);
+          Sa2[q] = make_float2(0.f, 0.f);
+          Sb2[q] = make_float2(0.f, 0.f);
+        }
 
-        // sweep 2: exponentials (kept) and their sum (two partial sums per pixel: shorter dependent FADD chains)
-        float e[CPT][PX];
+        // sweep 2: exponentials (kept) and their sum (two partial sums per pixel: shorter dependent chains)
+        float2 e2[CPT][PP];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           float z[PX];
           cs_unpack<T>(zr[i], z);
 #pragma unroll
-          for (int v = 0; v < PX; ++v) {
-            e[i][v] = ex2(fmaf(z[v], kLog2e, nm[v]));
-            if (i & 1) Sb[v] += e[i][v];
-            else Sh[v] += e[i][v];
+          for (int q = 0; q < PP; ++q) {
+            const float2 x = __ffma2_rn(make_float2(z[2 * q], z[2 * q + 1]), l2e, nm2[q]);
+            e2[i][q] = make_float2(ex2(x.x), ex2(x.y));
+            if (i & 1) Sb2[q] = __fadd2_rn(Sb2[q], e2[i][q]);
+            else Sa2[q] = __fadd2_rn(Sa2[q], e2[i][q]);
           }
         }
 #pragma unroll
-        for (int v = 0; v < PX; ++v) Sh[v] += Sb[v];
+        for (int q = 0; q < PP; ++q) {
+          const float2 t = __fadd2_rn(Sa2[q], Sb2[q]);
+          Sh[2 * q] = t.x;
+          Sh[2 * q + 1] = t.y;
+        }
 #pragma unroll
         for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
@@ -373,15 +387,15 @@ __global__ void __launch_bounds__((kCsGroupWarps * G + 1) * 32, 1) cs_fwd_kernel
 
         // sweep 3: sum_px p^2 per class (Dice denominator: NOT masked by the valid mask, dice_loss.py:55-56)
         if (dice && in) {
-          float r[PX];
+          float2 r2[PP];
 #pragma unroll
-          for (int v = 0; v < PX; ++v) r[v] = fast_rcp(Sh[v]);
+          for (int q = 0; q < PP; ++q) r2[q] = make_float2(fast_rcp(Sh[2 * q]), fast_rcp(Sh[2 * q + 1]));
 #pragma unroll
           for (int i = 0; i < CPT; ++i) {
 #pragma unroll
-            for (int v = 0; v < PX; ++v) {
-              const float pr = e[i][v] * r[v];
-              acc[i] = fmaf(pr, pr, acc[i]);
+            for (int q = 0; q < PP; ++q) {
+              const float2 pr = __fmul2_rn(e2[i][q], r2[q]);
+              acc[i] = fmaf(pr.y, pr.y, fmaf(pr.x, pr.x, acc[i]));
             }
           }
         }
