@@ -18,11 +18,12 @@
 // Mapping. One thread owns one cell (or 1/RG of its rows). For a row of the cell and a class c the interpolated logits
 // of the run's pixels are z_j = L_c + lx_j D_c with lx_j EQUALLY SPACED (step = the horizontal scale), so their
 // exponentials are a geometric progression e_j = E_0 R^j: two MUFU.EX2 per class and row, then products instead of
-// FFMA + MUFU per class-pixel. The kernel is bound by instruction issue, so the class sweeps run on Blackwell's packed
-// fp32 pipe forms (FMUL2 / FADD2 / FFMA2: two pixels per issue slot) and the 3-input FMNMX3:
+// FFMA + MUFU per class-pixel. Issue slots are one of the two units the kernel sits on, so the class sweeps run on
+// Blackwell's packed fp32 pipe forms (FMUL2 / FADD2 / FFMA2: two pixels per issue slot) and the 3-input FMNMX3:
 //   forward sweep   per class: chain of PXC exponentials (3 FMUL + 3 FMUL2), PXC/2 FADD2 into the pixel sums, and — two
 //                   classes at a time — PXC FMNMX3 into the pixel maxima                      (~23 issue slots / class)
-//   per-pixel pass  label, its logit, loss, top-1, 1 / sum, one-hot term                      (~45 issue slots / pixel)
+//   per-pixel pass  label, its logit, loss, top-1, 1 / sum; one-hot terms folded once per RUN of equal labels
+//                                                                                             (~47 issue slots / pixel)
 //   backward sweep  per class: sum_j a_j E_0 R^j and sum_j a_j lambda_j E_0 R^j as ONE packed Horner recurrence
 //                   (PXC - 1 FFMA2), then one read-modify-write of the class's 4 corner sums in the thread's private
 //                   shared-memory column (2 FFMA2)                                            (~21 issue slots / class)
@@ -35,7 +36,9 @@
 //
 // Top-1: the label's class is the arg-max iff its exponential reaches the pixel's maximum exponential up to the chain's
 // rounding (2^-19 relative): exact and near ties count as correct (torch.topk's choice among ties is unspecified).
-// Bound: instruction issue; HBM traffic is the label map.
+// Bound (ncu, config 2): the L1 / shared-memory data pipe at 67 % (every 16-byte-per-lane shared access is 4 wavefronts:
+// the private sums' read-modify-write per class and row is the bulk) and instruction issue at 57 %; HBM traffic is the
+// label map. What the data pipe dictated: 16-byte label loads, a bank-conflict-free column order in the cell write-out.
 // Algorithmic bytes per launch: 2*N*C*h*w*s + N*H*W*L.
 #pragma once
 #include "common.cuh"
