@@ -19,7 +19,7 @@ WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 MODE_DICE, MODE_TVERSKY = 0, 1
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 12
+ABI_VERSION = 13
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -156,7 +156,7 @@ SYMBOLS = [
      [_p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _i64, C.POINTER(_i32), _i32, _i32, _f, _p, _p]),
     ("b200seg_bce_fwd", C.c_int, [C.POINTER(BceDesc), _p]),
     ("b200seg_bce_bwd", C.c_int, [C.POINTER(BceDesc), _p]),
-    ("b200seg_lovasz_workspace_bytes", _i64, [_i64, _i32, _i32]),
+    ("b200seg_lovasz_workspace_bytes", _i64, [_i32, _i32, _i64, _i32, _i32]),
     ("b200seg_lovasz_fwd", C.c_int, [C.POINTER(LovaszDesc), _p]),
     ("b200seg_lovasz_bwd", C.c_int, [C.POINTER(LovaszBwdDesc), _p]),
     ("b200seg_last_error", C.c_char_p, []),

@@ -60,7 +60,7 @@ int up_combine_dispatch(const void* ws, void* grad, int dtype, int N, int C, int
 int scale_inplace_dispatch(void* x, int dtype, long long n, const float* g, cudaStream_t st);
 int lovasz_fwd_dispatch(const b200seg_lovasz_desc* d, cudaStream_t st);
 int lovasz_bwd_dispatch(const b200seg_lovasz_bwd_desc* d, cudaStream_t st);
-long long lovasz_workspace_bytes(long long seg_len, int segs, int pairs);
+long long lovasz_workspace_bytes(int N, int C, long long HW, int per_image, int pairs);
 bool bulk_supported(const void* logits, const void* labels, const void* grad, int logit_dtype, int label_dtype, int C,
                     long long HW, bool has_pixel_weight);
 
@@ -215,8 +215,8 @@ extern "C" int b200seg_scale_inplace(void* x, int32_t dtype, int64_t n, const fl
   return scale_inplace_dispatch(x, dtype, n, g, (cudaStream_t)stream);
 }
 
-extern "C" int64_t b200seg_lovasz_workspace_bytes(int64_t seg_len, int32_t segments, int32_t pairs) {
-  return lovasz_workspace_bytes(seg_len, segments, pairs);
+extern "C" int64_t b200seg_lovasz_workspace_bytes(int32_t N, int32_t C, int64_t HW, int32_t per_image, int32_t pairs) {
+  return lovasz_workspace_bytes(N, C, HW, per_image, pairs);
 }
 
 extern "C" int b200seg_lovasz_fwd(const b200seg_lovasz_desc* d, void* stream) {
@@ -233,8 +233,7 @@ extern "C" int b200seg_lovasz_fwd(const b200seg_lovasz_desc* d, void* stream) {
   B200SEG_REQUIRE(!(d->per_image && d->has_avg_factor && d->reduction == B200SEG_RED_SUM),
                   "avg_factor can not be used with reduction=\"sum\"");   // models/losses/utils.py:78-79
   B200SEG_REQUIRE(d->seg_stats && d->out, "lovasz_fwd: NULL seg_stats / out");
-  const long long seg_len = (long long)d->N * d->HW;   // keys per sort (per_image: all images of a class in one sort)
-  B200SEG_REQUIRE(seg_len < 2147483647LL, "lovasz_fwd: %lld pixels per sort exceed 2^31-1", seg_len);
+  B200SEG_REQUIRE((long long)d->N * d->HW < 2147483647LL, "lovasz_fwd: %lld pixels exceed 2^31-1", (long long)d->N * d->HW);
   if (d->N > 0 && d->HW > 0) {
     B200SEG_REQUIRE(d->logits && d->labels && d->lab16 && d->workspace, "lovasz_fwd: NULL tensor");
     B200SEG_REQUIRE(d->binary || d->lse, "lovasz_fwd: the multi-class loss needs the per-pixel log-sum-exp");

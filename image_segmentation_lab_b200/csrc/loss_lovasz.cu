@@ -1,4 +1,5 @@
-// Lovasz-Softmax / Lovasz hinge loss (the tail of SURVEY 8 f4), sm_100a.
+// Lovasz-Softmax / Lovasz hinge loss (the tail of SURVEY 8 f4), sm_100a. Every kernel in this file is hand-written;
+// no library sort (round 1 called cub::DeviceRadixSort once per class: 73 % of the time of this row).
 //
 // Replaces models/losses/lovasz_loss.py:26-234. Per class c the reference materialises softmax(N,C,H,W), permutes it to
 // (P,C), compacts the valid pixels (boolean index + nonzero), then for every class builds fg = (labels == c),
@@ -7,16 +8,23 @@
 // (P,)-sized temporaries per class in a Python loop, a host sync per class for 'present' (:153), and an autograd graph
 // that walks all of it backwards.
 //
-// Here, per (image group g, class c) SEGMENT (one group = the whole batch, or one image when per_image=True; in that
-// case all images of a class are ordered by ONE sort of 64-bit keys with the image index in the high word):
+// Here one SEGMENT is a (class c, image group g) pair — one group = the whole batch, or one image when per_image=True —
+// and ALL segments of a batch of classes go through every kernel together (grid.y / a ticket = the segment), so that a
+// launch covers tens of millions of items and streams at HBM rate instead of paying launch tails per class:
+//   lovasz_prep_kernel   labels (any dtype) -> int16 class ids.
 //   lovasz_keys_kernel   p_c = ex2(z_c*log2e - lse*log2e) from the logits row of class c and the per-pixel log-sum-exp of
 //                        ONE forward pass (b200seg_loss_fwd, WANT_LSE); error and foreground bit packed into one 32-bit
 //                        sort key:  key = ((bits(e) + 1) << 1) | fg  (e >= 0, so its fp32 bit pattern is monotone;
-//                        lossless); ignored pixels get key 0 and sink to the end of the descending order.
-//   cub::DeviceRadixSort 4 digit passes over (key, pixel index) pairs — keys only when no gradient is wanted. A segment
-//                        of a 512x1024x8 batch is 4 M pairs = 64 MB for both buffers of both arrays: L2 resident on B200,
-//                        which is why segments are sorted one at a time instead of as one (class, error) 64-bit sort.
-//                        (Library code: the CUDA toolkit's CUB, compiled into this .so; everything else is hand-written.)
+//                        lossless); ignored pixels get key 0 and sink to the end of the descending order. The same
+//                        kernel counts the digit histograms of EVERY sort pass (warp-private counters fed by
+//                        match.any groups: no shared-memory atomics), so the keys are not read again for them.
+//   lov_hist_scan_kernel exclusive scan of each (pass, segment) histogram -> first output slot of every digit value.
+//   lov_sort_pass_kernel one least-significant-digit radix pass, stable, over (key, pixel index) pairs — keys only when
+//                        no gradient is wanted — for all segments at once. Single read / single write per pass: a tile
+//                        (256 threads x ITEMS) ranks its items with match.any groups against warp-private counters,
+//                        publishes its digit counts, orders the tile in shared memory while the counts of the tiles
+//                        before it are collected by a decoupled look-back (tiles take their index from a ticket
+//                        counter, so every tile waited for is already resident), and writes runs of equal digits.
 //   lovasz_count_kernel / lovasz_tilescan_kernel / lovasz_grad_kernel
 //                        exclusive scan of the foreground bits over the sorted order (tile counts -> one-CTA scan ->
 //                        per-tile rescan), then with EXACT integer counts cum_i = #fg in [0,i], I_i = gts - cum_i,
@@ -25,7 +33,7 @@
 //                            g_i = I_i/(U_i (U_i-1))  (fg_i = 0),   g_0 = 1 - I_0/U_0
 //                        (the reference's fp32 J_i - J_{i-1} cancels catastrophically: for P = 4 M its increments carry
 //                        ~25 % noise; its cumsums stop being exact at 2^24), loss_c = sum e_i g_i, and
-//                        dloss_c/dp_c = -+g_i scattered to the pixel's slot of G (C,N,H,W) f32 (class-major: a segment
+//                        dloss_c/dp_c = -+g_i scattered to the pixel's slot of G (C,N,HW) f32 (class-major: a segment
 //                        is one contiguous slice, the scatter index is the sorted value itself).
 //   lovasz_finalize_kernel  mean over the present / all / listed classes, class weights, per-image reduction
 //                        (weight_reduce_loss), and the coefficient table of the backward. No host sync anywhere.
@@ -34,8 +42,9 @@
 // float->uint key and the foreground bit in the value's top bit.
 //
 // Ties: the loss is invariant to the order inside a block of equal errors (the block's increments telescope); the
-// gradient is not (neither is the reference's: torch.sort's order among ties is unspecified).
-#include <cub/device/device_radix_sort.cuh>
+// gradient is not (neither is the reference's: torch.sort's order among ties is unspecified). The sort here is stable
+// and deterministic: equal errors keep pixel order.
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -68,100 +77,413 @@ __global__ void __launch_bounds__(256) lovasz_prep_kernel(const void* __restrict
   lab16[i] = r;
 }
 
-// ---------------------------------------------------------------------------------------------- sort keys
+// ---------------------------------------------------------------------------------------------- radix sort geometry
+// Descending order = ascending order of the complemented key: digit(pass) = (~key >> pass*RB) & (2^RB - 1).
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+template <int RB> struct SortGeo {
+  static constexpr int NB = 1 << RB;                 // digit values per pass
+  static constexpr int NP = (32 + RB - 1) / RB;      // passes over a 32-bit key
+  static constexpr int BPT = NB / kSortThreads;      // digit values owned by a thread in the scans (RB >= 8)
+  static_assert(RB >= 8 && RB <= 11, "digit width");
+};
+__device__ __forceinline__ uint32_t sort_digit(uint32_t key, int shift, uint32_t mask) { return ((~key) >> shift) & mask; }
+
+// lanes of the warp holding the same digit. MODE 0: match.any; MODE 1: one ballot per digit bit
+template <int RB, int MODE> __device__ __forceinline__ unsigned digit_peers(uint32_t d) {
+  if constexpr (MODE == 0) {
+    return __match_any_sync(0xffffffffu, d);
+  } else {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < RB + 1; ++k) {                 // RB + 1: the "nothing to count" value 2^RB of the histogram kernel
+      const bool bit = (d >> k) & 1u;
+      const unsigned b = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? b : ~b;
+    }
+    return peers;
+  }
+}
+// warp-private digit count: the lanes holding the same digit form a group, its lowest lane adds the group
+// size to the warp's counter of that digit. Lanes with d >= NB (nothing to count) group among themselves and are skipped.
+template <int RB, int MODE>
+__device__ __forceinline__ void warp_count_digit(uint16_t* __restrict__ wcnt, uint32_t d, uint32_t nb, int lane) {
+  const unsigned peers = digit_peers<RB, MODE>(d);
+  if (d < nb && lane == __ffs(peers) - 1) wcnt[d] = (uint16_t)(wcnt[d] + __popc(peers));
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------- sort keys + histograms
 struct LovKeysParams {
   const void* logits;     // (N,C,HW) multi-class, (N,HW) binary
   const float* lse;       // (N,HW), multi-class only
   const int16_t* lab16;   // (N,HW)
-  void* keys;             // (imgs * HW) uint32, or uint64 in batched mode
+  uint32_t* keys;         // (segments, len)
   uint32_t* vals;         // same count, or NULL (keys only)
-  long long HW;
-  int C, c;
-  int n_img;              // number of images in the launch (batched mode: = segments)
+  uint32_t* hist;         // (passes, segments, 2^RB), zeroed by the caller
+  long long HW, len;      // pixels per image, items per segment
+  int C, c0;              // classes of the tensor, first class of this batch of classes
+  int groups, nseg;       // image groups per class (1, or N when per_image), segments = classes in the batch * groups
+  int chunk;              // items per CTA (a multiple of 256 * V)
 };
 
-// KeyT = uint32_t: one segment per launch (the images blockIdx.y of one group are concatenated, value = index in the group).
-// KeyT = uint64_t: BATCHED per-image mode — every image is its own segment, all of them sorted by ONE radix sort: the
-// high word carries (n_img - 1 - image) so that the descending order lists image 0 first; value = pixel index in the image.
-template <typename T, int V, bool BINARY, typename KeyT>
-__global__ void __launch_bounds__(256) lovasz_keys_kernel(const LovKeysParams p) {
-  constexpr bool kBatched = sizeof(KeyT) == 8;
-  const int nl = blockIdx.y;
-  const long long hw0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (hw0 >= p.HW) return;
-  const size_t n = (size_t)nl;
-  const size_t px = n * p.HW + hw0;
-  const T* zp = reinterpret_cast<const T*>(p.logits) + (BINARY ? px : (n * p.C + p.c) * p.HW + hw0);
-  float z[V];
-  load_vec<T, V>(zp, z);
-  int lab[V];
-  if constexpr (V == 4) {
-    const uint2 r = ld_stream8(p.lab16 + px);
-    lab[0] = (int16_t)(r.x & 0xffffu); lab[1] = (int16_t)(r.x >> 16);
-    lab[2] = (int16_t)(r.y & 0xffffu); lab[3] = (int16_t)(r.y >> 16);
-  } else {
-    lab[0] = p.lab16[px];
+// grid (chunks per segment, segments). Segment s = (class c0 + s / groups, group s % groups); its items are the pixels
+// g * len + i of the flat (N,HW) maps. value = index inside the segment (binary: | foreground << 31).
+template <typename T, int V, bool BINARY, int RB, int MODE>
+__global__ void __launch_bounds__(kSortThreads) lovasz_keys_kernel(const LovKeysParams p) {
+  using G = SortGeo<RB>;
+  extern __shared__ __align__(16) unsigned char lov_smem[];
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(lov_smem);                 // [NP][warps][NB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    uint4* z = reinterpret_cast<uint4*>(lov_smem);
+    for (int i = tid; i < G::NP * kSortWarps * G::NB / 8; i += kSortThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  uint32_t key[V], val[V];
-  const size_t i0 = (size_t)nl * p.HW + hw0;                               // slot in the key / value arrays
-  const uint32_t v0 = kBatched ? (uint32_t)hw0 : (uint32_t)i0;             // index inside the segment
-  if constexpr (BINARY) {
+  __syncthreads();
+  const int s = blockIdx.y;
+  const int cj = s / p.groups, g = s - cj * p.groups;
+  const int c = p.c0 + cj;
+  const long long start = (long long)blockIdx.x * p.chunk;
+  const long long end = min(p.len, start + (long long)p.chunk);
+  const size_t seg0 = (size_t)s * (size_t)p.len;
+  for (long long base = start; base < end; base += kSortThreads * V) {
+    const long long i = base + (long long)tid * V;
+    const bool active = i < end;                       // len % V == 0: a thread's V items are all inside or all outside
+    uint32_t key[V], val[V];
+    if (active) {
+      const long long fp = (long long)g * p.len + i;   // flat pixel in (N,HW)
+      const long long n = p.groups > 1 ? (long long)g : fp / p.HW;
+      const long long hw = fp - n * p.HW;
+      const T* zp = reinterpret_cast<const T*>(p.logits) + (BINARY ? (size_t)fp : ((size_t)n * p.C + c) * p.HW + hw);
+      float z[V];
+      load_vec<T, V>(zp, z);
+      int lab[V];
+      if constexpr (V == 4) {
+        const uint2 r = ld_stream8(p.lab16 + fp);
+        lab[0] = (int16_t)(r.x & 0xffffu); lab[1] = (int16_t)(r.x >> 16);
+        lab[2] = (int16_t)(r.y & 0xffffu); lab[3] = (int16_t)(r.y >> 16);
+      } else {
+        lab[0] = p.lab16[fp];
+      }
+      if constexpr (BINARY) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const uint32_t fg = lab[v] != 0 && lab[v] != kLovIgnored;       // labels are 0 / 1 (:78-79)
-      const float sign = fg ? 1.f : -1.f;
-      key[v] = lab[v] == kLovIgnored ? 0u : hinge_key(1.f - z[v] * sign);
-      val[v] = (v0 + v) | (fg << 31);
-    }
-  } else {
-    float l[V];
-    load_vec<float, V>(p.lse + px, l);
+        for (int v = 0; v < V; ++v) {
+          const uint32_t fg = lab[v] != 0 && lab[v] != kLovIgnored;       // labels are 0 / 1 (:78-79)
+          const float sign = fg ? 1.f : -1.f;
+          key[v] = lab[v] == kLovIgnored ? 0u : hinge_key(1.f - z[v] * sign);
+          val[v] = ((uint32_t)i + v) | (fg << 31);
+        }
+      } else {
+        float l[V];
+        load_vec<float, V>(p.lse + fp, l);
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const float pc = ex2(fmaf(z[v], kLog2e, -l[v] * kLog2e));
-      const uint32_t fg = lab[v] == p.c;
-      const float e = fabsf((fg ? 1.f : 0.f) - pc);
-      key[v] = lab[v] == kLovIgnored ? 0u : (((__float_as_uint(e) + 1u) << 1) | fg);
-      val[v] = v0 + v;
-    }
-  }
-  KeyT* kout = reinterpret_cast<KeyT*>(p.keys) + i0;
-  if constexpr (kBatched) {
-    const uint32_t hi = (uint32_t)(p.n_img - 1 - nl);
-    if constexpr (V == 4) {
-      reinterpret_cast<uint4*>(kout)[0] = make_uint4(key[0], hi, key[1], hi);
-      reinterpret_cast<uint4*>(kout)[1] = make_uint4(key[2], hi, key[3], hi);
+        for (int v = 0; v < V; ++v) {
+          const float pc = ex2(fmaf(z[v], kLog2e, -l[v] * kLog2e));
+          const uint32_t fg = lab[v] == c;
+          const float e = fabsf((fg ? 1.f : 0.f) - pc);
+          key[v] = lab[v] == kLovIgnored ? 0u : (((__float_as_uint(e) + 1u) << 1) | fg);
+          val[v] = (uint32_t)i + v;
+        }
+      }
+      uint32_t* kout = p.keys + seg0 + i;
+      if constexpr (V == 4) *reinterpret_cast<uint4*>(kout) = make_uint4(key[0], key[1], key[2], key[3]);
+      else kout[0] = key[0];
+      if (p.vals) {
+        if constexpr (V == 4) *reinterpret_cast<uint4*>(p.vals + seg0 + i) = make_uint4(val[0], val[1], val[2], val[3]);
+        else p.vals[seg0 + i] = val[0];
+      }
     } else {
-      kout[0] = ((KeyT)hi << 32) | key[0];
+#pragma unroll
+      for (int v = 0; v < V; ++v) key[v] = 0u;
+    }
+#pragma unroll
+    for (int ps = 0; ps < G::NP; ++ps) {
+      uint16_t* wcnt = cnt + ((size_t)ps * kSortWarps + warp) * G::NB;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+      {
+        if constexpr (MODE == 2) {
+          if (active) atomicAdd(reinterpret_cast<uint32_t*>(lov_smem) + ps * G::NB + sort_digit(key[v], ps * RB, G::NB - 1), 1u);
+        } else {
+          warp_count_digit<RB, MODE>(wcnt, active ? sort_digit(key[v], ps * RB, G::NB - 1) : (uint32_t)G::NB, G::NB, lane);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < G::NP * G::NB; k += kSortThreads) {
+    const int ps = k / G::NB, b = k - ps * G::NB;
+    uint32_t t = 0;
+    if constexpr (MODE == 2) {
+      t = reinterpret_cast<uint32_t*>(lov_smem)[k];
+    } else {
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) t += cnt[((size_t)ps * kSortWarps + w) * G::NB + b];
+    }
+    if (t) atomicAdd(p.hist + ((size_t)ps * p.nseg + s) * G::NB + b, t);
+  }
+}
+
+// grid = passes * segments: exclusive scan of one histogram in place (first output slot of every digit value)
+template <int RB>
+__global__ void __launch_bounds__(kSortThreads) lov_hist_scan_kernel(uint32_t* __restrict__ hist) {
+  using G = SortGeo<RB>;
+  __shared__ uint32_t s_w[kSortWarps];
+  uint32_t* h = hist + (size_t)blockIdx.x * G::NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t v[G::BPT], tsum = 0;
+#pragma unroll
+  for (int b = 0; b < G::BPT; ++b) { v[b] = h[tid * G::BPT + b]; tsum += v[b]; }
+  uint32_t x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  uint32_t run = x - tsum;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) run += (w < warp) ? s_w[w] : 0u;
+#pragma unroll
+  for (int b = 0; b < G::BPT; ++b) { h[tid * G::BPT + b] = run; run += v[b]; }
+}
+
+// ---------------------------------------------------------------------------------------------- one radix pass
+struct LovSortParams {
+  const uint32_t* kin; uint32_t* kout;
+  const uint32_t* vin; uint32_t* vout;     // PAIRS only
+  const uint32_t* base;   // (segments, NB): first slot of every digit value inside the segment, this pass
+  uint32_t* desc;         // (segments * tiles, NB): (count << 2) | state, zeroed by the caller; state 1 = this tile's
+                          // own count, 2 = the count of this tile and all tiles before it in the segment
+  uint32_t* ticket;       // zeroed by the caller
+  long long len;          // items per segment (< 2^30)
+  int tiles;              // tiles per segment
+  int shift;
+};
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int RB, int ITEMS, bool PAIRS> struct SortSmem {
+  using G = SortGeo<RB>;
+  static constexpr int TILE = kSortThreads * ITEMS;
+  static constexpr int CNT_BYTES = kSortWarps * G::NB * 2;
+  static constexpr int BYTES = CNT_BYTES + (PAIRS ? 2 : 1) * TILE * 4 + 2 * G::NB * 4;
+};
+
+// One tile = 256 threads x ITEMS consecutive items of one segment, order inside the tile = (warp, item, lane).
+// MODE: how the lanes with equal digits find each other (digit_peers). MINB: CTAs per SM the register budget allows.
+// EARLYV: the values are requested with the keys (more registers live through the ranking) instead of after it.
+template <int RB, int ITEMS, bool PAIRS, int MODE, int MINB, bool EARLYV>
+__global__ void __launch_bounds__(kSortThreads, MINB) lov_sort_pass_kernel(const LovSortParams p) {
+  using G = SortGeo<RB>;
+  using SM = SortSmem<RB, ITEMS, PAIRS>;
+  constexpr int NB = G::NB, BPT = G::BPT, TILE = SM::TILE;
+  constexpr uint32_t MASK = NB - 1;
+  static_assert(ITEMS % 2 == 0, "ranks are kept in 16-bit pairs");
+  extern __shared__ __align__(16) unsigned char lov_smem[];
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(lov_smem);                         // [warps][NB]
+  uint32_t* exk = reinterpret_cast<uint32_t*>(lov_smem + SM::CNT_BYTES);         // [TILE] keys in tile order
+  uint32_t* exv = exk + TILE;                                                    // [TILE] values (PAIRS)
+  uint32_t* binstart = exk + (PAIRS ? 2 : 1) * TILE;                             // [NB]
+  uint32_t* gdelta = binstart + NB;                                              // [NB]
+  __shared__ uint32_t s_ticket;
+  __shared__ uint32_t s_w[kSortWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+  {
+    uint4* z = reinterpret_cast<uint4*>(lov_smem);
+    for (int i = tid; i < SM::CNT_BYTES / 16; i += kSortThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const uint32_t gt = s_ticket;                        // global tile number: tiles are taken in segment-major order
+  const int s = (int)(gt / (uint32_t)p.tiles), tile = (int)(gt - (uint32_t)s * (uint32_t)p.tiles);
+  const size_t seg0 = (size_t)s * (size_t)p.len;
+  const long long tile0 = (long long)tile * TILE;
+  const int nvalid = (int)min((long long)TILE, p.len - tile0);
+  const int shift = p.shift;
+
+  // ---- load (coalesced: lane-strided inside the warp's slice) and rank. Items past the end take key 0: the largest
+  // digit of the pass, and being last in tile order they land behind every real item.
+  const long long w0 = tile0 + (long long)warp * (32 * ITEMS) + lane;
+  const bool full = tile0 + TILE <= p.len;
+  uint32_t key[ITEMS], val[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const long long i = w0 + j * 32;
+    key[j] = (full || i < p.len) ? __ldcs(p.kin + seg0 + i) : 0u;
+  }
+  if constexpr (PAIRS && EARLYV) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const long long i = w0 + j * 32;
+      val[j] = (full || i < p.len) ? __ldcs(p.vin + seg0 + i) : 0u;
+    }
+  }
+  uint32_t rk[ITEMS / 2];                              // rank of the item among the warp's items with the same digit
+  uint16_t* wcnt = cnt + warp * NB;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t d = sort_digit(key[j], shift, MASK);
+    const unsigned peers = digit_peers<RB, MODE>(d);
+    const int lead = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == lead) {
+      old = wcnt[d];
+      wcnt[d] = (uint16_t)(old + __popc(peers));
+    }
+    old = __shfl_sync(0xffffffffu, old, lead) + __popc(peers & lt);
+    if (j & 1) rk[j / 2] |= old << 16;
+    else rk[j / 2] = old;
+    __syncwarp();
+  }
+  if constexpr (PAIRS && !EARLYV) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const long long i = w0 + j * 32;
+      val[j] = (full || i < p.len) ? __ldcs(p.vin + seg0 + i) : 0u;
+    }
+  }
+  __syncthreads();
+
+  // ---- counters -> exclusive prefix over the warps (in place); tile totals per digit value; first slot in the tile
+  uint32_t tot[BPT];
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) tot[b] = 0;
+  if constexpr (BPT == 8) {
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      uint4* q = reinterpret_cast<uint4*>(cnt + w * NB + tid * 8);
+      const uint4 c = *q;
+      const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = cw[k] & 0xffffu, hi = cw[k] >> 16;
+        o[k] = tot[2 * k] | (tot[2 * k + 1] << 16);
+        tot[2 * k] += lo;
+        tot[2 * k + 1] += hi;
+      }
+      *q = make_uint4(o[0], o[1], o[2], o[3]);
     }
   } else {
-    if constexpr (V == 4) *reinterpret_cast<uint4*>(kout) = make_uint4(key[0], key[1], key[2], key[3]);
-    else kout[0] = key[0];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+#pragma unroll
+      for (int b = 0; b < BPT; ++b) {
+        uint16_t* q = cnt + w * NB + tid * BPT + b;
+        const uint32_t c = *q;
+        *q = (uint16_t)tot[b];
+        tot[b] += c;
+      }
+    }
   }
-  if (p.vals) {
-    if constexpr (V == 4) *reinterpret_cast<uint4*>(p.vals + i0) = make_uint4(val[0], val[1], val[2], val[3]);
-    else p.vals[i0] = val[0];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) tsum += tot[b];
+  uint32_t x = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_w[warp] = x;
+  // publish this tile's counts before anything else (the tiles after it wait for them)
+  const uint32_t dmax = (0xffffffffu >> shift) & MASK;
+  const uint32_t ninv = (uint32_t)(TILE - nvalid);
+  uint32_t* drow = p.desc + (size_t)gt * NB + tid * BPT;
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    if ((uint32_t)(tid * BPT + b) == dmax) tot[b] -= ninv;
+    st_relaxed_u32(drow + b, (tot[b] << 2) | (tile == 0 ? 2u : 1u));
+  }
+  __syncthreads();
+  {
+    uint32_t run = x - tsum;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) run += (w < warp) ? s_w[w] : 0u;
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      binstart[tid * BPT + b] = run;
+      run += tot[b] + (((uint32_t)(tid * BPT + b) == dmax) ? ninv : 0u);
+    }
+  }
+  __syncthreads();
+
+  // ---- order the tile in shared memory
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t d = sort_digit(key[j], shift, MASK);
+    const uint32_t q = binstart[d] + wcnt[d] + ((j & 1) ? (rk[j / 2] >> 16) : (rk[j / 2] & 0xffffu));
+    exk[q] = key[j];
+    if constexpr (PAIRS) exv[q] = val[j];
+  }
+
+  // ---- decoupled look-back: items with the same digit in the tiles before this one (of the same segment)
+  uint32_t excl[BPT];
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) excl[b] = 0;
+  if (tile > 0) {
+    uint32_t pending = (1u << BPT) - 1u;
+    const uint32_t* row = drow;
+    while (pending) {                                  // ends at tile 0 at the latest (it publishes state 2)
+      row -= NB;
+      uint32_t v[BPT];
+      for (;;) {
+        bool ready = true;
+#pragma unroll
+        for (int b = 0; b < BPT; ++b) {
+          v[b] = ld_relaxed_u32(row + b);
+          ready = ready && ((v[b] & 3u) != 0u || !((pending >> b) & 1u));
+        }
+        if (ready) break;
+        __nanosleep(40);
+      }
+#pragma unroll
+      for (int b = 0; b < BPT; ++b) {
+        if ((pending >> b) & 1u) {
+          excl[b] += v[b] >> 2;
+          if ((v[b] & 3u) == 2u) pending &= ~(1u << b);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) st_relaxed_u32(drow + b, ((excl[b] + tot[b]) << 2) | 2u);
+  }
+  const uint32_t* brow = p.base + (size_t)s * NB + tid * BPT;
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) gdelta[tid * BPT + b] = brow[b] + excl[b] - binstart[tid * BPT + b];
+  __syncthreads();
+
+  // ---- write the runs
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int q = tid + k * kSortThreads;
+    if (q < nvalid) {
+      const uint32_t kk = exk[q];
+      const size_t a = seg0 + (size_t)(gdelta[sort_digit(kk, shift, MASK)] + (uint32_t)q);
+      p.kout[a] = kk;
+      if constexpr (PAIRS) p.vout[a] = exv[q];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- scan over the sorted order
-// 8 consecutive sorted items of one segment (low word of the key = error | foreground bit; the high word of a batched
-// 64-bit key is the image index, not needed once the order is established)
-template <typename KeyT>
-__device__ __forceinline__ void lov_load_tile(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+// 8 consecutive sorted items of one segment
+__device__ __forceinline__ void lov_load_tile(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                               long long i0, long long len, bool vec, uint32_t (&k)[kLovItems],
                                               uint32_t (&v)[kLovItems], bool want_vals) {
   if (vec && i0 + kLovItems <= len) {
-    if constexpr (sizeof(KeyT) == 4) {
-      const uint4 a = *reinterpret_cast<const uint4*>(keys + i0), b = *reinterpret_cast<const uint4*>(keys + i0 + 4);
-      k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 a = *reinterpret_cast<const uint4*>(keys + i0 + 2 * j);
-        k[2 * j] = a.x; k[2 * j + 1] = a.z;
-      }
-    }
+    const uint4 a = *reinterpret_cast<const uint4*>(keys + i0), b = *reinterpret_cast<const uint4*>(keys + i0 + 4);
+    k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
     if (want_vals) {
       const uint4 c = *reinterpret_cast<const uint4*>(vals + i0), d = *reinterpret_cast<const uint4*>(vals + i0 + 4);
       v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
@@ -170,7 +492,7 @@ __device__ __forceinline__ void lov_load_tile(const KeyT* __restrict__ keys, con
 #pragma unroll
     for (int j = 0; j < kLovItems; ++j) {
       const bool in = i0 + j < len;
-      k[j] = in ? (uint32_t)keys[i0 + j] : 0u;
+      k[j] = in ? keys[i0 + j] : 0u;
       v[j] = (in && want_vals) ? vals[i0 + j] : 0u;
     }
   }
@@ -181,15 +503,15 @@ template <bool BINARY> __device__ __forceinline__ uint32_t lov_fg(uint32_t key, 
 }
 
 // grid (tiles per segment, segments): foreground count of every tile
-template <bool BINARY, typename KeyT>
-__global__ void __launch_bounds__(kLovThreads) lovasz_count_kernel(const KeyT* __restrict__ keys,
+template <bool BINARY>
+__global__ void __launch_bounds__(kLovThreads) lovasz_count_kernel(const uint32_t* __restrict__ keys,
                                                                    const uint32_t* __restrict__ vals, long long len,
                                                                    int vec, uint32_t* __restrict__ tile_cnt) {
   __shared__ uint32_t s[kLovThreads / 32];
   const size_t seg0 = (size_t)blockIdx.y * len;
   const long long i0 = ((long long)blockIdx.x * kLovThreads + threadIdx.x) * kLovItems;
   uint32_t k[kLovItems], v[kLovItems];
-  lov_load_tile<KeyT>(keys + seg0, vals ? vals + seg0 : nullptr, i0, len, vec != 0, k, v, BINARY);
+  lov_load_tile(keys + seg0, vals ? vals + seg0 : nullptr, i0, len, vec != 0, k, v, BINARY);
   uint32_t cnt = 0;
 #pragma unroll
   for (int j = 0; j < kLovItems; ++j) cnt += lov_fg<BINARY>(k[j], v[j]);
@@ -204,13 +526,20 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_count_kernel(const KeyT* _
   }
 }
 
+// statistics slot of segment s = (class c0 + s / groups, group s % groups) inside seg_stats (n_groups, n_seg, 2); the
+// pointer handed to the kernels already points at class c0 of group 0
+__device__ __forceinline__ double* lov_seg_stat(double* base, int s, int groups, int n_seg) {
+  const int cj = s / groups, g = s - cj * groups;
+  return base + ((size_t)g * n_seg + cj) * 2;
+}
+
 // one CTA per segment: exclusive scan of its tile counts; writes the segment's foreground total (+1 = "segment processed")
 __global__ void __launch_bounds__(1024) lovasz_tilescan_kernel(const uint32_t* __restrict__ tile_cnt_all,
                                                                uint32_t* __restrict__ tile_off_all, int nb,
-                                                               double* __restrict__ seg_stat_all, int seg_stat_stride) {
+                                                               double* __restrict__ seg_stat_base, int groups, int n_seg) {
   const uint32_t* tile_cnt = tile_cnt_all + (size_t)blockIdx.x * nb;      // one CTA per segment
   uint32_t* tile_off = tile_off_all + (size_t)blockIdx.x * nb;
-  double* seg_stat = seg_stat_all + (size_t)blockIdx.x * seg_stat_stride;
+  double* seg_stat = lov_seg_stat(seg_stat_base, blockIdx.x, groups, n_seg);
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -248,18 +577,18 @@ __global__ void __launch_bounds__(1024) lovasz_tilescan_kernel(const uint32_t* _
 }
 
 struct LovGradParams {
-  const void* keys;
+  const uint32_t* keys;
   const uint32_t* vals;       // NULL when no gradient is wanted (multi-class)
   const uint32_t* tile_off;   // (segments, tiles per segment)
-  double* seg_stat;           // segment 0: [0] loss accumulator, [1] gts + 1; segment s at + s * seg_stat_stride
+  double* seg_stat;           // class c0, group 0: [0] loss accumulator, [1] gts + 1 (lov_seg_stat for the others)
   float* G;                   // NULL = forward only
-  float* Gseg;                // slice of G where segment 0 starts: multi-class (C,N,HW) f32 at class c, binary (N,HW)
+  float* Gseg;                // slice of G where segment 0 starts: multi-class (C,N,HW) f32 at class c0, binary (N,HW)
   long long len;              // items per segment (consecutive segments are `len` apart in keys, vals and G)
-  int seg_stat_stride;
+  int groups, n_seg;
   int vec;
 };
 
-template <bool BINARY, typename KeyT>
+template <bool BINARY>
 __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradParams p) {
   __shared__ uint32_t s_w[kLovThreads / 32];
   __shared__ float s_l[kLovThreads / 32];
@@ -268,9 +597,8 @@ __global__ void __launch_bounds__(kLovThreads) lovasz_grad_kernel(const LovGradP
   const bool want_vals = BINARY || p.G != nullptr;
   uint32_t k[kLovItems], v[kLovItems];
   const size_t seg0 = (size_t)blockIdx.y * p.len;
-  double* seg_stat = p.seg_stat + (size_t)blockIdx.y * p.seg_stat_stride;
-  lov_load_tile<KeyT>(reinterpret_cast<const KeyT*>(p.keys) + seg0, p.vals ? p.vals + seg0 : nullptr, i0, p.len, p.vec != 0, k, v,
-                      want_vals);
+  double* seg_stat = lov_seg_stat(p.seg_stat, blockIdx.y, p.groups, p.n_seg);
+  lov_load_tile(p.keys + seg0, p.vals ? p.vals + seg0 : nullptr, i0, p.len, p.vec != 0, k, v, want_vals);
   uint32_t tsum = 0;
 #pragma unroll
   for (int j = 0; j < kLovItems; ++j) tsum += lov_fg<BINARY>(k[j], v[j]);
@@ -457,138 +785,222 @@ __global__ void __launch_bounds__(256) lovasz_hinge_bwd_kernel(const LovBwdParam
   reinterpret_cast<T*>(p.grad)[px] = from_float<T>(r);
 }
 
+
 // ---------------------------------------------------------------------------------------------- host side
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static inline int bits_for(int n) {   // bits needed to hold values 0 .. n-1 (>= 1)
-  int b = 1;
-  while ((1 << b) < n) ++b;
-  return b;
+
+constexpr int kItemsRB8 = 16, kItemsRB11 = 32;     // items per thread of a sort tile
+constexpr int kKeysChunk = 256 * 4 * 32;           // items per CTA of the keys kernel (4096 per warp: 16-bit counters)
+constexpr long long kLovBudget = 4ll << 30;        // workspace the query asks for at most (classes go in batches beyond it)
+
+static int lov_radix_bits() {
+  static const int rb = [] {
+    const char* e = std::getenv("B200SEG_LOV_RB");
+    return (e && std::atoi(e) == 11) ? 11 : 8;
+  }();
+  return rb;
 }
+static inline int lov_sort_tile(int rb) { return kSortThreads * (rb == 11 ? kItemsRB11 : kItemsRB8); }
+static inline int lov_passes(int rb) { return (32 + rb - 1) / rb; }
 
 struct LovWorkspace {
-  void *keys_a, *keys_b;
-  uint32_t *vals_a, *vals_b, *tile_cnt, *tile_off;
-  void* cub_temp;
-  size_t cub_bytes, total;
+  uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *tile_cnt, *tile_off;
+  uint32_t *ticket, *hist, *desc;     // one zeroed region: tickets (one per pass), histograms, look-back descriptors
+  void* zero_base;
+  size_t zero_bytes, desc_pass_words, total;
+  int tiles;
 };
 
-// items = keys per sort; segs = segments per sort (> 1: batched per-image mode with 64-bit keys)
-static int lov_carve(long long items, int segs, bool pairs, void* base, LovWorkspace* w) {
-  size_t cub_bytes = 0;
-  const int n = (int)items;
-  cudaError_t e;
-  if (segs > 1) {
-    const int end_bit = 32 + bits_for(segs);
-    e = pairs ? cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                                          (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, end_bit, (cudaStream_t)0)
-              : cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, n, 0,
-                                                         end_bit, (cudaStream_t)0);
-  } else {
-    e = pairs ? cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                          (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 32, (cudaStream_t)0)
-              : cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 32,
-                                                         (cudaStream_t)0);
-  }
-  if (e != cudaSuccess) {
-    set_error("lovasz: radix-sort workspace query failed: %s", cudaGetErrorString(e));
-    return 2;
-  }
-  const size_t karr = align256((size_t)items * (segs > 1 ? 8 : 4));
-  const size_t varr = align256((size_t)items * 4);
-  const long long seg_len = items / segs;
-  const size_t nb = (size_t)((seg_len + kLovTile - 1) / kLovTile) * segs;
+// S segments of len items each
+static void lov_carve(int rb, long long len, int S, bool pairs, void* base, LovWorkspace* w) {
+  const int nbins = 1 << rb, np = lov_passes(rb);
+  const size_t items = (size_t)len * S;
+  const size_t arr = align256(items * 4);
+  const size_t nb = (size_t)((len + kLovTile - 1) / kLovTile) * S;
   const size_t tb = align256((nb + 1) * sizeof(uint32_t));
+  w->tiles = (int)((len + lov_sort_tile(rb) - 1) / lov_sort_tile(rb));
+  w->desc_pass_words = (size_t)S * w->tiles * nbins;
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
-  w->keys_a = p + off; off += karr;
-  w->keys_b = p + off; off += karr;
-  w->vals_a = reinterpret_cast<uint32_t*>(p + off); off += pairs ? varr : 0;
-  w->vals_b = reinterpret_cast<uint32_t*>(p + off); off += pairs ? varr : 0;
+  w->keys_a = reinterpret_cast<uint32_t*>(p + off); off += arr;
+  w->keys_b = reinterpret_cast<uint32_t*>(p + off); off += arr;
+  w->vals_a = reinterpret_cast<uint32_t*>(p + off); off += pairs ? arr : 0;
+  w->vals_b = reinterpret_cast<uint32_t*>(p + off); off += pairs ? arr : 0;
   w->tile_cnt = reinterpret_cast<uint32_t*>(p + off); off += tb;
   w->tile_off = reinterpret_cast<uint32_t*>(p + off); off += tb;
-  w->cub_temp = p + off; off += align256(cub_bytes ? cub_bytes : 1);
-  w->cub_bytes = cub_bytes;
+  w->zero_base = p + off;
+  const size_t z0 = off;
+  w->ticket = reinterpret_cast<uint32_t*>(p + off); off += 256;
+  w->hist = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)np * S * nbins * 4);
+  w->desc = reinterpret_cast<uint32_t*>(p + off); off += align256((size_t)np * w->desc_pass_words * 4);
+  w->zero_bytes = off - z0;
   w->total = off;
+}
+static size_t lov_total(long long len, int S, bool pairs) {   // the larger of the two digit widths (the choice is an env knob)
+  LovWorkspace a, b;
+  lov_carve(8, len, S, pairs, nullptr, &a);
+  lov_carve(11, len, S, pairs, nullptr, &b);
+  return a.total > b.total ? a.total : b.total;
+}
+// largest batch of classes (1 .. n) whose workspace fits `bytes`; 0 if not even one class fits
+static int lov_class_batch(long long len, int groups, int n, bool pairs, long long bytes) {
+  int hi = n;
+  if ((long long)hi * groups > 65535) hi = 65535 / groups;   // segments ride on grid.y
+  if (hi < 1) hi = 1;
+  if ((long long)lov_total(len, groups, pairs) > bytes) return 0;
+  int lo = 1;                                                // invariant: lo fits
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if ((long long)lov_total(len, mid * groups, pairs) <= bytes) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+long long lovasz_workspace_bytes(int N, int C, long long HW, int per_image, int pairs) {
+  if (N <= 0 || HW <= 0 || C <= 0) return 256;
+  const int groups = per_image ? N : 1;
+  const long long len = per_image ? HW : (long long)N * HW;
+  int J = lov_class_batch(len, groups, C, pairs != 0, kLovBudget);
+  if (J < 1) J = 1;
+  return (long long)lov_total(len, J * groups, pairs != 0);
+}
+
+static int lov_mode() {
+  static const int m = [] {
+    const char* e = std::getenv("B200SEG_LOV_MODE");
+    return e ? std::atoi(e) : 0x2B;
+  }();
+  return m;
+}
+template <int RB, int ITEMS, bool PAIRS>
+static int lov_launch_pass(const LovSortParams& sp, unsigned grid, cudaStream_t st) {
+  const int m = lov_mode() & 15;     // bit 0: ballots, bit 1: values loaded early, bits 2-3: CTAs per SM (0: 2, 1: 3, 2: 4)
+  void (*k)(LovSortParams);
+  switch (m) {
+#define LOV_CASE(M, MODE, MINB, EV) case M: k = lov_sort_pass_kernel<RB, ITEMS, PAIRS, MODE, MINB, EV>; break;
+    LOV_CASE(0, 0, 2, false) LOV_CASE(1, 1, 2, false) LOV_CASE(2, 0, 2, true) LOV_CASE(3, 1, 2, true)
+    LOV_CASE(4, 0, 3, false) LOV_CASE(5, 1, 3, false) LOV_CASE(6, 0, 3, true) LOV_CASE(7, 1, 3, true)
+    LOV_CASE(8, 0, 4, false) LOV_CASE(9, 1, 4, false) LOV_CASE(10, 0, 4, true)
+    default: k = lov_sort_pass_kernel<RB, ITEMS, PAIRS, 1, 4, true>; break;
+#undef LOV_CASE
+  }
+  constexpr int smem = SortSmem<RB, ITEMS, PAIRS>::BYTES;
+  if (smem > 48 * 1024)
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), smem)) return e;
+  k<<<grid, kSortThreads, smem, st>>>(sp);
   return 0;
 }
 
-long long lovasz_workspace_bytes(long long seg_len, int segs, int pairs) {
-  if (seg_len <= 0 || segs <= 0) return 256;
-  LovWorkspace w;
-  if (lov_carve(seg_len * segs, segs, pairs != 0, nullptr, &w)) return -1;
-  return (long long)w.total;
+template <typename T, int V, bool BINARY, int RB>
+static int lov_launch_keys(const LovKeysParams& kp, dim3 grid, cudaStream_t st) {
+  const int hm = lov_mode() >> 4;
+  auto k = hm == 2 ? lovasz_keys_kernel<T, V, BINARY, RB, 2> : hm == 1 ? lovasz_keys_kernel<T, V, BINARY, RB, 1> : lovasz_keys_kernel<T, V, BINARY, RB, 0>;
+  constexpr int smem = SortGeo<RB>::NP * kSortWarps * SortGeo<RB>::NB * 2;
+  if (smem > 48 * 1024)
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), smem)) return e;
+  k<<<grid, kSortThreads, smem, st>>>(kp);
+  return 0;
 }
 
-template <typename T, typename KeyT>
-static int lov_fwd_typed(const b200seg_lovasz_desc* d, cudaStream_t st) {
-  constexpr bool kBatched = sizeof(KeyT) == 8;
+// one batch of classes [c0, c0 + J): every kernel covers its J * groups segments
+template <typename T, int RB>
+static int lov_fwd_batch(const b200seg_lovasz_desc* d, int c0, int J, cudaStream_t st) {
+  using G = SortGeo<RB>;
+  constexpr int ITEMS = RB == 11 ? kItemsRB11 : kItemsRB8;
   const bool binary = d->binary != 0;
   const int n_seg = binary ? 1 : d->C;
   const long long HW = d->HW;
-  // kBatched: every image is a segment and ONE sort orders all of them; else one segment = the whole batch (or N == 1)
-  const int segs = kBatched ? d->N : 1;
-  const long long seg_len = kBatched ? HW : (long long)d->N * HW;
-  const long long items = seg_len * segs;
+  const int groups = d->per_image ? d->N : 1;
+  const long long len = d->per_image ? HW : (long long)d->N * HW;
+  const int S = J * groups;
   const bool pairs = binary || d->G != nullptr;
   LovWorkspace w;
-  if (int e = lov_carve(items, segs, pairs, d->workspace, &w)) return e;
+  lov_carve(RB, len, S, pairs, d->workspace, &w);
   B200SEG_REQUIRE((long long)w.total <= d->workspace_bytes, "lovasz_fwd: workspace of %lld bytes needed, %lld given",
                   (long long)w.total, (long long)d->workspace_bytes);
-  const long long npx = (long long)d->N * HW;
+  B200SEG_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
+
+  LovKeysParams kp;
+  kp.logits = d->logits; kp.lse = d->lse; kp.lab16 = d->lab16;
+  kp.keys = w.keys_a; kp.vals = pairs ? w.vals_a : nullptr; kp.hist = w.hist;
+  kp.HW = HW; kp.len = len; kp.C = d->C; kp.c0 = c0; kp.groups = groups; kp.nseg = S; kp.chunk = kKeysChunk;
+  const bool vec = HW % 4 == 0 && aligned16(d->logits) && aligned16(d->lab16) && (binary || aligned16(d->lse));
+  dim3 kgrid((unsigned)((len + kKeysChunk - 1) / kKeysChunk), S);
+  int e;
+  if (vec) e = binary ? lov_launch_keys<T, 4, true, RB>(kp, kgrid, st) : lov_launch_keys<T, 4, false, RB>(kp, kgrid, st);
+  else e = binary ? lov_launch_keys<T, 1, true, RB>(kp, kgrid, st) : lov_launch_keys<T, 1, false, RB>(kp, kgrid, st);
+  if (e) return e;
+  if ((e = check_launch("lovasz_keys_kernel"))) return e;
+  lov_hist_scan_kernel<RB><<<G::NP * S, kSortThreads, 0, st>>>(w.hist);
+  if ((e = check_launch("lov_hist_scan_kernel"))) return e;
+
+  uint32_t *kin = w.keys_a, *kout = w.keys_b, *vin = w.vals_a, *vout = w.vals_b;
+  for (int ps = 0; ps < G::NP; ++ps) {
+    LovSortParams sp;
+    sp.kin = kin; sp.kout = kout; sp.vin = pairs ? vin : nullptr; sp.vout = pairs ? vout : nullptr;
+    sp.base = w.hist + (size_t)ps * S * G::NB;
+    sp.desc = w.desc + (size_t)ps * w.desc_pass_words;
+    sp.ticket = w.ticket + ps;
+    sp.len = len; sp.tiles = w.tiles; sp.shift = ps * RB;
+    const unsigned grid = (unsigned)((size_t)S * w.tiles);
+    e = pairs ? lov_launch_pass<RB, ITEMS, true>(sp, grid, st) : lov_launch_pass<RB, ITEMS, false>(sp, grid, st);
+    if (e) return e;
+    if ((e = check_launch("lov_sort_pass_kernel"))) return e;
+    uint32_t* t = kin; kin = kout; kout = t;
+    t = vin; vin = vout; vout = t;
+  }
+  const uint32_t* ksorted = kin;
+  const uint32_t* vsorted = pairs ? vin : nullptr;
+
+  const int scan_vec = (S == 1 || len % 4 == 0) ? 1 : 0;      // 16-byte loads of the sorted arrays stay aligned
+  const int nb = (int)((len + kLovTile - 1) / kLovTile);
+  double* seg = d->seg_stats + (size_t)c0 * 2;
+  dim3 sgrid(nb, S);
+  if (binary) lovasz_count_kernel<true><<<sgrid, kLovThreads, 0, st>>>(ksorted, vsorted, len, scan_vec, w.tile_cnt);
+  else lovasz_count_kernel<false><<<sgrid, kLovThreads, 0, st>>>(ksorted, nullptr, len, scan_vec, w.tile_cnt);
+  lovasz_tilescan_kernel<<<S, 1024, 0, st>>>(w.tile_cnt, w.tile_off, nb, seg, groups, n_seg);
+  LovGradParams gp;
+  gp.keys = ksorted; gp.vals = vsorted; gp.tile_off = w.tile_off; gp.seg_stat = seg; gp.groups = groups; gp.n_seg = n_seg;
+  gp.G = d->G; gp.len = len; gp.vec = scan_vec;
+  gp.Gseg = d->G ? d->G + (size_t)(binary ? 0 : c0) * d->N * HW : nullptr;
+  if (binary) lovasz_grad_kernel<true><<<sgrid, kLovThreads, 0, st>>>(gp);
+  else lovasz_grad_kernel<false><<<sgrid, kLovThreads, 0, st>>>(gp);
+  count_launch(5 + G::NP);
+  return check_launch("lovasz scan kernels");
+}
+
+template <typename T, int RB>
+static int lov_fwd_typed(const b200seg_lovasz_desc* d, cudaStream_t st) {
+  const bool binary = d->binary != 0;
+  const int groups = d->per_image ? d->N : 1;
+  const long long len = d->per_image ? d->HW : (long long)d->N * d->HW;
+  const bool pairs = binary || d->G != nullptr;
+  B200SEG_REQUIRE(len < (1ll << 30), "lovasz_fwd: %lld items per segment exceed 2^30-1", len);
+  const long long npx = (long long)d->N * d->HW;
   lovasz_prep_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(d->labels, d->label_dtype, npx, binary ? 2 : d->C,
                                                                     d->has_ignore, d->ignore_index, d->lab16);
   count_launch();
   if (int e = check_launch("lovasz_prep_kernel")) return e;
-
-  const bool vec = HW % 4 == 0 && aligned16(d->logits) && aligned16(d->lab16) && (binary || aligned16(d->lse));
-  const int scan_vec = (segs == 1 || seg_len % 8 == 0) ? 1 : 0;      // 16-byte loads of the sorted arrays stay aligned
-  const int nb = (int)((seg_len + kLovTile - 1) / kLovTile);
-  const int end_bit = kBatched ? 32 + bits_for(segs) : 32;
-  const int n_list = binary ? 1 : (d->classes_host ? d->n_classes : d->C);
-  for (int j = 0; j < n_list; ++j) {
-    const int c = binary ? 0 : (d->classes_host ? d->classes_host[j] : j);
-    LovKeysParams kp;
-    kp.logits = d->logits; kp.lse = d->lse; kp.lab16 = d->lab16;
-    kp.keys = w.keys_a; kp.vals = pairs ? w.vals_a : nullptr;
-    kp.HW = HW; kp.C = d->C; kp.c = c; kp.n_img = d->N;
-    if (vec) {
-      dim3 grid((unsigned)((HW / 4 + 255) / 256), d->N);
-      if (binary) lovasz_keys_kernel<T, 4, true, KeyT><<<grid, 256, 0, st>>>(kp);
-      else lovasz_keys_kernel<T, 4, false, KeyT><<<grid, 256, 0, st>>>(kp);
-    } else {
-      dim3 grid((unsigned)((HW + 255) / 256), d->N);
-      if (binary) lovasz_keys_kernel<T, 1, true, KeyT><<<grid, 256, 0, st>>>(kp);
-      else lovasz_keys_kernel<T, 1, false, KeyT><<<grid, 256, 0, st>>>(kp);
-    }
-    if (int e = check_launch("lovasz_keys_kernel")) return e;
-    size_t cb = w.cub_bytes;
-    const KeyT* kin = reinterpret_cast<const KeyT*>(w.keys_a);
-    KeyT* kout = reinterpret_cast<KeyT*>(w.keys_b);
-    cudaError_t ce = pairs ? cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, cb, kin, kout, (const uint32_t*)w.vals_a,
-                                                                       w.vals_b, (int)items, 0, end_bit, st)
-                           : cub::DeviceRadixSort::SortKeysDescending(w.cub_temp, cb, kin, kout, (int)items, 0, end_bit, st);
-    if (ce != cudaSuccess) {
-      set_error("lovasz_fwd: radix sort failed: %s", cudaGetErrorString(ce));
-      return 2;
-    }
-    // segment s of this launch = image group s: statistics at (s, c), G slice at (c, s)
-    double* seg = d->seg_stats + (size_t)c * 2;
-    const int seg_stride = n_seg * 2;
-    dim3 sgrid(nb, segs);
-    const uint32_t* vsorted = pairs ? w.vals_b : nullptr;
-    if (binary) lovasz_count_kernel<true, KeyT><<<sgrid, kLovThreads, 0, st>>>(kout, vsorted, seg_len, scan_vec, w.tile_cnt);
-    else lovasz_count_kernel<false, KeyT><<<sgrid, kLovThreads, 0, st>>>(kout, nullptr, seg_len, scan_vec, w.tile_cnt);
-    lovasz_tilescan_kernel<<<segs, 1024, 0, st>>>(w.tile_cnt, w.tile_off, nb, seg, seg_stride);
-    LovGradParams gp;
-    gp.keys = kout; gp.vals = vsorted; gp.tile_off = w.tile_off; gp.seg_stat = seg; gp.seg_stat_stride = seg_stride;
-    gp.G = d->G; gp.len = seg_len; gp.vec = scan_vec;
-    gp.Gseg = d->G ? d->G + (size_t)(binary ? 0 : c) * d->N * HW : nullptr;
-    if (binary) lovasz_grad_kernel<true, KeyT><<<sgrid, kLovThreads, 0, st>>>(gp);
-    else lovasz_grad_kernel<false, KeyT><<<sgrid, kLovThreads, 0, st>>>(gp);
-    count_launch(4);
-    if (int e = check_launch("lovasz scan kernels")) return e;
+  if (binary) return lov_fwd_batch<T, RB>(d, 0, 1, st);
+  if (d->classes_host) {                                  // explicit class list: one class per batch
+    B200SEG_REQUIRE(lov_class_batch(len, groups, 1, pairs, d->workspace_bytes) >= 1,
+                    "lovasz_fwd: workspace of %lld bytes is too small for one class", (long long)d->workspace_bytes);
+    for (int j = 0; j < d->n_classes; ++j)
+      if (int e = lov_fwd_batch<T, RB>(d, d->classes_host[j], 1, st)) return e;
+    return 0;
   }
+  const int J = lov_class_batch(len, groups, d->C, pairs, d->workspace_bytes);
+  B200SEG_REQUIRE(J >= 1, "lovasz_fwd: workspace of %lld bytes is too small for one class", (long long)d->workspace_bytes);
+  const int nbatch = (d->C + J - 1) / J;
+  const int Jb = (d->C + nbatch - 1) / nbatch;            // even batches
+  for (int c0 = 0; c0 < d->C; c0 += Jb)
+    if (int e = lov_fwd_batch<T, RB>(d, c0, min(Jb, d->C - c0), st)) return e;
   return 0;
+}
+
+template <typename T> static int lov_fwd_rb(const b200seg_lovasz_desc* d, cudaStream_t st) {
+  return lov_radix_bits() == 11 ? lov_fwd_typed<T, 11>(d, st) : lov_fwd_typed<T, 8>(d, st);
 }
 
 int lovasz_fwd_dispatch(const b200seg_lovasz_desc* d, cudaStream_t st) {
@@ -597,13 +1009,10 @@ int lovasz_fwd_dispatch(const b200seg_lovasz_desc* d, cudaStream_t st) {
   B200SEG_CUDA(cudaMemsetAsync(d->seg_stats, 0, (size_t)n_groups * n_seg * 2 * sizeof(double), st));
   if (d->N > 0 && d->HW > 0) {
     int e;
-    const bool batched = d->per_image && d->N > 1;   // all images of a class in one 64-bit-key sort
     switch (d->logit_dtype) {
-      case B200SEG_F32: e = batched ? lov_fwd_typed<float, uint64_t>(d, st) : lov_fwd_typed<float, uint32_t>(d, st); break;
-      case B200SEG_BF16:
-        e = batched ? lov_fwd_typed<__nv_bfloat16, uint64_t>(d, st) : lov_fwd_typed<__nv_bfloat16, uint32_t>(d, st);
-        break;
-      default: e = batched ? lov_fwd_typed<__half, uint64_t>(d, st) : lov_fwd_typed<__half, uint32_t>(d, st); break;
+      case B200SEG_F32: e = lov_fwd_rb<float>(d, st); break;
+      case B200SEG_BF16: e = lov_fwd_rb<__nv_bfloat16>(d, st); break;
+      default: e = lov_fwd_rb<__half>(d, st); break;
     }
     if (e) return e;
   }

@@ -75,10 +75,8 @@ class _LovaszFunction(torch.autograd.Function):
                 fd.ce_loss_weight = 1.0
                 _lib.check(lib.b200seg_loss_fwd(C.byref(fd), stream))
                 keep.append(st)
-            batched = per_image and N > 1          # all images of a class ordered by one sort (64-bit keys)
-            seg_len, segs = (HW, N) if batched else (N * HW, 1)
             pairs = int(binary or needs_grad)
-            ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(seg_len, segs, pairs)) if N * HW > 0 else 256
+            ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(N, n_seg, HW, int(per_image), pairs)) if N * HW > 0 else 256
             if ws_bytes < 0:
                 raise RuntimeError(_lib.last_error())
             ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 12
+#define B200SEG_ABI_VERSION 13
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -242,8 +242,8 @@ int b200seg_bce_bwd(const b200seg_bce_desc* d, void* stream);   /* reads stats[1
 
 /* Lovasz-Softmax ('multi_class') and Lovasz hinge ('binary') losses, models/losses/lovasz_loss.py:26-298.
  * One SEGMENT per (image group, class): the whole batch, or one image when per_image. Per segment: sort keys from the
- * logits row and the per-pixel log-sum-exp, a device radix sort (descending errors), a scan of the foreground bits in
- * sorted order, the Jaccard increments in closed form, loss_c = sum e_i g_i and dloss_c/dp_c scattered into G.      */
+ * logits row and the per-pixel log-sum-exp, a hand-written segmented radix sort (descending errors, stable; all
+ * segments of a batch of classes per launch), a scan of the foreground bits in sorted order, the Jaccard increments in closed form, loss_c = sum e_i g_i and dloss_c/dp_c scattered into G.      */
 typedef struct b200seg_lovasz_desc {
   const void*  logits;          /* multi-class: (N,C,HW) RAW logits (the soft-max of :281-282 is fused in);
                                  * binary: (N,HW) logits (C must be 1)                                              */
@@ -274,10 +274,11 @@ typedef struct b200seg_lovasz_desc {
   float*   out;                 /* per_image && reduction none: n_groups floats; else 1 float (loss_weight applied) */
   float*   coef;                /* (n_groups, C or 1) f32: d out / d loss_seg, for the backward; or NULL            */
 } b200seg_lovasz_desc;
-/* per_image with N > 1: (seg_len = HW, segments = N) — all images of a class are ordered by ONE sort of 64-bit keys
- * (image index in the high word); otherwise (seg_len = N*HW, segments = 1). pairs = 1 when G != NULL or binary.
- * Needs a CUDA device (queries the sort). */
-int64_t b200seg_lovasz_workspace_bytes(int64_t seg_len, int32_t segments, int32_t pairs);
+/* Bytes the forward wants for this shape (C = 1 for binary; pairs = 1 when G != NULL or binary): the (key, pixel index)
+ * double buffers of every (class, image group) segment, the digit histograms and the look-back descriptors of the radix
+ * sort. Up to 4 GiB it covers all classes in one batch of launches; beyond that the classes go through in several
+ * batches. b200seg_lovasz_fwd adapts to whatever workspace_bytes it is given (at least one class must fit). */
+int64_t b200seg_lovasz_workspace_bytes(int32_t N, int32_t C, int64_t HW, int32_t per_image, int32_t pairs);
 int b200seg_lovasz_fwd(const b200seg_lovasz_desc* d, void* stream);
 
 typedef struct b200seg_lovasz_bwd_desc {

@@ -306,8 +306,7 @@ def test_lovasz_cabi_buffers_have_no_out_of_bounds_writes(B):
         n_groups = N if per_image else 1
         n_seg = 1 if binary else Cc
         lse = torch.logsumexp(x.double(), 1).float().reshape(N, HW).contiguous() if not binary else None
-        batched = per_image and N > 1
-        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(HW if batched else N * HW, N if batched else 1, 1))
+        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(N, 1 if binary else Cc, HW, int(per_image), 1))
         bufs = {}
         for name, nbytes in (('lab16', N * HW * 2), ('G', N * n_seg * HW * 4), ('ws', ws_bytes), ('seg', n_groups * n_seg * 16),
                              ('out', max(n_groups, 1) * 4), ('coef', n_groups * n_seg * 4), ('grad', N * Cc * HW * 4)):
