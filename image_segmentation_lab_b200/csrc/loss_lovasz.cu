@@ -262,7 +262,7 @@ template <int RB, int ITEMS, bool PAIRS> struct SortSmem {
   using G = SortGeo<RB>;
   static constexpr int TILE = kSortThreads * ITEMS;
   static constexpr int CNT_BYTES = kSortWarps * G::NB * 2;
-  static constexpr int BYTES = CNT_BYTES + (PAIRS ? 2 : 1) * TILE * 4 + 2 * G::NB * 4;
+  static constexpr int BYTES = CNT_BYTES + (PAIRS ? 2 : 1) * TILE * 4 + G::NB * 4;
 };
 
 // One tile = 256 threads x ITEMS consecutive items of one segment, order inside the tile = (warp, item, lane).
@@ -278,8 +278,7 @@ __device__ __forceinline__ void lov_sort_tile(const LovSortParams& p, unsigned c
   uint16_t* cnt = reinterpret_cast<uint16_t*>(lov_smem);                         // [warps][NB]
   uint32_t* exk = reinterpret_cast<uint32_t*>(lov_smem + SM::CNT_BYTES);         // [TILE] keys in tile order
   uint32_t* exv = exk + TILE;                                                    // [TILE] values (PAIRS)
-  uint32_t* binstart = exk + (PAIRS ? 2 : 1) * TILE;                             // [NB]
-  uint32_t* gdelta = binstart + NB;                                              // [NB]
+  uint32_t* gdelta = exk + (PAIRS ? 2 : 1) * TILE;                               // [NB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t seg0 = (size_t)s * (size_t)p.len;
   const uint32_t tile0 = (uint32_t)tile * TILE;
@@ -319,36 +318,19 @@ __device__ __forceinline__ void lov_sort_tile(const LovSortParams& p, unsigned c
   }
   __syncthreads();
 
-  // ---- counters -> exclusive prefix over the warps (in place); tile totals per digit value; first slot in the tile
+  // ---- counters -> tile totals per digit value -> first slot of every digit value in the tile; the warp counters are
+  // replaced by the first slot of the warp's items of that digit value (16 bits: a tile has at most 2^16 items)
+  static_assert(TILE <= 65536, "tile slots are kept in 16 bits");
   uint32_t tot[BPT];
+  uint16_t cw[kSortWarps][BPT];
 #pragma unroll
   for (int b = 0; b < BPT; ++b) tot[b] = 0;
-  if constexpr (BPT == 8) {
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      uint4* q = reinterpret_cast<uint4*>(cnt + w * NB + tid * 8);
-      const uint4 c = *q;
-      const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
-      uint32_t o[4];
+  for (int w = 0; w < kSortWarps; ++w) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t lo = cw[k] & 0xffffu, hi = cw[k] >> 16;
-        o[k] = tot[2 * k] | (tot[2 * k + 1] << 16);
-        tot[2 * k] += lo;
-        tot[2 * k + 1] += hi;
-      }
-      *q = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  } else {
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-#pragma unroll
-      for (int b = 0; b < BPT; ++b) {
-        uint16_t* q = cnt + w * NB + tid * BPT + b;
-        const uint32_t c = *q;
-        *q = (uint16_t)tot[b];
-        tot[b] += c;
-      }
+    for (int b = 0; b < BPT; ++b) {
+      cw[w][b] = cnt[w * NB + tid * BPT + b];
+      tot[b] += cw[w][b];
     }
   }
   uint32_t tsum = 0;
@@ -367,18 +349,26 @@ __device__ __forceinline__ void lov_sort_tile(const LovSortParams& p, unsigned c
   uint32_t* drow = p.desc + (size_t)gt * NB + tid * BPT;
 #pragma unroll
   for (int b = 0; b < BPT; ++b) {
-    if (!FULL && (uint32_t)(tid * BPT + b) == dmax) tot[b] -= ninv;
-    st_relaxed_u32(drow + b, (tot[b] << 2) | (tile == 0 ? 2u : 1u));
+    const uint32_t t = tot[b] - ((!FULL && (uint32_t)(tid * BPT + b) == dmax) ? ninv : 0u);
+    st_relaxed_u32(drow + b, (t << 2) | (tile == 0 ? 2u : 1u));
   }
   __syncthreads();
+  uint32_t bstart[BPT];
   {
     uint32_t run = x - tsum;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) run += (w < warp) ? s_w[w] : 0u;
 #pragma unroll
     for (int b = 0; b < BPT; ++b) {
-      binstart[tid * BPT + b] = run;
-      run += tot[b] + ((!FULL && (uint32_t)(tid * BPT + b) == dmax) ? ninv : 0u);
+      bstart[b] = run;
+      uint32_t r = run;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        cnt[w * NB + tid * BPT + b] = (uint16_t)r;
+        r += cw[w][b];
+      }
+      run += tot[b];
+      if (!FULL && (uint32_t)(tid * BPT + b) == dmax) tot[b] -= ninv;
     }
   }
   __syncthreads();
@@ -387,7 +377,7 @@ __device__ __forceinline__ void lov_sort_tile(const LovSortParams& p, unsigned c
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t d = sort_digit(dg[j], shift, MASK);
-    const uint32_t q = binstart[d] + wcnt[d] + ((j & 1) ? (rk[j / 2] >> 16) : (rk[j / 2] & 0xffffu));
+    const uint32_t q = wcnt[d] + ((j & 1) ? (rk[j / 2] >> 16) : (rk[j / 2] & 0xffffu));
     exk[q] = dg[j];
     if constexpr (PAIRS) exv[q] = val[j];
   }
@@ -424,13 +414,14 @@ __device__ __forceinline__ void lov_sort_tile(const LovSortParams& p, unsigned c
     for (int b = 0; b < BPT; ++b) st_relaxed_u32(drow + b, ((excl[b] + tot[b]) << 2) | 2u);
   }
   const uint32_t* brow = p.base + (size_t)s * NB + tid * BPT;
+  const uint32_t seg0_32 = (uint32_t)seg0;             // all segments together hold < 2^31 items
 #pragma unroll
-  for (int b = 0; b < BPT; ++b) gdelta[tid * BPT + b] = brow[b] + excl[b] - binstart[tid * BPT + b];
+  for (int b = 0; b < BPT; ++b) gdelta[tid * BPT + b] = seg0_32 + brow[b] + excl[b] - bstart[b];
   __syncthreads();
 
   // ---- write the runs: slot q of the tile goes to gdelta[its digit] + q
-  uint32_t* kout = p.kout + seg0;
-  uint32_t* vout = PAIRS ? p.vout + seg0 : nullptr;
+  uint32_t* kout = p.kout;
+  uint32_t* vout = p.vout;
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const uint32_t q = (uint32_t)tid + k * kSortThreads;
@@ -825,6 +816,7 @@ static size_t lov_total(long long len, int S, bool pairs) {
 static int lov_class_batch(long long len, int groups, int n, bool pairs, long long bytes) {
   int hi = n;
   if ((long long)hi * groups > 65535) hi = 65535 / groups;   // segments ride on grid.y
+  if ((long long)hi * groups * len >= (1ll << 31)) hi = (int)(((1ll << 31) - 1) / (groups * len));   // 32-bit item index
   if (hi < 1) hi = 1;
   if ((long long)lov_total(len, groups, pairs) > bytes) return 0;
   int lo = 1;                                                // invariant: lo fits
