@@ -816,9 +816,11 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
         out['lovasz_softmax_cityscapes_shape'] = {
             'shape': [8, 19, 512, 1024], 'dtype': 'float32', 'pixels': px,
             'fwd': dict(ms=a, mpix_s=px / a / 1e3), 'fwd_bwd': dict(ms=b, mpix_s=px / b / 1e3),
-            'plan': 'ce_fwd_kernel (lse) + per class: lovasz_keys_kernel, radix sort (CUB, L2-resident segment), '
+            'plan': 'ce_fwd_kernel (lse) + for all classes at once: lovasz_keys_kernel (keys + digit histograms), '
+                    'hand-written segmented radix sort (lov_sort_pass_kernel x 4: ballot ranking, decoupled look-back), '
                     'lovasz_count/tilescan/grad kernels; lovasz_finalize_kernel; lovasz_bwd_kernel',
-            'note': 'sort-bound (4 digit passes over 4 M key/index pairs per class); no HBM roofline is claimed for it'}
+            'note': 'sort-bound (4 digit passes over 80 M key/index pairs, instruction-issue bound); no HBM roofline is '
+                    'claimed for it'}
         del xl, yl
         torch.cuda.empty_cache()
     except Exception as e:   # the extra line must never cost the headline

@@ -296,9 +296,11 @@ def test_lovasz_cabi_buffers_have_no_out_of_bounds_writes(B):
     def intact(buf, n, what):
         assert bool((buf[:GUARD] == 0x5A).all()) and bool((buf[GUARD + n:] == 0x5A).all()), what + ': guard overwritten'
 
-    cases = [((2, 5, 24, 40), False, False), ((3, 7, 37, 53), False, False), ((1, 3, 50, 41), False, False),
-             ((3, 4, 45, 46), False, True), ((2, 1, 33, 31), True, False), ((3, 1, 64, 48), True, True)]
-    for shape, binary, per_image in cases:
+    # last field: classes the workspace is sized for (fewer than C: the classes go through in several batches of launches)
+    cases = [((2, 5, 24, 40), False, False, 5), ((3, 7, 37, 53), False, False, 7), ((1, 3, 50, 41), False, False, 3),
+             ((3, 4, 45, 46), False, True, 4), ((2, 1, 33, 31), True, False, 1), ((3, 1, 64, 48), True, True, 1),
+             ((2, 5, 67, 93), False, False, 2), ((3, 4, 45, 46), False, True, 1)]
+    for shape, binary, per_image, ws_classes in cases:
         N, Cc, H, W = shape
         HW = H * W
         x = synth_logits(shape, 13, device='cuda', margin=False)
@@ -306,7 +308,7 @@ def test_lovasz_cabi_buffers_have_no_out_of_bounds_writes(B):
         n_groups = N if per_image else 1
         n_seg = 1 if binary else Cc
         lse = torch.logsumexp(x.double(), 1).float().reshape(N, HW).contiguous() if not binary else None
-        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(N, 1 if binary else Cc, HW, int(per_image), 1))
+        ws_bytes = int(lib.b200seg_lovasz_workspace_bytes(N, ws_classes, HW, int(per_image), 1))
         bufs = {}
         for name, nbytes in (('lab16', N * HW * 2), ('G', N * n_seg * HW * 4), ('ws', ws_bytes), ('seg', n_groups * n_seg * 16),
                              ('out', max(n_groups, 1) * 4), ('coef', n_groups * n_seg * 4), ('grad', N * Cc * HW * 4)):
@@ -345,3 +347,39 @@ def test_lovasz_cabi_buffers_have_no_out_of_bounds_writes(B):
     # a too-small workspace is refused before any launch
     d.workspace_bytes = 1024
     assert lib.b200seg_lovasz_fwd(C.byref(d), stream) != 0 and 'workspace' in _lib.last_error()
+
+
+@pytest.mark.parametrize('shape,kw', [
+    ((3, 5, 157, 211), dict(reduction='none')),                              # 24 full sort tiles + a partial one per class
+    ((5, 3, 91, 123), dict(per_image=True, reduction='mean')),               # 15 segments of 2.7 tiles
+    ((2, 2, 300, 301), dict(reduction='none', classes='all')),
+])
+def test_lovasz_multi_tile_segments(B, shape, kw):
+    """The hand-written radix sort across tile boundaries: look-back chains of tens of tiles, a partial last tile, several
+    segments per launch; loss and gradient against the exact-Jaccard fp64 oracle."""
+    x = synth_logits(shape, 31, device='cuda', margin=False)
+    y = synth_labels(shape[:1] + shape[2:], shape[1], 31, ignore_index=255, block=7, device='cuda')
+    l, g = _run(B, x, y, kw)
+    xo = x.double().requires_grad_(True)
+    lo = O.lovasz_loss_module(xo, y, ignore_index=255, acc_dtype=torch.float64, **kw)
+    lo.sum().backward()
+    assert rel_err(l.reshape(lo.shape), lo) <= LOSS_TOL
+    _grad_gate(str(shape), g, xo.grad)
+
+
+def test_lovasz_sort_ties_and_determinism(B):
+    """Logits quantised to a few values: long runs of equal sort keys (the stable sort keeps pixel order inside them; the
+    loss does not depend on that order, lovasz_loss.py:26-39 telescopes) — and two runs are bit-identical."""
+    shape = (2, 4, 96, 128)
+    x = (synth_logits(shape, 5, device='cuda', margin=False) * 2).round() / 2
+    y = synth_labels(shape[:1] + shape[2:], shape[1], 5, ignore_index=255, block=9, device='cuda')
+    l1, g1 = _run(B, x, y, dict(reduction='none'))
+    l2, g2 = _run(B, x, y, dict(reduction='none'))
+    assert torch.equal(g1, g2)
+    assert abs(float(l1) - float(l2)) <= 1e-6 * abs(float(l1))          # the class sums are fp64 atomics of fp32 tile sums
+    lo = O.lovasz_loss_module(x.double(), y, ignore_index=255, acc_dtype=torch.float64, reduction='none')
+    assert rel_err(l1.reshape(lo.shape), lo) <= LOSS_TOL
+    z = torch.zeros(shape, device='cuda')                                   # every key of a class equal
+    lz, _ = _run(B, z, y, dict(reduction='none'))
+    lzo = O.lovasz_loss_module(z.double(), y, ignore_index=255, acc_dtype=torch.float64, reduction='none')
+    assert rel_err(lz.reshape(lzo.shape), lzo) <= LOSS_TOL
