@@ -534,6 +534,8 @@ def flatten_workloads(line, extras):
     put('c5ii_frac', extras, 'C5ii_miou_from_logits', 'roofline', 'frac')
     put('c5_resized_ms', extras, 'C5_resized_lowres_logits', 'ms')
     put('c5_resized_frac', extras, 'C5_resized_lowres_logits', 'roofline', 'frac')
+    put('f1_sigmoid_ce_fwd_bwd_ms', extras, 'F1_sigmoid_ce_2class', 'fwd_bwd', 'ms')
+    put('f1_sigmoid_ce_fwd_bwd_frac', extras, 'F1_sigmoid_ce_2class', 'fwd_bwd', 'roofline', 'frac')
     put('lovasz_fwd_bwd_ms', extras, 'lovasz_softmax_cityscapes_shape', 'fwd_bwd', 'ms')
     put('c4dp_strong_ms', extras, 'C4_dp', 'strong', 'ms')
     put('c4dp_strong_frac', extras, 'C4_dp', 'strong', 'roofline', 'frac')
@@ -700,7 +702,7 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
         a = algo_bytes / (ms * 1e-3) / 1e9
         return {'bound': 'hbm', 'achieved': a, 'peak': peak, 'unit': 'GB/s', 'frac': a / peak, 'peak_kind': peak_kind}
 
-    def bench_losses(name, shape, dtype, losses, label_dtype=torch.int64, iters=20, single=False, plan=''):
+    def bench_losses(name, shape, dtype, losses, label_dtype=torch.int64, iters=20, single=False, plan='', graph=False):
         n, c, hh, ww = shape
         s = 4 if dtype == torch.float32 else 2
         xs = [make_logits(shape, 300 + i, dtype=dtype, device=dev).requires_grad_(True) for i in range(2)]
@@ -723,8 +725,28 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
 
         for i in range(3):
             fwd(i); fwdbwd(i)
-        ms_f = timed_events(fwd, iters)
-        ms_fb = timed_events(fwdbwd, iters)
+        if graph:   # steps of a few tens of microseconds: replayed from CUDA graphs (2 input sets), as the headline is
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    fwd(i); fwdbwd(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gf, gfb = [], []
+            for i in range(2):
+                for fn, lst in ((fwd, gf), (fwdbwd, gfb)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn(i)
+                    lst.append(g)
+            for i in range(4):
+                gf[i & 1].replay(); gfb[i & 1].replay()
+            ms_f = timed_events(lambda i: gf[i & 1].replay(), iters)
+            ms_fb = timed_events(lambda i: gfb[i & 1].replay(), iters)
+        else:
+            ms_f = timed_events(fwd, iters)
+            ms_fb = timed_events(fwdbwd, iters)
         px = n * hh * ww
         elems = n * c * hh * ww
         algo_f = elems * s + px * L
@@ -749,6 +771,16 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     ce2.single_pass = False
     bench_losses('C4_voc_fp32_ce_two_pass', (32, 21, 512, 512), torch.float32, ce2, iters=10,
                  plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
+
+    # ---- row f1: the sigmoid path the shipped default config runs (use_sigmoid=True, 2 classes, configs/network/deeplabv3):
+    # one-hot expansion + BCE-with-logits in one stream per direction (csrc/loss_bce.cu)
+    try:
+        bench_losses('F1_sigmoid_ce_2class', (32, 2, 512, 512), torch.float32, B.CrossEntropyLoss(use_sigmoid=True), iters=20,
+                     single=True, graph=True,
+                     plan='bce_kernel<fused>: loss, reduced scalar and gradient in one pass (one read and one write of the '
+                          'logits); CUDA-graph replay')
+    except Exception as e:
+        out['F1_sigmoid_ce_2class'] = {'error': repr(e)}
 
     # ---- resize-fused CE beyond the headline shape: align_corners=True (thread-per-cell kernel, csrc/loss_upgen.cuh) and
     # 150 classes at 1/8 resolution (C > 32: the class-tiled plan of the same file); both deterministic — there is no

@@ -19,7 +19,7 @@ WANT_CE, WANT_DICE, WANT_ACC, WANT_LOSS_PX, WANT_LSE = 1, 2, 4, 8, 16
 MODE_DICE, MODE_TVERSKY = 0, 1
 ST_CE_SUM, ST_N_VALID, ST_N_CORRECT, ST_N_BAD, ST_N_ACC, STATS_WORDS = 0, 1, 2, 3, 4, 8
 RED_NONE, RED_MEAN, RED_SUM = 0, 1, 2
-ABI_VERSION = 13
+ABI_VERSION = 14
 LOG_CE_SUM, LOG_N_VALID, LOG_N_CORRECT, LOG_N_ACC, LOG_N_BAD, LOG_N_PIXELS, LOG_DICE_SUM, LOG_N_IMAGES, LOG_WORDS = \
     0, 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -98,7 +98,8 @@ class BceDesc(C.Structure):
         ("single_channel", C.c_int32), ("use_nvalid", C.c_int32),
         ("loss_weight", C.c_float), ("grad_scale_host", C.c_float),
         ("loss_elem", C.c_void_p), ("grad_out", C.c_void_p), ("grad_elem", C.c_void_p), ("grad_logits", C.c_void_p),
-        ("stats", C.c_void_p),
+        ("stats", C.c_void_p), ("out", C.c_void_p), ("out_scale_host", C.c_float), ("acc_has_ignore", C.c_int32),
+        ("acc_out", C.c_void_p), ("acc_ignore_index", C.c_int64),
     ]
 
 

@@ -82,6 +82,17 @@ def fused_resize_losses(seg_logit, seg_label, losses_decode, align_corners=False
         else:
             out[name] = out[name] + value
 
+    # a lone sigmoid cross-entropy (the shipped default config): its launch also counts the top-1 hits, so the
+    # accuracy needs no pass of its own over the logits
+    if (fused_ce is None and fused_dice is None and len(others) == 1 and type(others[0]) is CrossEntropyLoss
+            and others[0].use_sigmoid and not return_stats and src.is_cuda and src.dim() == 4 and src.shape[1] > 1):
+        m = others[0]
+        acc = torch.empty(1, dtype=torch.float32, device=src.device)
+        label = seg_label.squeeze(1) if seg_label.dim() == 4 else seg_label
+        out[m.loss_name] = m(src, label, weight=seg_weight, ignore_index=ignore_index, _acc_out=acc, _acc_ignore=ignore_index)
+        out['acc_seg'] = acc
+        return out
+
     spec = _merge_spec(fused_ce, fused_dice, seg_logit.device, seg_weight, ignore_index, align_corners, True)
     l_ce, l_dice, acc, log_vec = run_fused(src, seg_label, seg_weight, spec, with_log=True)
     # keep the reference's insertion order of the loss dict

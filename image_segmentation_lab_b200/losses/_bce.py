@@ -13,7 +13,7 @@ _EPS = float(torch.finfo(torch.float32).eps)
 class _BceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, label, weight, pos_weight, reduction, avg_factor, ignore_index, avg_non_ignore, single,
-                grad_enabled=True):
+                grad_enabled=True, loss_weight=1.0, single_pass=True, acc_out=None, acc_ignore=None):
         lib = _lib.load()
         _lib.require_cuda(pred, 'pred')
         if pred.dtype not in _lib.LOGIT_DTYPES:
@@ -40,9 +40,17 @@ class _BceFunction(torch.autograd.Function):
                 scale = 1.0 / float(torch.tensor(avg_factor + _EPS, dtype=torch.float32))
             elif not use_nvalid:
                 scale = 1.0 / n_elem
+        scale *= float(loss_weight)
+        # single pass (the gradient is written by the forward kernel, with the upstream gradient taken as 1) whenever the
+        # denominator is known before the launch; never for float16: a gradient formed at ~1/numel would be flushed
+        # before a GradScaler's factor arrives (same rule as the soft-max path's flat plan)
+        fused = bool(needs_grad and single_pass and reduction != 'none' and not use_nvalid and x.dtype != torch.float16
+                     and N * HW > 0)
         with torch.cuda.device(dev):
-            stats = torch.empty(2, dtype=torch.int64, device=dev)
+            stats = torch.empty(8, dtype=torch.int64, device=dev)
             loss_elem = torch.empty(x.shape, dtype=torch.float32, device=dev) if reduction == 'none' else None
+            out = None if reduction == 'none' else torch.empty((), dtype=torch.float32, device=dev)
+            grad = torch.empty_like(x) if fused else None
             d = _lib.BceDesc()
             d.logits = x.data_ptr(); d.labels = lab.data_ptr()
             d.pixel_weight = w.data_ptr() if w is not None else None
@@ -51,35 +59,51 @@ class _BceFunction(torch.autograd.Function):
             d.N, d.C, d.HW = N, Cc, HW
             d.ignore_index = int(ignore_index)
             d.single_channel = int(bool(single))
-            d.loss_weight = 1.0
+            d.use_nvalid = int(use_nvalid)
+            d.loss_weight = float(loss_weight)
             d.loss_elem = loss_elem.data_ptr() if loss_elem is not None else None
             d.stats = stats.data_ptr()
+            d.out = out.data_ptr() if out is not None else None
+            d.out_scale_host = float(scale)
+            if acc_out is not None:      # top-1 accuracy of the same launch (decode_head.py:295)
+                assert acc_out.dtype == torch.float32 and acc_out.is_cuda and acc_out.numel() == 1
+                d.acc_out = acc_out.data_ptr()
+                d.acc_has_ignore = int(acc_ignore is not None)
+                d.acc_ignore_index = int(acc_ignore) if acc_ignore is not None else 0
+            if fused:
+                d.grad_logits = grad.data_ptr()
+                d.grad_scale_host = float(scale)
             _lib.check(lib.b200seg_bce_fwd(C.byref(d), _lib.stream_ptr(dev)))
             if reduction == 'none':
                 out = loss_elem
-            else:
-                total = stats[:1].view(torch.float64)[0]
-                if use_nvalid:
-                    denom = (stats[1].to(torch.float64) * Cc + _EPS).to(torch.float32).to(torch.float64)
-                    out = (total / denom).to(torch.float32)
-                else:
-                    out = (total * scale).to(torch.float32)
         if needs_grad:
-            ctx.save_for_backward(x, lab, w if w is not None else stats, stats)
+            ctx.save_for_backward(x, lab, w if w is not None else stats, stats, grad if fused else stats)
             ctx.has_w = w is not None
             ctx.pos_weight = pos_weight
+            ctx.fused = fused
+            ctx.consumed = False
             ctx.cfg = (reduction, scale, use_nvalid, int(ignore_index), bool(single))
         return out
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        x, lab, w, stats = ctx.saved_tensors
+        x, lab, w, stats, fgrad = ctx.saved_tensors
         reduction, scale, use_nvalid, ignore_index, single = ctx.cfg
         N, Cc = x.shape[0], x.shape[1]
         HW = x[0, 0].numel()
         dev = x.device
+        none = (None,) * 13
         with torch.cuda.device(dev):
+            if ctx.fused:
+                if ctx.consumed:
+                    raise RuntimeError("the single-pass loss graph can be back-propagated once; build the loss with "
+                                       "single_pass=False to call backward() repeatedly (retain_graph)")
+                ctx.consumed = True
+                gs = g.detach().to(torch.float32).reshape(()).contiguous()
+                _lib.check(lib.b200seg_scale_inplace(fgrad.data_ptr(), _lib.LOGIT_DTYPES[fgrad.dtype], fgrad.numel(),
+                                                     gs.data_ptr(), _lib.stream_ptr(dev)))
+                return (fgrad,) + none
             grad = torch.empty_like(x)
             d = _lib.BceDesc()
             d.logits = x.data_ptr(); d.labels = lab.data_ptr()
@@ -101,14 +125,18 @@ class _BceFunction(torch.autograd.Function):
             d.grad_logits = grad.data_ptr()
             d.stats = stats.data_ptr()
             _lib.check(lib.b200seg_bce_bwd(C.byref(d), _lib.stream_ptr(dev)))
-        return grad, None, None, None, None, None, None, None, None, None
+        return (grad,) + none
 
 
 def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=None, class_weight=None,
-                         ignore_index=-100, avg_non_ignore=False, **kwargs):
+                         ignore_index=-100, avg_non_ignore=False, _loss_weight=1.0, _single_pass=True, _acc_out=None,
+                         _acc_ignore=None, **kwargs):
     """Same arguments and results as the reference (:100-164). ``pred`` (N,C,H,W) with ``label`` (N,H,W) expands
     the label to one-hot inside the kernel; ``pred`` (N,1,H,W) treats the label (0/1) as the target (:126-134);
-    ``pred`` and ``label`` of equal shape use the label as a soft target mask as the reference does."""
+    ``pred`` and ``label`` of equal shape use the label as a soft target mask as the reference does.
+    ``_loss_weight`` / ``_single_pass`` are this package's own (CrossEntropyLoss folds its loss_weight into the launch);
+    ``_acc_out`` (a (1,) float32 CUDA tensor) receives the top-1 accuracy of ``pred`` against ``label`` over the pixels
+    whose label is not ``_acc_ignore`` from the same launch (fused_resize_losses: decode_head.py:295)."""
     if reduction not in ('none', 'mean', 'sum'):
         raise ValueError('%s is not a valid value for reduction' % reduction)
     if avg_factor is not None and reduction == 'sum':
@@ -128,7 +156,8 @@ def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=
                 raise NotImplementedError('binary_cross_entropy with element-wise targets supports a scalar class_weight only '
                                           '(got %d entries)' % pos_w.numel())
         out = _BceFunction.apply(pred.reshape(-1, 1, 1), label.reshape(-1, 1), None if weight is None else weight.reshape(-1, 1),
-                                 pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, True, torch.is_grad_enabled())
+                                 pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, True, torch.is_grad_enabled(),
+                                 float(_loss_weight), bool(_single_pass))
         if reduction == 'none':
             out = out.reshape(shape)
         if pred.dtype != torch.float32 and not torch.is_autocast_enabled():
@@ -142,7 +171,7 @@ def binary_cross_entropy(pred, label, weight=None, reduction='mean', avg_factor=
     if class_weight is not None:
         pos_w = torch.as_tensor(class_weight, dtype=torch.float32, device=pred.device).contiguous()
     out = _BceFunction.apply(x, label, weight, pos_w, reduction, avg_factor, ignore_index, avg_non_ignore, single,
-                             torch.is_grad_enabled())
+                             torch.is_grad_enabled(), float(_loss_weight), bool(_single_pass), _acc_out, _acc_ignore)
     if reduction == 'none':
         out = out.reshape(pred.shape)
         if single:

@@ -121,9 +121,10 @@ class CrossEntropyLoss(nn.Module):
             from ._bce import binary_cross_entropy
             assert reduction_override in (None, 'none', 'mean', 'sum')
             reduction = reduction_override if reduction_override else self.reduction
-            return self.loss_weight * binary_cross_entropy(
+            return binary_cross_entropy(
                 cls_score, label, weight, class_weight=self._class_weight_on(cls_score.device), reduction=reduction,
-                avg_factor=avg_factor, avg_non_ignore=self.avg_non_ignore, ignore_index=ignore_index, **kwargs)
+                avg_factor=avg_factor, avg_non_ignore=self.avg_non_ignore, ignore_index=ignore_index,
+                _loss_weight=float(self.loss_weight), _single_pass=bool(self.single_pass), **kwargs)
         spec = self.spec(cls_score.device, weight, avg_factor, reduction_override, ignore_index)
         pred4, lab, w, restore = _as_image(cls_score, label, weight)
         loss, _, _ = run_fused(pred4, lab, w, spec)

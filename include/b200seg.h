@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200SEG_ABI_VERSION 13
+#define B200SEG_ABI_VERSION 14
 
 /* logit element types */
 enum { B200SEG_F32 = 0, B200SEG_BF16 = 1, B200SEG_F16 = 2 };
@@ -234,8 +234,18 @@ typedef struct b200seg_bce_desc {
   float*  loss_elem;            /* forward: (N,C,HW) f32 per-element loss or NULL                 */
   const float* grad_out;        /* backward: scalar f32 (device) or NULL                          */
   const float* grad_elem;       /* backward: (N,C,HW) f32 upstream gradient (reduction='none')    */
-  void*   grad_logits;          /* backward: (N,C,HW) logit_dtype                                 */
-  uint64_t* stats;              /* [0] double: sum of weighted losses; [1] int64: valid pixels    */
+  void*   grad_logits;          /* backward: (N,C,HW) logit_dtype. FORWARD with grad_logits != NULL = single pass: the
+                                 * gradient grad_scale_host * d(sum of losses)/d logits is written too (upstream gradient
+                                 * taken as 1: rescale with b200seg_scale_inplace); needs use_nvalid == 0, loss_elem NULL */
+  uint64_t* stats;              /* 8 words: [0] double: sum of weighted losses; [1] int64: valid pixels; [2] CTAs done;
+                                 * [3] top-1 hits; [4] pixels counted by the accuracy                  */
+  float*  out;                  /* forward: f32 scalar = out_scale_host * sum [/ (n_valid*C + eps) when use_nvalid],
+                                 * written on the device by the last CTA; or NULL                  */
+  float   out_scale_host;
+  int32_t acc_has_ignore;       /* accuracy(..., ignore_index=None) -> 0                           */
+  float*  acc_out;              /* forward: (1,) f32 top-1 accuracy of the same launch (accuracy.py:41-60: arg-max over the
+                                 * class logits == label, over pixels with label != acc_ignore_index), or NULL */
+  int64_t acc_ignore_index;
 } b200seg_bce_desc;
 int b200seg_bce_fwd(const b200seg_bce_desc* d, void* stream);   /* zeroes stats, then accumulates     */
 int b200seg_bce_bwd(const b200seg_bce_desc* d, void* stream);   /* reads stats[1] when use_nvalid     */

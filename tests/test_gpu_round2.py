@@ -492,3 +492,76 @@ def test_resize_fused_many_classes_class_tiled(B):
         r = B.fused_resize_losses(x, y, B.CrossEntropyLoss(), ignore_index=255)
     ro = O.head_losses(x, y, [('ce', {}, 'loss_ce')], ignore_index=255)
     assert rel_err(r['loss_ce'], ro['loss_ce']) <= LOSS_TOL
+
+
+def test_bce_single_pass_matches_two_pass_and_oracle(B):
+    """Sigmoid CE (row f1): the single-pass plan (gradient written by the forward launch, reduced scalar by its last CTA)
+    against the two-pass plan and the oracle — loss_weight, pixel weights, pos_weight, every reduction with a known
+    denominator, an upstream gradient != 1 (the late rescale), bf16; float16 and avg_non_ignore stay two-pass."""
+    x0 = synth_logits((3, 4, 40, 56), 17, device='cuda', margin=False)
+    y = synth_labels((3, 40, 56), 4, 17, ignore_index=255, block=4, device='cuda')
+    w = torch.rand((3, 40, 56), device='cuda') + 0.5
+    for kw, fkw in ((dict(), dict()), (dict(reduction='sum', loss_weight=0.3), dict()),
+                    (dict(loss_weight=2.0), dict(weight=w)),
+                    (dict(), dict(avg_factor=1234.0)), (dict(avg_non_ignore=True), dict())):
+        res = []
+        for single in (True, False):
+            m = B.CrossEntropyLoss(use_sigmoid=True, **kw)
+            m.single_pass = single
+            x = x0.clone().requires_grad_(True)
+            loss = m(x, y, ignore_index=255, **fkw)
+            (loss * 3.0).backward()
+            res.append((loss.detach(), x.grad))
+        xo = x0.clone().requires_grad_(True)
+        kwo = dict(kw)
+        lw = kwo.pop('loss_weight', 1.0)
+        if 'class_weight' in kwo:
+            kwo['class_weight'] = xo.new_tensor(kwo['class_weight'])
+        lo = lw * O.binary_cross_entropy(xo, y, fkw.get('weight'), ignore_index=255, avg_factor=fkw.get('avg_factor'), **kwo)
+        (lo * 3.0).backward()
+        for loss, grad in res:
+            assert rel_err(loss, lo) <= LOSS_TOL, (kw, float(loss), float(lo))
+            assert rel_err(grad, xo.grad) <= GRAD_TOL, kw
+    # pos_weight = class_weight (:160-161) on (N,C) predictions, where the reference's broadcast lines up with the classes
+    g = torch.Generator().manual_seed(3)
+    p2 = torch.randn((600, 5), generator=g).cuda()
+    y2 = torch.randint(0, 5, (600,), generator=g).cuda()
+    y2[::7] = 255
+    cwl = [0.5, 1.0, 2.0, 1.5, 3.0]
+    for single in (True, False):
+        m = B.CrossEntropyLoss(use_sigmoid=True, class_weight=cwl, loss_weight=1.7)
+        m.single_pass = single
+        x = p2.clone().requires_grad_(True)
+        m(x, y2, ignore_index=255).backward()
+        xo = p2.clone().requires_grad_(True)
+        lo = 1.7 * O.binary_cross_entropy(xo, y2, ignore_index=255, class_weight=xo.new_tensor(cwl))
+        lo.backward()
+        assert rel_err(x.grad, xo.grad) <= GRAD_TOL
+    # the head call: a lone sigmoid loss also yields the top-1 accuracy from the same launch (decode_head.py:295)
+    x = x0.clone().requires_grad_(True)
+    r = B.fused_resize_losses(x, y.unsqueeze(1), B.CrossEntropyLoss(use_sigmoid=True), ignore_index=255)
+    r['loss_ce'].backward()
+    xo = x0.clone().requires_grad_(True)
+    lo = O.binary_cross_entropy(xo, y, ignore_index=255)
+    lo.backward()
+    assert rel_err(r['loss_ce'], lo) <= LOSS_TOL and rel_err(x.grad, xo.grad) <= GRAD_TOL
+    ao = O.accuracy(x0, y, ignore_index=255)
+    assert r['acc_seg'].shape == (1,) and abs(float(r['acc_seg']) - float(ao)) <= 1e-4 * float(ao)
+    # the single-pass graph is consumed by its backward (like the soft-max path's flat plan)
+    m = B.CrossEntropyLoss(use_sigmoid=True)
+    x = x0.clone().requires_grad_(True)
+    loss = m(x, y, ignore_index=255)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+    # float16: two-pass (a large upstream gradient must meet the 1/numel factor in fp32), as ADVICE r1 asked of the flat plan
+    xh = x0.half().requires_grad_(True)
+    lh = B.CrossEntropyLoss(use_sigmoid=True)(xh, y, ignore_index=255)
+    (lh.float() * 16384.0).backward()                     # (the loss itself comes back as float16: 65536 would overflow it)
+    xr = x0.half().float().requires_grad_(True)
+    (O.binary_cross_entropy(xr, y, ignore_index=255) * 16384.0).backward()
+    assert rel_err(xh.grad.float(), xr.grad) <= 2e-3
+    # no_grad / forward only
+    with torch.no_grad():
+        ln = B.CrossEntropyLoss(use_sigmoid=True)(x0, y, ignore_index=255)
+    assert rel_err(ln, O.binary_cross_entropy(x0, y, ignore_index=255)) <= LOSS_TOL
