@@ -16,11 +16,13 @@ side stream (--allreduce-every 1 issues it every step).
                 fused_resize_losses + backward, D2H read of the loss.
   roofline      the dominant kernel (up_gen_kernel) timed alone with CUDA events: algorithmic bytes / time vs the
                 measured HBM copy peak (MEASURED_PEAKS.json).
-  cpu_baseline  the oracle (the reference's ATen chain restated, oracle/oracle.py) on the host cores, bounded sample.
+  cpu_baseline  the reference's own resize / CrossEntropyLoss / accuracy (oracle/_ref: byte code compiled from its files
+                by oracle/build_ref.py; kind "reference") on the host cores, bounded sample; the oracle port
+                (oracle/oracle.py; kind "port") when oracle/_ref is absent.
   workloads     extra single-GPU results for BASELINE configs 3, 4 and 5 (HBM-bound shapes), each with its roofline.
 
-`--impl reference` times the reference's CPU implementation of the same workload (the oracle port; the reference is
-pure Python and cannot travel to the GPU box) on all host threads.
+`--impl reference` times the reference's CPU implementation of the same workload on all host threads: its own files,
+executed from oracle/_ref byte code (the sources stay in /root/reference; see oracle/build_ref.py), else the oracle port.
 """
 import argparse
 import json
@@ -133,16 +135,49 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
+_REF = None
+
+
+def cpu_kind():
+    """'reference' when the reference's own files can be executed here (oracle/_ref: byte code compiled from the sources
+    under /root/reference by oracle/build_ref.py — it travels to the GPU box), else 'port' (oracle/oracle.py, which
+    tests/test_reference_live.py pins bit for bit to those files)."""
+    global _REF
+    if _REF is None:
+        from oracle import ref_loader
+        try:
+            _REF = (ref_loader.load(), ref_loader.origin()) if ref_loader.available() else (None, None)
+        except Exception:
+            _REF = (None, None)
+    return 'reference' if _REF[0] is not None else 'port'
+
+
 def cpu_step(x, y, ignore):
-    from oracle import oracle as O
     x.grad = None
-    out = O.head_losses(x, y, [('ce', {}, 'loss_ce')], align_corners=False, ignore_index=ignore)
+    if cpu_kind() == 'reference':
+        # BaseDecodeHead.losses as the reference runs it (models/decode_heads/decode_head.py:261-295), on its own code
+        R = _REF[0]
+        if not hasattr(R, '_bench_ce'):
+            R._bench_ce = R.CrossEntropyLoss()
+        full = R.resize(input=x, size=y.shape[2:], mode='bilinear', align_corners=False)
+        lab = y.squeeze(1)
+        out = {'loss_ce': R._bench_ce(full, lab, weight=None, ignore_index=ignore),
+               'acc_seg': R.accuracy(full, lab, ignore_index=ignore)}
+    else:
+        from oracle import oracle as O
+        out = O.head_losses(x, y, [('ce', {}, 'loss_ce')], align_corners=False, ignore_index=ignore)
     out['loss_ce'].backward()
     return out
 
 
+def cpu_kind_note():
+    return ('the UNMODIFIED reference files (resize, CrossEntropyLoss, accuracy) executed from oracle/_ref byte code'
+            if cpu_kind() == 'reference' else 'oracle port of the reference chain (oracle/oracle.py)')
+
+
 def run_cpu(steps, warmup, n_images):
-    """The reference's CPU path (oracle port) on a bounded sample: n_images of the C2 batch per step."""
+    """The reference's CPU path (its own files when oracle/_ref is present, else the oracle port) on a bounded sample:
+    n_images of the C2 batch per step."""
     warnings.simplefilter('ignore')
     torch.set_num_threads(os.cpu_count() or 1)
     x = make_logits((n_images, C2['C'], C2['h'], C2['w']), 1234 + 100).requires_grad_(True)
@@ -169,9 +204,9 @@ def reference_main(args):
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(),
-        'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
+        'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': cores, 'kind': cpu_kind(),
                          'sample': 'full batch: %d of the %d images per step (resize + CE fwd/bwd + accuracy, torch %s CPU, '
-                                   'os.cpu_count()=%s)' % (n_img, C2['N'], torch.__version__, os.cpu_count())},
+                                   'os.cpu_count()=%s); %s' % (n_img, C2['N'], torch.__version__, os.cpu_count(), cpu_kind_note())},
         'e2e': {'value': value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -431,9 +466,10 @@ def b200_main(args):
             except Exception as ex:  # extras never invalidate the headline
                 extras = {'error': repr(ex)}
         v, ms_cpu = run_cpu(6, 1, C2['N'])
-        cpu_base = {'value': v, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+        cpu_base = {'value': v, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': cpu_kind(),
                     'sample': 'full C2 batch (8 images), 6 timed steps of resize + CE fwd/bwd + accuracy on the host CPU '
-                              '(torch %s, os.cpu_count()=%s), %.0f ms/step' % (torch.__version__, os.cpu_count(), ms_cpu)}
+                              '(torch %s, os.cpu_count()=%s), %.0f ms/step; %s'
+                              % (torch.__version__, os.cpu_count(), ms_cpu, cpu_kind_note())}
         # the same restatement on CUDA tensors: the reference's unfused ATen chain on THIS GPU ("the kernel to
         # beat on the same box") — a reported baseline like cpu_baseline, never on the product path
         try:

@@ -1,20 +1,35 @@
-"""Loads the reference's own hot-path files from /root/reference BY FILE PATH (test infrastructure).
+"""Loads the reference's own hot-path files BY FILE PATH (test infrastructure).
 
 The reference cannot be imported as a package (core/__init__.py:7 imports a missing core.sampler; mmcv,
-albumentations and prettytable are absent), but the six files on the path load verbatim once four
-trivial stand-ins are seeded in sys.modules. Only available where /root/reference exists
-(this container) — never on the GPU box; used to generate tests/golden/ and by tests/test_reference_live.py.
+albumentations and prettytable are absent), but the files on the path load verbatim once four trivial stand-ins are
+seeded in sys.modules. Two places to load them from:
+  * /root/reference (this container): the sources where they lie — used to generate tests/golden/ and by
+    tests/test_reference_live.py;
+  * oracle/_ref/ (byte code compiled from those sources by oracle/build_ref.py; git-ignored, travels to the GPU box):
+    the same unmodified code where /root/reference does not exist — the CPU arm of bench.py.
 """
+import importlib.machinery
 import importlib.util
 import os
 import sys
 import types
 
+from . import build_ref
+
 REF_ROOT = os.environ.get('B200SEG_REFERENCE_ROOT', '/root/reference')
 
 
-def available():
+def source_available():
     return os.path.isfile(os.path.join(REF_ROOT, 'models', 'losses', 'cross_entropy_loss.py'))
+
+
+def available():
+    return source_available() or build_ref.usable()
+
+
+def origin():
+    """'source' (/root/reference), 'bytecode' (oracle/_ref) or None."""
+    return 'source' if source_available() else ('bytecode' if build_ref.usable() else None)
 
 
 def _stub(name, **attrs):
@@ -25,7 +40,12 @@ def _stub(name, **attrs):
 
 
 def _load(name, rel):
-    spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+    src = os.path.join(REF_ROOT, rel)
+    if os.path.isfile(src):
+        spec = importlib.util.spec_from_file_location(name, src)
+    else:
+        pyc = build_ref.compiled_path(rel)
+        spec = importlib.util.spec_from_file_location(name, pyc, loader=importlib.machinery.SourcelessFileLoader(name, pyc))
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
@@ -41,7 +61,7 @@ def load():
     if _CACHE is not None:
         return _CACHE
     if not available():
-        raise RuntimeError('reference tree not found at %s' % REF_ROOT)
+        raise RuntimeError('reference tree not found at %s and no byte code under oracle/_ref' % REF_ROOT)
     saved = {k: sys.modules.get(k) for k in ('mmcv', 'prettytable', 'models', 'models.builder', 'models.losses',
                                               'models.losses.utils', 'core', 'core.fileio')}
 

@@ -8,7 +8,7 @@ import torch
 from oracle import oracle as O
 from oracle import ref_loader
 
-pytestmark = pytest.mark.skipif(not ref_loader.available(), reason='/root/reference is not present on this machine')
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason='neither /root/reference nor oracle/_ref byte code on this machine')
 
 
 @pytest.fixture(scope='module')
@@ -92,3 +92,26 @@ def test_lovasz_bitwise(ref, kw):
     b = O.lovasz_loss_module(xo, y, ignore_index=255, **kw)
     b.sum().backward()
     assert torch.equal(a, b) and torch.equal(xr.grad, xo.grad)
+
+
+@pytest.mark.skipif(not ref_loader.source_available(), reason='needs the reference sources to compile')
+def test_bytecode_form_is_the_same_code(tmp_path, monkeypatch):
+    """oracle/_ref (what travels to the GPU box) is the reference's code: compiled from the sources where they lie, every
+    function's byte code equals the source module's, and a fresh load from byte code alone runs the head chain."""
+    from oracle import build_ref
+    assert build_ref.build() == len(build_ref.FILES) and build_ref.usable()
+    src = ref_loader.load()
+    monkeypatch.setattr(ref_loader, 'REF_ROOT', str(tmp_path))
+    monkeypatch.setattr(ref_loader, '_CACHE', None)
+    assert ref_loader.origin() == 'bytecode'
+    bc = ref_loader.load()
+    for name in ('resize', 'cross_entropy', 'binary_cross_entropy', 'accuracy', 'weight_reduce_loss', 'lovasz_grad'):
+        assert getattr(bc, name).__code__.co_code == getattr(src, name).__code__.co_code, name
+    for name in ('CrossEntropyLoss', 'DiceLoss', 'TverskyLoss', 'LovaszLoss'):
+        assert getattr(bc, name).forward.__code__.co_code == getattr(src, name).forward.__code__.co_code, name
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((2, 5, 6, 7), generator=g)
+    y = torch.randint(0, 5, (2, 12, 14), generator=g)
+    a = src.CrossEntropyLoss()(src.resize(x, size=(12, 14), mode='bilinear', align_corners=False), y, ignore_index=255)
+    b = bc.CrossEntropyLoss()(bc.resize(x, size=(12, 14), mode='bilinear', align_corners=False), y, ignore_index=255)
+    assert torch.equal(a, b)
