@@ -89,6 +89,35 @@ struct ClassDecoder {
       }
     }
   }
+  // up to 8 consecutive samples starting at element i (any alignment); slots >= n read as ignored. The dtype switch
+  // is taken once, the loads of a case are independent of each other.
+  __device__ __forceinline__ void upto8(const void* p, size_t i, int n, int (&o)[8]) const {
+    if (dt == B200SEG_L_F32) {
+      const float* q = reinterpret_cast<const float*>(p) + i;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = k < n ? __ldg(q + k) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = k < n ? from_f32(v[k]) : kIgnored;
+    } else if (dt == B200SEG_L_I64) {
+      const uint2* q = reinterpret_cast<const uint2*>(p) + i;
+      uint2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = k < n ? __ldg(q + k) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = k < n ? from_i64(v[k].x, v[k].y) : kIgnored;
+    } else if (dt == B200SEG_L_U8) {
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(p) + i;
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = k < n ? (int)__ldg(q + k) : 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = k < n ? from_i32(v[k]) : kIgnored;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = k < n ? one(p, i + k) : kIgnored;
+    }
+  }
   // 8 consecutive samples starting at element i (i % 8 == 0, base 16-byte aligned)
   __device__ __forceinline__ void eight(const void* p, size_t i, int (&o)[8]) const {
     const char* b = reinterpret_cast<const char*>(p);
@@ -425,10 +454,109 @@ __device__ __forceinline__ void resize_pixels_simple(const b200seg_image& im, lo
   }
 }
 
+// Band form of the (row, run) unit for UP-SAMPLED rows: R output rows that share the same pair of source rows (a "band" of
+// the row index map, exactly like a run of the column map) are taken by one thread together. The horizontal sums of
+// ATen's expression, X = fma(w0, v00, w1 v01) and Y = fma(w0, v10, w1 v11), depend on the source rows and the output
+// column only, so they are formed ONCE per class and column and shared by the R rows; a row then costs FMUL + FFMA and
+// the compare / select triple: 6.4 issue slots per class-pixel at R = 4 against 10.9 for the row form, with the
+// per-unit work (index decomposition, weights, tap addresses) spread over 4 x as many pixels. Same operations on the
+// same operands as aten_bilerp: bit-exact. The R rows' class indices sit in the bytes of one register (C <= 255):
+// a predicated PRMT replaces the select.
+template <int K> __device__ __forceinline__ void argmax_step(float& best, unsigned& bi4, float z, unsigned c) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %0;\n\t@p mov.f32 %0, %2;\n\t@p prmt.b32 %1, %1, %3, %4;\n\t}"
+      : "+f"(best), "+r"(bi4)
+      : "f"(z), "r"(c), "n"(K == 0 ? 0x3214 : (K == 1 ? 0x3240 : (K == 2 ? 0x3410 : 0x4210))));
+}
+
+template <typename T, int THREADS, bool PRIVATE, int R>
+__device__ __forceinline__ void resize_band_units(const b200seg_image& im, const int* run_x, const int* run_y, int G, unsigned u_begin,
+                                                  unsigned u_end, float sh, float sw, bool ac, int C, const ClassDecoder& dgt,
+                                                  long long* pout, Counters<THREADS, PRIVATE>& ctr) {
+  static_assert(R == 4, "the row slots are the four bytes of a register");
+  constexpr int PXC = 8;
+  const unsigned runs = (unsigned)im.w + 1u, GR = (unsigned)G * runs;
+  const int hw = im.h * im.w;
+  const T* base = reinterpret_cast<const T*>(im.pred);
+  for (unsigned u = u_begin + threadIdx.x; u < u_end; u += THREADS) {
+    const unsigned b = u / GR, rem = u - b * GR, sgrp = rem / runs, r = rem - sgrp * runs;
+    const int Y0 = run_y[b] + (int)sgrp * R, Yend = run_y[b + 1];
+    const int X0 = run_x[r], X1 = run_x[r + 1];
+    if (Y0 >= Yend || X0 >= X1) continue;
+    const int nrow = min(R, Yend - Y0);
+    int y0, y1, x0, x1;
+    float h0[R], h1[R], lxf;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {                          // (y0, y1) is the same for every row of the band
+      resize_src(sh, Y0 + min(k, nrow - 1), im.h, ac, y0, y1, h1[k]);
+      h0[k] = __fsub_rn(1.f, h1[k]);
+    }
+    resize_src(sw, X0, im.w, ac, x0, x1, lxf);
+    const int o00 = y0 * im.w + x0, o01 = y0 * im.w + x1, o10 = y1 * im.w + x0, o11 = y1 * im.w + x1;
+    for (int Xc = X0; Xc < X1; Xc += PXC) {
+      const int npx = min(PXC, X1 - Xc);
+      float w0[PXC], w1[PXC], best[R][PXC];
+      unsigned bi4[PXC];
+#pragma unroll
+      for (int j = 0; j < PXC; ++j) {
+        const float s = aten_src_index(sw, Xc + min(j, npx - 1), ac);
+        w1[j] = __fsub_rn(s, (float)x0);
+        w0[j] = __fsub_rn(1.f, w1[j]);
+        bi4[j] = 0u;
+#pragma unroll
+        for (int k = 0; k < R; ++k) best[k][j] = neg_inf();
+      }
+      const T* pl = base;
+      T ta = __ldg(pl + o00), tb = __ldg(pl + o01), tc = __ldg(pl + o10), td = __ldg(pl + o11);
+      for (int c = 0; c < C; ++c) {
+        const float a = to_float<T>(ta), bb = to_float<T>(tb), cc = to_float<T>(tc), d = to_float<T>(td);
+        pl += hw;
+        if (c + 1 < C) {                                   // the next class's taps are in flight during this class's arithmetic
+          ta = __ldg(pl + o00); tb = __ldg(pl + o01); tc = __ldg(pl + o10); td = __ldg(pl + o11);
+        }
+#pragma unroll
+        for (int j = 0; j < PXC; ++j) {
+          const float Xv = __fmaf_rn(w0[j], a, __fmul_rn(w1[j], bb));
+          const float Yv = __fmaf_rn(w0[j], cc, __fmul_rn(w1[j], d));
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            float z = __fmaf_rn(h0[k], Xv, __fmul_rn(h1[k], Yv));
+            if constexpr (sizeof(T) == 2) z = to_float<T>(from_float<T>(z));   // F.interpolate returns the logit dtype
+            if (k == 0) argmax_step<0>(best[k][j], bi4[j], z, (unsigned)c);   // strict >: lowest index wins ties
+            else if (k == 1) argmax_step<1>(best[k][j], bi4[j], z, (unsigned)c);
+            else if (k == 2) argmax_step<2>(best[k][j], bi4[j], z, (unsigned)c);
+            else argmax_step<3>(best[k][j], bi4[j], z, (unsigned)c);
+          }
+        }
+      }
+      // write-out, one row at a time (a rolled loop: unrolled it was 4000 instructions of straight-line code)
+#pragma unroll 1
+      for (int k = 0; k < nrow; ++k) {
+        const size_t px0 = (size_t)(Y0 + k) * im.W + Xc;
+        int gv[PXC];
+        dgt.upto8(im.gt, px0, npx, gv);
+        const int sh8 = 8 * k;
+        if (pout) {
+#pragma unroll
+          for (int j = 0; j < PXC; ++j)
+            if (j < npx) pout[px0 + j] = (long long)((bi4[j] >> sh8) & 0xffu);
+        }
+#pragma unroll
+        for (int j = 0; j < PXC; ++j) {
+          const int bi = (int)((bi4[j] >> sh8) & 0xffu);
+          if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv[j]);
+          else if (gv[j] != kIgnored) ctr.update(bi, gv[j]);
+        }
+      }
+    }
+  }
+}
+
 template <typename T, int THREADS, bool PRIVATE>
-__global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfParams p, const int align_corners) {
+__global__ void __launch_bounds__(THREADS, 2) confusion_resize_kernel(const ConfParams p, const int align_corners) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int run_x[kRunTableMax + 2];
+  __shared__ int run_y[kRunTableMax + 2];
+  __shared__ int band_max;
   Counters<THREADS, PRIVATE> ctr{reinterpret_cast<unsigned int*>(smem_raw), p.C};
   ctr.zero();
   __syncthreads();
@@ -465,14 +593,45 @@ __global__ void __launch_bounds__(THREADS) confusion_resize_kernel(const ConfPar
     }
     const int hw = im.h * im.w;
     const T* base = reinterpret_cast<const T*>(im.pred);
-    // run starts of this image: run r = columns [run_x[r], run_x[r + 1])
+    // run starts of this image: run r = columns [run_x[r], run_x[r + 1]); bands of rows likewise in run_y
+    constexpr int kBandRows = 4;
+    const bool band_ok = im.h + 2 <= kRunTableMax && C <= 255;
     __syncthreads();
+    if (threadIdx.x == 0) band_max = 0;
     for (int r = threadIdx.x; r <= im.w + 1; r += THREADS) run_x[r] = aten_run_start(sw, r, im.w, im.W, ac);
+    if (band_ok)
+      for (int r = threadIdx.x; r <= im.h + 1; r += THREADS) run_y[r] = aten_run_start(sh, r, im.h, im.H, ac);
     __syncthreads();
-    // this CTA's share of the image's (row, run) units: the image's chunks split the units evenly
+    if (band_ok) {
+      int longest = 0;
+      for (int r = threadIdx.x; r <= im.h; r += THREADS) longest = max(longest, run_y[r + 1] - run_y[r]);
+      if (longest > 1) atomicMax(&band_max, longest);
+      __syncthreads();
+    }
     const int runs = im.w + 1;
-    const long long units = (long long)im.H * runs;
     const long long img_chunks = p.chunk_prefix[img + 1] - p.chunk_prefix[img];
+    // up-sampled rows (some band holds >= 2 rows): units of (band, group of kBandRows rows, run)
+    const int G = (band_max + kBandRows - 1) / kBandRows;
+    const long long band_units = (long long)(im.h + 1) * G * runs;
+    if (band_ok && band_max >= 2 && band_units < (1ll << 31)) {
+      const long long upc = (band_units + img_chunks - 1) / img_chunks;
+      const long long u_begin = (chunk - p.chunk_prefix[img]) * upc;
+      long long u_end = (img_chunk_end - p.chunk_prefix[img]) * upc;
+      if (u_end > band_units) u_end = band_units;
+      if (u_begin < u_end)
+        resize_band_units<T, THREADS, PRIVATE, kBandRows>(im, run_x, run_y, G, (unsigned)u_begin, (unsigned)u_end, sh, sw, ac, C, dgt,
+                                                          pout, ctr);
+      if (!p.totals_only) {
+        ctr.flush(p.areas + (size_t)img * 3 * C);
+      } else {
+        since_flush += img_chunk_end - chunk;
+        if (since_flush >= kMaxChunksPerFlush) { ctr.flush(p.areas); since_flush = 0; }
+      }
+      chunk = img_chunk_end;
+      continue;
+    }
+    // this CTA's share of the image's (row, run) units: the image's chunks split the units evenly
+    const long long units = (long long)im.H * runs;
     const long long upc = (units + img_chunks - 1) / img_chunks;
     const long long u_begin = (chunk - p.chunk_prefix[img]) * upc;
     long long u_end = (img_chunk_end - p.chunk_prefix[img]) * upc;

@@ -699,3 +699,25 @@ def test_areas_from_lowres_logits_resize_fused(B, ac, dtype):
                             show_result=False, align_corners=ac)
         ev.process(0, {'decode': [l.clone() for l in lm]}, {'ori_gt': gts[:4]})
         assert torch.equal(ev.area_totals('decode')[[0, 2, 3]], gm.sum(0).cpu())
+
+
+@pytest.mark.parametrize('C', [19, 40, 300])
+def test_areas_resize_fused_band_and_row_forms(B, C):
+    """The two unit forms of confusion_resize_kernel (bands of up-sampled rows that share their horizontal sums; single
+    rows otherwise) and both counter flavours (private columns for small C, shared atomics above; byte-packed class
+    indices need C <= 255): long bands split into several groups, ragged last groups, rows down-sampled while columns
+    are up-sampled, one-row and one-column logits, several images of different shapes in one launch — all bit-exact."""
+    cases = [((1, C, 8, 16), (100, 129)), ((1, C, 5, 40), (64, 40)), ((1, C, 40, 6), (17, 90)), ((1, C, 1, 9), (13, 31)),
+             ((1, C, 6, 1), (50, 7)), ((1, C, 33, 65), (264, 520)), ((1, C, 3, 3), (2, 2)), ((1, C, 16, 16), (17, 19))]
+    g = torch.Generator().manual_seed(777 + C)
+    logits = [(torch.randn(s, generator=g) * 3).cuda() for s, _ in cases]
+    gts = [synth_labels((1,) + gt, min(C, 250), 300 + i, ignore_index=255)[0].float().cuda() for i, (_, gt) in enumerate(cases)]
+    for ac in (False, True):
+        maps = []
+        got = B.areas_device(logits, gts, C, 255, from_logits=True, align_corners=ac, pred_maps=maps)
+        preds = [O.resize(l, size=tuple(gt.shape), mode='bilinear', align_corners=ac).argmax(dim=1).squeeze(0)
+                 for l, gt in zip(logits, gts)]
+        for i, (p_, m_) in enumerate(zip(preds, maps)):
+            assert torch.equal(p_, m_), (ac, i, int((p_ != m_).sum()))
+        assert torch.equal(got, _areas_oracle_gpu(preds, gts, C, 255))
+        assert torch.equal(B.area_totals_device(logits, gts, C, 255, from_logits=True, align_corners=ac), got.sum(0))
