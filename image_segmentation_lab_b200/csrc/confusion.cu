@@ -89,33 +89,33 @@ struct ClassDecoder {
       }
     }
   }
-  // up to 8 consecutive samples starting at element i (any alignment); slots >= n read as ignored. The dtype switch
+  // up to N consecutive samples starting at element i (any alignment); slots >= n read as ignored. The dtype switch
   // is taken once, the loads of a case are independent of each other.
-  __device__ __forceinline__ void upto8(const void* p, size_t i, int n, int (&o)[8]) const {
+  template <int N> __device__ __forceinline__ void upto(const void* p, size_t i, int n, int (&o)[N]) const {
     if (dt == B200SEG_L_F32) {
       const float* q = reinterpret_cast<const float*>(p) + i;
-      float v[8];
+      float v[N];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = k < n ? __ldg(q + k) : 0.f;
+      for (int k = 0; k < N; ++k) v[k] = k < n ? __ldg(q + k) : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = k < n ? from_f32(v[k]) : kIgnored;
+      for (int k = 0; k < N; ++k) o[k] = k < n ? from_f32(v[k]) : kIgnored;
     } else if (dt == B200SEG_L_I64) {
       const uint2* q = reinterpret_cast<const uint2*>(p) + i;
-      uint2 v[8];
+      uint2 v[N];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = k < n ? __ldg(q + k) : make_uint2(0u, 0u);
+      for (int k = 0; k < N; ++k) v[k] = k < n ? __ldg(q + k) : make_uint2(0u, 0u);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = k < n ? from_i64(v[k].x, v[k].y) : kIgnored;
+      for (int k = 0; k < N; ++k) o[k] = k < n ? from_i64(v[k].x, v[k].y) : kIgnored;
     } else if (dt == B200SEG_L_U8) {
       const uint8_t* q = reinterpret_cast<const uint8_t*>(p) + i;
-      int v[8];
+      int v[N];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = k < n ? (int)__ldg(q + k) : 0;
+      for (int k = 0; k < N; ++k) v[k] = k < n ? (int)__ldg(q + k) : 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = k < n ? from_i32(v[k]) : kIgnored;
+      for (int k = 0; k < N; ++k) o[k] = k < n ? from_i32(v[k]) : kIgnored;
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = k < n ? one(p, i + k) : kIgnored;
+      for (int k = 0; k < N; ++k) o[k] = k < n ? one(p, i + k) : kIgnored;
     }
   }
   // 8 consecutive samples starting at element i (i % 8 == 0, base 16-byte aligned)
@@ -462,10 +462,75 @@ __device__ __forceinline__ void resize_pixels_simple(const b200seg_image& im, lo
 // per-unit work (index decomposition, weights, tap addresses) spread over 4 x as many pixels. Same operations on the
 // same operands as aten_bilerp: bit-exact. The R rows' class indices sit in the bytes of one register (C <= 255):
 // a predicated PRMT replaces the select.
-template <int K> __device__ __forceinline__ void argmax_step(float& best, unsigned& bi4, float z, unsigned c) {
-  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %0;\n\t@p mov.f32 %0, %2;\n\t@p prmt.b32 %1, %1, %3, %4;\n\t}"
+template <int K> __device__ __forceinline__ void argmax_step(float& best, unsigned& bi4, float z, unsigned c, float one) {
+  // The sweep sits on the ALU pipe (FSETP / FSEL / PRMT run at half rate) while the FMA pipe is a quarter busy: the value
+  // update is issued as a predicated FFMA, best = z * one + (-0) == z for every z, with `one` a run-time 1.0f the
+  // assembler cannot fold — it runs on the FMA pipe.
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %0;\n\t@p fma.rn.f32 %0, %2, %5, 0f80000000;\n\t@p prmt.b32 %1, %1, %3, %4;\n\t}"
       : "+f"(best), "+r"(bi4)
-      : "f"(z), "r"(c), "n"(K == 0 ? 0x3214 : (K == 1 ? 0x3240 : (K == 2 ? 0x3410 : 0x4210))));
+      : "f"(z), "r"(c), "n"(K == 0 ? 0x3214 : (K == 1 ? 0x3240 : (K == 2 ? 0x3410 : 0x4210))), "f"(one));
+}
+
+// One chunk of PXC columns (npx <= PXC of them live) of a band unit: class sweep + write-out of nrow rows.
+template <typename T, int THREADS, bool PRIVATE, int R, int PXC>
+__device__ __forceinline__ void band_chunk(const b200seg_image& im, const T* base, int hw, int C, int o00, int o01, int o10, int o11,
+                                           const float (&h0)[R], const float (&h1)[R], float sw, bool ac, int x0, int Xc, int npx,
+                                           int Y0, int nrow, const ClassDecoder& dgt, long long* pout,
+                                           Counters<THREADS, PRIVATE>& ctr) {
+  float w0[PXC], w1[PXC], best[R][PXC];
+  unsigned bi4[PXC];
+  const float one = __fmul_rn((float)blockDim.x, 1.f / THREADS);   // 1.0f, opaque to the assembler (see argmax_step)
+#pragma unroll
+  for (int j = 0; j < PXC; ++j) {
+    const float s = aten_src_index(sw, Xc + min(j, npx - 1), ac);
+    w1[j] = __fsub_rn(s, (float)x0);                       // ATen: lambda1 = src - (int)src, and (int)src == x0 in this run
+    w0[j] = __fsub_rn(1.f, w1[j]);
+    bi4[j] = 0u;
+#pragma unroll
+    for (int k = 0; k < R; ++k) best[k][j] = neg_inf();
+  }
+  const T* pl = base;
+  T ta = __ldg(pl + o00), tb = __ldg(pl + o01), tc = __ldg(pl + o10), td = __ldg(pl + o11);
+  for (int c = 0; c < C; ++c) {
+    const float a = to_float<T>(ta), bb = to_float<T>(tb), cc = to_float<T>(tc), d = to_float<T>(td);
+    pl += hw;
+    if (c + 1 < C) {                                       // the next class's taps are in flight during this class's arithmetic
+      ta = __ldg(pl + o00); tb = __ldg(pl + o01); tc = __ldg(pl + o10); td = __ldg(pl + o11);
+    }
+#pragma unroll
+    for (int j = 0; j < PXC; ++j) {
+      const float Xv = __fmaf_rn(w0[j], a, __fmul_rn(w1[j], bb));
+      const float Yv = __fmaf_rn(w0[j], cc, __fmul_rn(w1[j], d));
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        float z = __fmaf_rn(h0[k], Xv, __fmul_rn(h1[k], Yv));
+        if constexpr (sizeof(T) == 2) z = to_float<T>(from_float<T>(z));   // F.interpolate returns the logit dtype
+        if (k == 0) argmax_step<0>(best[k][j], bi4[j], z, (unsigned)c, one);   // strict >: lowest index wins ties
+        else if (k == 1) argmax_step<1>(best[k][j], bi4[j], z, (unsigned)c, one);
+        else if (k == 2) argmax_step<2>(best[k][j], bi4[j], z, (unsigned)c, one);
+        else argmax_step<3>(best[k][j], bi4[j], z, (unsigned)c, one);
+      }
+    }
+  }
+  // write-out, one row at a time (a rolled loop: unrolled it was 4000 instructions of straight-line code)
+#pragma unroll 1
+  for (int k = 0; k < nrow; ++k) {
+    const size_t px0 = (size_t)(Y0 + k) * im.W + Xc;
+    int gv[PXC];
+    dgt.template upto<PXC>(im.gt, px0, npx, gv);
+    const int sh8 = 8 * k;
+    if (pout) {
+#pragma unroll
+      for (int j = 0; j < PXC; ++j)
+        if (j < npx) pout[px0 + j] = (long long)((bi4[j] >> sh8) & 0xffu);
+    }
+#pragma unroll
+    for (int j = 0; j < PXC; ++j) {
+      const int bi = (int)((bi4[j] >> sh8) & 0xffu);
+      if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv[j]);
+      else if (gv[j] != kIgnored) ctr.update(bi, gv[j]);
+    }
+  }
 }
 
 template <typename T, int THREADS, bool PRIVATE, int R>
@@ -473,16 +538,17 @@ __device__ __forceinline__ void resize_band_units(const b200seg_image& im, const
                                                   unsigned u_end, float sh, float sw, bool ac, int C, const ClassDecoder& dgt,
                                                   long long* pout, Counters<THREADS, PRIVATE>& ctr) {
   static_assert(R == 4, "the row slots are the four bytes of a register");
-  constexpr int PXC = 8;
   const unsigned runs = (unsigned)im.w + 1u, GR = (unsigned)G * runs;
   const int hw = im.h * im.w;
   const T* base = reinterpret_cast<const T*>(im.pred);
-  for (unsigned u = u_begin + threadIdx.x; u < u_end; u += THREADS) {
-    const unsigned b = u / GR, rem = u - b * GR, sgrp = rem / runs, r = rem - sgrp * runs;
+  for (unsigned uw = u_begin + (threadIdx.x & ~31u); uw < u_end; uw += THREADS) {     // warp-uniform trip count
+    const unsigned u = uw + (threadIdx.x & 31u);
+    const unsigned uc = u < u_end ? u : u_end - 1u;
+    const unsigned b = uc / GR, rem = uc - b * GR, sgrp = rem / runs, r = rem - sgrp * runs;
     const int Y0 = run_y[b] + (int)sgrp * R, Yend = run_y[b + 1];
-    const int X0 = run_x[r], X1 = run_x[r + 1];
-    if (Y0 >= Yend || X0 >= X1) continue;
-    const int nrow = min(R, Yend - Y0);
+    const int X0 = run_x[r];
+    const int X1 = (u < u_end && Y0 < Yend) ? run_x[r + 1] : X0;     // an empty unit is a run without columns
+    const int nrow = max(1, min(R, Yend - Y0));
     int y0, y1, x0, x1;
     float h0[R], h1[R], lxf;
 #pragma unroll
@@ -490,62 +556,28 @@ __device__ __forceinline__ void resize_band_units(const b200seg_image& im, const
       resize_src(sh, Y0 + min(k, nrow - 1), im.h, ac, y0, y1, h1[k]);
       h0[k] = __fsub_rn(1.f, h1[k]);
     }
-    resize_src(sw, X0, im.w, ac, x0, x1, lxf);
+    resize_src(sw, X0 < im.W ? X0 : im.W - 1, im.w, ac, x0, x1, lxf);
     const int o00 = y0 * im.w + x0, o01 = y0 * im.w + x1, o10 = y1 * im.w + x0, o11 = y1 * im.w + x1;
-    for (int Xc = X0; Xc < X1; Xc += PXC) {
-      const int npx = min(PXC, X1 - Xc);
-      float w0[PXC], w1[PXC], best[R][PXC];
-      unsigned bi4[PXC];
-#pragma unroll
-      for (int j = 0; j < PXC; ++j) {
-        const float s = aten_src_index(sw, Xc + min(j, npx - 1), ac);
-        w1[j] = __fsub_rn(s, (float)x0);
-        w0[j] = __fsub_rn(1.f, w1[j]);
-        bi4[j] = 0u;
-#pragma unroll
-        for (int k = 0; k < R; ++k) best[k][j] = neg_inf();
-      }
-      const T* pl = base;
-      T ta = __ldg(pl + o00), tb = __ldg(pl + o01), tc = __ldg(pl + o10), td = __ldg(pl + o11);
-      for (int c = 0; c < C; ++c) {
-        const float a = to_float<T>(ta), bb = to_float<T>(tb), cc = to_float<T>(tc), d = to_float<T>(td);
-        pl += hw;
-        if (c + 1 < C) {                                   // the next class's taps are in flight during this class's arithmetic
-          ta = __ldg(pl + o00); tb = __ldg(pl + o01); tc = __ldg(pl + o10); td = __ldg(pl + o11);
-        }
-#pragma unroll
-        for (int j = 0; j < PXC; ++j) {
-          const float Xv = __fmaf_rn(w0[j], a, __fmul_rn(w1[j], bb));
-          const float Yv = __fmaf_rn(w0[j], cc, __fmul_rn(w1[j], d));
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            float z = __fmaf_rn(h0[k], Xv, __fmul_rn(h1[k], Yv));
-            if constexpr (sizeof(T) == 2) z = to_float<T>(from_float<T>(z));   // F.interpolate returns the logit dtype
-            if (k == 0) argmax_step<0>(best[k][j], bi4[j], z, (unsigned)c);   // strict >: lowest index wins ties
-            else if (k == 1) argmax_step<1>(best[k][j], bi4[j], z, (unsigned)c);
-            else if (k == 2) argmax_step<2>(best[k][j], bi4[j], z, (unsigned)c);
-            else argmax_step<3>(best[k][j], bi4[j], z, (unsigned)c);
-          }
-        }
-      }
-      // write-out, one row at a time (a rolled loop: unrolled it was 4000 instructions of straight-line code)
-#pragma unroll 1
-      for (int k = 0; k < nrow; ++k) {
-        const size_t px0 = (size_t)(Y0 + k) * im.W + Xc;
-        int gv[PXC];
-        dgt.upto8(im.gt, px0, npx, gv);
-        const int sh8 = 8 * k;
-        if (pout) {
-#pragma unroll
-          for (int j = 0; j < PXC; ++j)
-            if (j < npx) pout[px0 + j] = (long long)((bi4[j] >> sh8) & 0xffu);
-        }
-#pragma unroll
-        for (int j = 0; j < PXC; ++j) {
-          const int bi = (int)((bi4[j] >> sh8) & 0xffu);
-          if constexpr (PRIVATE) ctr.update_private(ctr.cnt + threadIdx.x, bi, gv[j]);
-          else if (gv[j] != kIgnored) ctr.update(bi, gv[j]);
-        }
+    // Chunks of 8 columns; what is left of the runs takes a narrower chunk — a run of 9 columns in one lane would otherwise
+    // cost its whole warp a second 8-wide class sweep with a single live column. The width is chosen per WARP (the
+    // widest remainder among its lanes), so that short edge runs ride masked in their neighbours' sweep.
+    int Xc = X0;
+    while (true) {
+      const int left = X1 - Xc;
+      const int widest = __reduce_max_sync(0xffffffffu, left);
+      if (widest <= 0) break;
+      if (widest > 4) {
+        if (left > 0)
+          band_chunk<T, THREADS, PRIVATE, R, 8>(im, base, hw, C, o00, o01, o10, o11, h0, h1, sw, ac, x0, Xc, min(left, 8), Y0, nrow, dgt, pout, ctr);
+        Xc += 8;
+      } else if (widest > 2) {
+        if (left > 0)
+          band_chunk<T, THREADS, PRIVATE, R, 4>(im, base, hw, C, o00, o01, o10, o11, h0, h1, sw, ac, x0, Xc, min(left, 4), Y0, nrow, dgt, pout, ctr);
+        Xc += 4;
+      } else {
+        if (left > 0)
+          band_chunk<T, THREADS, PRIVATE, R, 2>(im, base, hw, C, o00, o01, o10, o11, h0, h1, sw, ac, x0, Xc, min(left, 2), Y0, nrow, dgt, pout, ctr);
+        Xc += 2;
       }
     }
   }
