@@ -497,13 +497,17 @@ __device__ __forceinline__ void band_chunk(const b200seg_image& im, const T* bas
     if (c + 1 < C) {                                       // the next class's taps are in flight during this class's arithmetic
       ta = __ldg(pl + o00); tb = __ldg(pl + o01); tc = __ldg(pl + o10); td = __ldg(pl + o11);
     }
+    float Xv[PXC], Yv[PXC];
 #pragma unroll
     for (int j = 0; j < PXC; ++j) {
-      const float Xv = __fmaf_rn(w0[j], a, __fmul_rn(w1[j], bb));
-      const float Yv = __fmaf_rn(w0[j], cc, __fmul_rn(w1[j], d));
+      Xv[j] = __fmaf_rn(w0[j], a, __fmul_rn(w1[j], bb));
+      Yv[j] = __fmaf_rn(w0[j], cc, __fmul_rn(w1[j], d));
+    }
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        float z = __fmaf_rn(h0[k], Xv, __fmul_rn(h1[k], Yv));
+    for (int k = 0; k < R; ++k) {                          // row outside, column inside: consecutive updates hit different registers
+#pragma unroll
+      for (int j = 0; j < PXC; ++j) {
+        float z = __fmaf_rn(h0[k], Xv[j], __fmul_rn(h1[k], Yv[j]));
         if constexpr (sizeof(T) == 2) z = to_float<T>(from_float<T>(z));   // F.interpolate returns the logit dtype
         if (k == 0) argmax_step<0>(best[k][j], bi4[j], z, (unsigned)c, one);   // strict >: lowest index wins ties
         else if (k == 1) argmax_step<1>(best[k][j], bi4[j], z, (unsigned)c, one);

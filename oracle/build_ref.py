@@ -1,7 +1,7 @@
 """Recipe for oracle/_ref/: the reference's OWN hot-path files compiled to CPython byte code (test infrastructure).
 
 The reference is Python, so "building" it means `py_compile`: every file on the path is compiled from
-the source WHERE IT LIES under /root/reference into oracle/_ref/<same relative path>.pyc. No reference source is copied
+the source WHERE IT LIES under /root/reference into oracle/_ref/<same relative path, .refbc>. No reference source is copied
 into this repository: oracle/_ref/ holds binaries only and is git-ignored (not gpurun-ignored, so it travels to the GPU
 box like the built .so files, whose interpreter is the same image's CPython). oracle/ref_loader.py loads these files
 when /root/reference itself is absent; `bench.py --impl reference` and the `cpu_baseline` leg then time the
@@ -24,7 +24,7 @@ FILES = ('utils/ops.py', 'models/losses/utils.py', 'models/losses/cross_entropy_
 
 
 def compiled_path(rel):
-    return os.path.join(OUT, rel + 'c')
+    return os.path.join(OUT, rel[:-3] + '.refbc')   # not '.pyc': snapshot tools drop those
 
 
 def build(verbose=False):
