@@ -516,12 +516,17 @@ __device__ __forceinline__ void band_chunk(const b200seg_image& im, const T* bas
       }
     }
   }
-  // write-out, one row at a time (a rolled loop: unrolled it was 4000 instructions of straight-line code)
+  // write-out, one row at a time (a rolled loop: unrolled it was 4000 instructions of straight-line code); the next row's
+  // ground truth is requested before this row's counters are updated
+  int gnext[PXC];
+  dgt.template upto<PXC>(im.gt, (size_t)Y0 * im.W + Xc, npx, gnext);
 #pragma unroll 1
   for (int k = 0; k < nrow; ++k) {
     const size_t px0 = (size_t)(Y0 + k) * im.W + Xc;
     int gv[PXC];
-    dgt.template upto<PXC>(im.gt, px0, npx, gv);
+#pragma unroll
+    for (int j = 0; j < PXC; ++j) gv[j] = gnext[j];
+    if (k + 1 < nrow) dgt.template upto<PXC>(im.gt, px0 + im.W, npx, gnext);
     const int sh8 = 8 * k;
     if (pout) {
 #pragma unroll
