@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -61,6 +62,12 @@ int scale_inplace_dispatch(void* x, int dtype, long long n, const float* g, cuda
 int lovasz_fwd_dispatch(const b200seg_lovasz_desc* d, cudaStream_t st);
 int lovasz_bwd_dispatch(const b200seg_lovasz_bwd_desc* d, cudaStream_t st);
 long long lovasz_workspace_bytes(int N, int C, long long HW, int per_image, int pairs);
+bool bulk_fwd_supported(const b200seg_loss_desc* d);
+int bulk_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st);
+static bool bulk_fwd_enabled() {   // B200SEG_NO_BULK_FWD=1: the streaming forward (A/B measurements and the old-vs-new parity test)
+  const char* e = getenv("B200SEG_NO_BULK_FWD");
+  return !(e && e[0] == '1');
+}
 bool bulk_supported(const void* logits, const void* labels, const void* grad, int logit_dtype, int label_dtype, int C,
                     long long HW, bool has_pixel_weight);
 
@@ -147,6 +154,8 @@ extern "C" int b200seg_loss_fwd(const b200seg_loss_desc* d, void* stream) {
     B200SEG_REQUIRE(d->dice_mode == B200SEG_MODE_DICE, "loss_fwd: unknown dice_mode %d", d->dice_mode);
     return d->C <= 32 ? tile_fwd_dispatch(d, st) : dice_stream_fwd_dispatch(d, st);
   }
+  // 16-byte tileable problems whose class tile fits shared memory take the bulk-copy pipeline in its forward-only form
+  if (bulk_fwd_enabled() && bulk_fwd_supported(d)) return bulk_fwd_dispatch(d, st);
   return ce_fwd_dispatch(d, st);
 }
 

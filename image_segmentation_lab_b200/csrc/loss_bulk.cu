@@ -38,6 +38,10 @@ struct BulkParams {
   int acc_has_ignore;
   long long acc_ignore;
   int want_acc;
+  // forward-only mode (GRAD = false): optional per-pixel outputs, no gradient
+  float* lse;            // (N,H,W) log-sum-exp or NULL
+  float* loss_px;        // (N,H,W) loss_weight * per-pixel loss or NULL
+  float lw;
 };
 
 constexpr int kBulkV = 2;                              // pixels per consumer thread (one 8-byte / 4-byte shared-memory access)
@@ -46,7 +50,10 @@ constexpr int kBulkPx = kBulkConsumers * kBulkV;       // pixels per tile
 constexpr int kBulkThreads = kBulkConsumers + 64;      // + one load-producer warp + one store warp
 constexpr int kBulkMaxStages = 4;
 
-template <typename T>
+// GRAD = false is the forward-only form (validation loss, `reduction='none'`, the first pass of the two-pass plans): the
+// same load pipeline, two sweeps over the tile instead of three, nothing written back — the store warp only hands the
+// stage back to the producer; per-pixel log-sum-exp / loss maps are stored by the consumers (8 bytes per thread, coalesced).
+template <typename T, bool GRAD>
 __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[kBulkMaxStages], done_bar[kBulkMaxStages], empty_bar[kBulkMaxStages];
@@ -103,16 +110,21 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
       unsigned char* stage = smem_raw + (size_t)s * p.stage_bytes;
       char* dst = reinterpret_cast<char*>(p.grad) + ((size_t)n * C * HW + px0) * sizeof(T);
       if (lane == 0) {
-        for (int c = 0; c < C; ++c) bulk_s2g(dst + (size_t)c * HW * sizeof(T), stage + (size_t)c * row_stride, row_bytes);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (k >= 1) {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          mbar_arrive(&empty_bar[prev_s]);
+        if constexpr (GRAD) {
+          for (int c = 0; c < C; ++c) bulk_s2g(dst + (size_t)c * HW * sizeof(T), stage + (size_t)c * row_stride, row_bytes);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (k >= 1) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            mbar_arrive(&empty_bar[prev_s]);
+          }
+        } else {
+          (void)dst; (void)stage; (void)row_bytes; (void)prev_s;
+          mbar_arrive(&empty_bar[s]);                       // every consumer has read the tile: the stage is free
         }
       }
       __syncwarp();
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (GRAD && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ===================== consumer warps: thread = kBulkV adjacent pixels of the tile
     constexpr int V = kBulkV;
@@ -178,19 +190,29 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
           for (int v = 0; v < V; ++v) {
             const float e = ex2(fmaf(to_float<T>(z.v[v]), kLog2e, nm[v]));
             ssum[v] += e;
-            if constexpr (sizeof(T) == 4) z.v[v] = from_float<T>(e);
+            if constexpr (GRAD && sizeof(T) == 4) z.v[v] = from_float<T>(e);
           }
-          if constexpr (sizeof(T) == 4) col[c * kBulkConsumers] = z;
+          if constexpr (GRAD && sizeof(T) == 4) col[c * kBulkConsumers] = z;
         }
-        float kg[V], rr[V];
+        float kg[V], rr[V], lsev[V], lpx[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const float lse = m[v] + fast_log(ssum[v]);
-          loss_acc = fmaf(kk[v], lse - zy[v], loss_acc);
+          const float l = kk[v] * (lse - zy[v]);
+          loss_acc += l;
+          lsev[v] = lse;
+          lpx[v] = l * p.lw;
           kg[v] = kk[v] * Gs;
           rr[v] = kg[v] * fast_rcp(ssum[v]);
         }
+        if constexpr (!GRAD) {
+          static_assert(V == 2, "one 8-byte store per thread");
+          const size_t o = (size_t)n * HW + px0 + t0;
+          if (p.lse) *reinterpret_cast<float2*>(p.lse + o) = make_float2(lsev[0], lsev[1]);
+          if (p.loss_px) *reinterpret_cast<float2*>(p.loss_px + o) = make_float2(lpx[0], lpx[1]);
+        }
         // pass 3: gradient k * (p - onehot) in place
+        if constexpr (GRAD) {
 #pragma unroll 4
         for (int c = 0; c < C; ++c) {
           Pack z = col[c * kBulkConsumers];
@@ -208,10 +230,11 @@ __global__ void __launch_bounds__(kBulkThreads) ce_bulk_kernel(const BulkParams 
           if (valid[v])
             reinterpret_cast<T*>(stage)[(size_t)yc[v] * kBulkPx + t0 + v] = from_float<T>(rr[v] * ex2(fmaf(zy[v], kLog2e, nm[v])) - kg[v]);
         }
+        }
       }
       // hand the tile to the store warp: generic-proxy writes -> async proxy, then arrive (no CTA-wide barrier: a consumer
       // warp goes straight on to the next tile)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if constexpr (GRAD) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&done_bar[s]);
     }
   }
@@ -233,14 +256,17 @@ bool bulk_supported(const void* logits, const void* labels, const void* grad, in
   return 6 * bulk_stage_bytes(C, elem) <= 220 * 1024;   // fp32: C <= 34, 16-bit: C <= 69
 }
 
-template <typename T> static int bulk_launch(BulkParams p, cudaStream_t st) {
+template <typename T, bool GRAD = true> static int bulk_launch(BulkParams p, cudaStream_t st) {
   const size_t stage = bulk_stage_bytes(p.C, (int)sizeof(T));
   int stages = (int)((200 * 1024) / stage);
   if (stages > kBulkMaxStages) stages = kBulkMaxStages;
+  // forward only: half the bytes per tile for the same arithmetic — the consumers are the limit, so the shared memory
+  // goes into more resident CTAs (consumer warps) with two stages each rather than into deeper rings
+  if (!GRAD && stages > 2) stages = 2;
   p.stages = stages;
   p.stage_bytes = (int)stage;
   const size_t smem = stage * stages;
-  auto k = ce_bulk_kernel<T>;
+  auto k = ce_bulk_kernel<T, GRAD>;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(k), 200 * 1024)) return e;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
@@ -269,6 +295,39 @@ int bulk_fused_dispatch(const b200seg_loss_fused_desc* d, cudaStream_t st) {
     case B200SEG_F16: return bulk_launch<__half>(p, st);
   }
   set_error("loss_fused: unsupported logit dtype %d", f->logit_dtype);
+  return 1;
+}
+
+// Forward only (b200seg_loss_fwd without Dice, at label resolution, no pixel weights, 16-byte tileable): same statistics
+// as ce_fwd_kernel, optional per-pixel log-sum-exp and loss maps.
+bool bulk_fwd_supported(const b200seg_loss_desc* d) {
+  if ((d->flags & B200SEG_WANT_DICE) || d->h != d->H || d->w != d->W) return false;
+  const float* lse = (d->flags & B200SEG_WANT_LSE) ? d->lse : nullptr;
+  const float* lpx = (d->flags & B200SEG_WANT_LOSS_PX) ? d->loss_px : nullptr;
+  if ((lse && !aligned16(lse)) || (lpx && !aligned16(lpx))) return false;
+  return bulk_supported(d->logits, d->labels, d->logits, d->logit_dtype, d->label_dtype, d->C, (long long)d->H * d->W,
+                        d->pixel_weight != nullptr);
+}
+
+int bulk_fwd_dispatch(const b200seg_loss_desc* d, cudaStream_t st) {
+  BulkParams p = {};
+  p.logits = d->logits; p.labels = d->labels; p.cw = d->ce_class_weight;
+  p.stats = reinterpret_cast<unsigned long long*>(d->stats);
+  p.ce_scale_host = 0.f;
+  p.lse = (d->flags & B200SEG_WANT_LSE) ? d->lse : nullptr;
+  p.loss_px = (d->flags & B200SEG_WANT_LOSS_PX) ? d->loss_px : nullptr;
+  p.lw = d->ce_loss_weight;
+  p.label_dtype = d->label_dtype; p.label_bytes = label_bytes(d->label_dtype);
+  p.N = d->N; p.C = d->C; p.HW = (long long)d->H * d->W;
+  p.tiles_per_image = (int)((p.HW + kBulkPx - 1) / kBulkPx);
+  p.total_tiles = (long long)p.tiles_per_image * p.N;
+  p.ignore_index = d->ignore_index; p.acc_has_ignore = d->acc_has_ignore; p.acc_ignore = d->acc_ignore_index;
+  switch (d->logit_dtype) {
+    case B200SEG_F32: return bulk_launch<float, false>(p, st);
+    case B200SEG_BF16: return bulk_launch<__nv_bfloat16, false>(p, st);
+    case B200SEG_F16: return bulk_launch<__half, false>(p, st);
+  }
+  set_error("loss_fwd: unsupported logit dtype %d", d->logit_dtype);
   return 1;
 }
 

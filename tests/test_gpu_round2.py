@@ -565,3 +565,58 @@ def test_bce_single_pass_matches_two_pass_and_oracle(B):
     with torch.no_grad():
         ln = B.CrossEntropyLoss(use_sigmoid=True)(x0, y, ignore_index=255)
     assert rel_err(ln, O.binary_cross_entropy(x0, y, ignore_index=255)) <= LOSS_TOL
+
+
+# ------------------------------------------------------------------------------------------------ forward-only bulk pipeline
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16])
+def test_bulk_forward_only_matches_oracle_and_streaming_forward(B, dtype):
+    """csrc/loss_bulk.cu in its forward-only form (validation loss under no_grad, reduction='none', the first pass of the
+    two-pass plans: cross_entropy_loss.py:56-72) against the oracle and against the streaming forward it replaces
+    (B200SEG_NO_BULK_FWD=1): reductions, class weights, avg_non_ignore + backward through the saved log-sum-exp, label
+    dtypes, a ragged last tile, out-of-range labels, all-ignored input."""
+    tol = LOSS_TOL if dtype == torch.float32 else HALF_TOL
+    cases = [((4, 21, 64, 64), {}, torch.int64), ((2, 19, 24, 40), dict(reduction='sum'), torch.uint8),
+             ((2, 21, 20, 28), dict(reduction='none'), torch.int64),
+             ((3, 8, 16, 24), dict(avg_non_ignore=True, class_weight=torch.linspace(0.5, 1.5, 8).tolist()), torch.int32),
+             ((1, 34 if dtype == torch.float32 else 69, 32, 36), dict(class_weight=None), torch.int64), ((2, 2, 8, 8), {}, torch.float32)]
+    for shape, kw, ldt in cases:
+        n, c, h, w = shape
+        x = synth_logits(shape, 77, dtype=dtype, device='cuda')
+        y = synth_labels((n, h, w), c, 77, device='cuda', block=4)
+        yo = y.clone()
+        if not kw.get('avg_non_ignore'):         # (a bad label counts in avg_non_ignore's denominator; ATen device-asserts on it)
+            y[0, 0, :3] = c + 5                  # out of range, not ignore_index: counted as bad, treated as ignored
+            yo[0, 0, :3] = 255
+        y = y.to(ldt)
+        res = {}
+        for mode in ('bulk', 'stream'):
+            if mode == 'stream':
+                os.environ['B200SEG_NO_BULK_FWD'] = '1'
+            try:
+                with torch.no_grad():
+                    l = B.CrossEntropyLoss(**kw)(x, y, ignore_index=255)
+                    a = B.accuracy(x, yo, ignore_index=255)
+                xa = x.clone().requires_grad_(True)
+                ce = B.CrossEntropyLoss(**kw)
+                ce.single_pass = False           # two-pass plan: forward saves the log-sum-exp, backward re-reads the logits
+                lg = ce(xa, y, ignore_index=255)
+                lg.sum().backward()
+                res[mode] = (l, a, lg.detach(), xa.grad)
+            finally:
+                os.environ.pop('B200SEG_NO_BULK_FWD', None)
+        xo = x.float().requires_grad_(True)
+        want = O.cross_entropy_loss_module(xo, yo.long(), ignore_index=255, **kw)
+        want.sum().backward()
+        name = '%s %s %s' % (shape, kw, dtype)
+        for mode in ('bulk', 'stream'):
+            l, a, lg, g = res[mode]
+            assert l.shape == want.shape, name
+            assert rel_err(l, want) <= tol and rel_err(lg, want) <= tol, (name, mode, rel_err(l, want))
+            assert rel_err(g, xo.grad) <= (GRAD_TOL if dtype == torch.float32 else 2 * HALF_TOL), (name, mode)
+        assert rel_err(res['bulk'][0], res['stream'][0]) <= 2e-6, name
+        assert torch.equal(res['bulk'][1], res['stream'][1]), name          # top-1 accuracy: integer counts
+        assert rel_err(res['bulk'][3].float(), res['stream'][3].float()) <= (2e-5 if dtype == torch.float32 else 2.0 ** -7), name
+    x = synth_logits((2, 21, 16, 16), 3, dtype=dtype, device='cuda')
+    y = torch.full((2, 16, 16), 255, device='cuda')
+    with torch.no_grad():
+        assert float(B.CrossEntropyLoss()(x, y, ignore_index=255)) == 0.0
