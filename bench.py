@@ -800,13 +800,13 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
                  [B.CrossEntropyLoss(class_weight=cw), B.DiceLoss(loss_weight=3.0)], iters=10,
                  plan='cs_fwd_kernel + finalize; cs_bwd_kernel (class-sliced tensor-map TMA pipeline: one read of the logits per direction)')
     bench_losses('C4_voc_fp32_ce', (32, 21, 512, 512), torch.float32, B.CrossEntropyLoss(), iters=20, single=True,
-                 plan='ce_bulk_kernel (cp.async.bulk load warp / consumers / store warp): forward+backward in one pass')
+                 plan='ce_bulk_kernel (cp.async.bulk load warp / consumers / store warp): forward+backward in one pass; fwd = its forward-only form')
     bench_losses('C3_ade20k_bf16_ce_only', (16, 150, 512, 512), torch.bfloat16, B.CrossEntropyLoss(class_weight=cw), iters=10,
                  plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
     ce2 = B.CrossEntropyLoss()
     ce2.single_pass = False
     bench_losses('C4_voc_fp32_ce_two_pass', (32, 21, 512, 512), torch.float32, ce2, iters=10,
-                 plan='ce_fwd_kernel (saves lse) + ce_bwd_kernel')
+                 plan='ce_bulk_kernel<forward only> (saves lse) + ce_bwd_kernel')
 
     # ---- row f1: the sigmoid path the shipped default config runs (use_sigmoid=True, 2 classes, configs/network/deeplabv3):
     # one-hot expansion + BCE-with-logits in one stream per direction (csrc/loss_bce.cu)
