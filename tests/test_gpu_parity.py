@@ -721,3 +721,15 @@ def test_areas_resize_fused_band_and_row_forms(B, C):
             assert torch.equal(p_, m_), (ac, i, int((p_ != m_).sum()))
         assert torch.equal(got, _areas_oracle_gpu(preds, gts, C, 255))
         assert torch.equal(B.area_totals_device(logits, gts, C, 255, from_logits=True, align_corners=ac), got.sum(0))
+    # every ground-truth dtype the evaluator accepts goes through the same write-out (float32 above; int64 / uint8 have their
+    # own vector forms, the others the scalar decoder), and 16-bit logits round the interpolated value before the compare
+    want = _areas_oracle_gpu(preds, gts, C, 255)
+    for gdt in (torch.int64, torch.uint8, torch.int32, torch.int16, torch.float64):
+        got = B.areas_device(logits, [g_.to(gdt) for g_ in gts], C, 255, from_logits=True, align_corners=True)
+        assert torch.equal(got, want), gdt
+    for ldt in (torch.bfloat16, torch.float16):
+        lh = [l.to(ldt) for l in logits]
+        ph = [O.resize(l, size=tuple(gt.shape), mode='bilinear', align_corners=False).float().argmax(dim=1).squeeze(0)
+              for l, gt in zip(lh, gts)]
+        got = B.areas_device(lh, [g_.long() for g_ in gts], C, 255, from_logits=True, align_corners=False)
+        assert torch.equal(got, _areas_oracle_gpu(ph, gts, C, 255)), ldt
