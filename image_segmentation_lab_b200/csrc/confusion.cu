@@ -471,6 +471,7 @@ template <int K> __device__ __forceinline__ void argmax_step(float& best, unsign
       : "f"(z), "r"(c), "n"(K == 0 ? 0x3214 : (K == 1 ? 0x3240 : (K == 2 ? 0x3410 : 0x4210))), "f"(one));
 }
 
+constexpr int kPrefetchAhead = 4;
 // One chunk of PXC columns (npx <= PXC of them live) of a band unit: class sweep + write-out of nrow rows.
 template <typename T, int THREADS, bool PRIVATE, int R, int PXC>
 __device__ __forceinline__ void band_chunk(const b200seg_image& im, const T* base, int hw, int C, int o00, int o01, int o10, int o11,
@@ -496,6 +497,16 @@ __device__ __forceinline__ void band_chunk(const b200seg_image& im, const T* bas
     pl += hw;
     if (c + 1 < C) {                                       // the next class's taps are in flight during this class's arithmetic
       ta = __ldg(pl + o00); tb = __ldg(pl + o01); tc = __ldg(pl + o10); td = __ldg(pl + o11);
+    }
+    if constexpr (PXC <= 4) {
+      // ... and the lines of the class kPrefetchAhead further on are requested into L1 (no register cost): at 1/4
+      // resolution the logits of an image are read about once, so a tap load is a DRAM access, which one class of
+      // arithmetic (~500 cycles of a scheduler's four warps) does not cover. A warp's lanes hold neighbouring runs: the
+      // left taps of all lanes cover the right taps' sectors but one. (Not in the 8-wide sweep: at 1/8 resolution the
+      // logits are small, the sweep is issue bound and the two extra instructions per class cost 6 %.)
+      const T* pf = base + (size_t)min(c + kPrefetchAhead, C - 1) * hw;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + o00));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + o10));
     }
     float Xv[PXC], Yv[PXC];
 #pragma unroll
