@@ -283,6 +283,13 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
             gn[0] = ld_stream16(gb + pxn * 4);
             gn[1] = ld_stream16(gb + pxn * 4 + 16);
           }
+          // ... and the lines of the iteration after that are requested into L2: bytes in flight without registers
+          // (measured: 0.90 -> 0.98 of the HBM copy peak; the register double buffer alone leaves 49 KB in flight per SM)
+          if (itn + 2 < n_full) {
+            const long long pxf = px + 2 * span;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + pxf * 8));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gb + pxf * 4));
+          }
           const float gf[8] = {__uint_as_float(gr[0].x), __uint_as_float(gr[0].y), __uint_as_float(gr[0].z),
                                __uint_as_float(gr[0].w), __uint_as_float(gr[1].x), __uint_as_float(gr[1].y),
                                __uint_as_float(gr[1].z), __uint_as_float(gr[1].w)};
