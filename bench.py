@@ -566,8 +566,12 @@ def flatten_workloads(line, extras):
     put('c2_c150_general_ms', extras, 'C2_like_c150_64to512', 'fwd_bwd', 'ms')
     put('c5i_ms', extras, 'C5i_miou_label_maps', 'ms')
     put('c5i_frac', extras, 'C5i_miou_label_maps', 'roofline', 'frac')
+    put('c5i_totals_ms', extras, 'C5i_miou_label_maps', 'totals_prepared', 'ms')
+    put('c5i_totals_frac', extras, 'C5i_miou_label_maps', 'totals_prepared', 'roofline', 'frac')
     put('c5ii_ms', extras, 'C5ii_miou_from_logits', 'ms')
     put('c5ii_frac', extras, 'C5ii_miou_from_logits', 'roofline', 'frac')
+    put('c5ii_totals_ms', extras, 'C5ii_miou_from_logits', 'totals_prepared', 'ms')
+    put('c5ii_totals_frac', extras, 'C5ii_miou_from_logits', 'totals_prepared', 'roofline', 'frac')
     put('c5_resized_ms', extras, 'C5_resized_lowres_logits', 'ms')
     put('c5_resized_frac', extras, 'C5_resized_lowres_logits', 'roofline', 'frac')
     put('f1_sigmoid_ce_fwd_bwd_ms', extras, 'F1_sigmoid_ce_2class', 'fwd_bwd', 'ms')
@@ -911,8 +915,20 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     px = n_img * 1024 * 2048
     out['C5i_miou_label_maps'] = {'images': n_img, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
                                   'roofline': roof(px * 12, ms), 'algorithmic_bytes': px * 12,
-                                  'note': 'one b200seg_confusion_labels launch for the 500-image list; random predictions '
-                                          '(worst case for the histogram), blocky ground truth'}
+                                  'note': 'one b200seg_confusion_labels launch for the 500-image list, per-image areas as '
+                                          'intersect_and_union returns them, image table built and uploaded inside the timed '
+                                          'call; random predictions (worst case for the histogram), blocky ground truth'}
+    # the same sweep as the evaluator runs it over a prepared list: table built once, (3,C) totals accumulated in the kernel
+    tab5 = B.prepare_images(preds, gt_all, Cn)
+
+    def sweep_t(i):
+        B.area_totals_device(tab5, None, Cn, 255)
+
+    sweep_t(0)
+    ms_t = timed_events(sweep_t, 5)
+    out['C5i_miou_label_maps']['totals_prepared'] = {'ms': ms_t, 'mpix_s': px / ms_t / 1e3, 'roofline': roof(px * 12, ms_t),
+                                                      'note': 'prepare_images once + area_totals_device: the kernel alone'}
+    del tab5
     del preds, pred_base
     torch.cuda.empty_cache()
     n_l = 500
@@ -929,7 +945,17 @@ def extra_workloads(B, _lib, dev, peak, peak_kind):
     out['C5ii_miou_from_logits'] = {'images': n_l, 'pixels': px, 'ms': ms, 'mpix_s': px / ms / 1e3,
                                     'roofline': roof(px * (Cn * 4 + 4), ms), 'algorithmic_bytes': px * (Cn * 4 + 4),
                                     'note': 'all 500 images (79.7 GB of fp32 logits), fused arg-max + areas, one launch'}
-    del logits, lbase
+    tab5 = B.prepare_images(logits, gl, Cn, from_logits=True)
+
+    def sweep2_t(i):
+        B.area_totals_device(tab5, None, Cn, 255)
+
+    sweep2_t(0)
+    ms_t = timed_events(sweep2_t, 3)
+    out['C5ii_miou_from_logits']['totals_prepared'] = {'ms': ms_t, 'mpix_s': px / ms_t / 1e3,
+                                                        'roofline': roof(px * (Cn * 4 + 4), ms_t),
+                                                        'note': 'prepare_images once + area_totals_device: the kernel alone'}
+    del logits, lbase, tab5
     torch.cuda.empty_cache()
 
     # ---- "next" row f2: the validation rescale fused into the arg-max — logits at 1/8 resolution (1,19,128,256) against

@@ -36,7 +36,7 @@ int ensure_dyn_smem(const void* func, int bytes);   // per (kernel, device) opt-
   } while (0)
 
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline int label_bytes(int dt) {
+__host__ __device__ inline int label_bytes(int dt) {
   switch (dt) {
     case B200SEG_L_U8: return 1;
     case B200SEG_L_I16: return 2;

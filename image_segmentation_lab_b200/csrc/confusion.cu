@@ -499,6 +499,15 @@ __device__ __forceinline__ void band_chunk(const b200seg_image& im, const T* bas
   }
   const T* pl = base;
   T ta = __ldg(pl + o00), tb = __ldg(pl + o01), tc = __ldg(pl + o10), td = __ldg(pl + o11);
+  if constexpr (PXC <= 4) {
+    // the ground truth of the chunk's rows is requested into L2 now and read after the class sweep (narrow chunks only:
+    // their sweep is short of covering the write-out's DRAM latency; the 8-wide form measured slower with it)
+    const unsigned gb = (unsigned)label_bytes(dgt.dt);
+    const char* gp = reinterpret_cast<const char*>(im.gt) + ((size_t)Y0 * im.W + Xc) * gb;
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if (k < nrow) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + (size_t)k * im.W * gb));
+  }
   for (int c = 0; c < C; ++c) {
     const float a = to_float<T>(ta), bb = to_float<T>(tb), cc = to_float<T>(tc), d = to_float<T>(td);
     pl += hw;
