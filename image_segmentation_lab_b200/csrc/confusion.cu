@@ -405,11 +405,13 @@ __global__ void __launch_bounds__(THREADS) confusion_kernel(const ConfParams p) 
 // as F.interpolate's output is: the arg-max — and with it every area — is BIT-EXACT against the reference's
 // resize -> argmax at any ratio and either align_corners setting (on inputs without soft-max rounding ties).
 //
-// Work unit = one output row x one RUN of columns sharing the same pair of source columns (x0, x1): a thread loads the
-// 4 taps of a class once per run (L1 hits: the low-resolution logits are small) and evaluates 6 fp32 operations + a
-// compare / select pair per class-pixel for the run's pixels, in chunks of 8. Run boundaries come from the source-index
-// map itself (any ratio), tabulated per image in shared memory. Bound: instruction issue (C interpolations per output
-// pixel); DRAM traffic is the ground-truth map (4 B per pixel) plus the small logits.
+// Work unit = a BAND of up to 4 output rows sharing the same pair of source rows x one RUN of columns sharing the same pair
+// of source columns (resize_band_units below; rows that are not up-sampled keep the one-row form of the kernel body): a
+// thread loads the 4 taps of a class once per unit (the next class's are in flight meanwhile), forms the horizontal sums
+// once per column and evaluates FMUL + FFMA + compare / select per class-pixel, in chunks of 8 / 4 / 2 columns. Band and
+// run boundaries come from the source-index maps themselves (any ratio), tabulated per image in shared memory. Bound:
+// instruction issue / the ALU pipe (C interpolations per output pixel); DRAM traffic is the ground-truth map (4 B per
+// pixel) plus the small logits.
 constexpr int kRunTableMax = 4096;   // w + 2 entries per image; wider logits take the simple per-pixel kernel
 
 // band key of an output position: 0 = source index clamped to 0 (align_corners=False), k + 1 = source floor k
