@@ -217,3 +217,34 @@ def test_packed_allreduce_single_process_is_identity():
     a, b = torch.arange(3, dtype=torch.int64), torch.tensor([1.5])
     out = par([a, b])
     assert torch.equal(out[0], a) and torch.equal(out[1], b)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line with the contract's keys,
+    the headline metric / workload of the CUDA arm, and the reference's own files as the thing timed wherever they can be
+    executed (oracle/_ref byte code or /root/reference), the oracle port otherwise."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in line, k
+    assert line['impl'] == 'reference' and line['unit'] == 'Mpix/s' and line['value'] > 0
+    assert line['config']['batch_per_gpu'] == 8 and 'workload' in line['config']
+    cb = line['cpu_baseline']
+    from oracle import ref_loader
+    assert cb['kind'] == ('reference' if ref_loader.available() else 'port')
+    assert cb['value'] == line['value'] and cb['cores'] >= 1 and '8 of the 8 images' in cb['sample']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # under torchrun only rank 0 prints; the other ranks exit 0 without work
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    r1 = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                         '--warmup', '0'], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ''
