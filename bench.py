@@ -19,7 +19,11 @@ side stream (--allreduce-every 1 issues it every step).
   cpu_baseline  the reference's own resize / CrossEntropyLoss / accuracy (oracle/_ref: byte code compiled from its files
                 by oracle/build_ref.py; kind "reference") on the host cores, bounded sample; the oracle port
                 (oracle/oracle.py; kind "port") when oracle/_ref is absent.
-  workloads     extra single-GPU results for BASELINE configs 3, 4 and 5 (HBM-bound shapes), each with its roofline.
+  workloads     extra single-GPU results for BASELINE configs 3, 4 and 5 (HBM-bound shapes), each with its roofline;
+                mirrored as flat scalars into roofline (c3_*, c4_*, c5i_*, c5ii_*, c5_resized_*, f1_*, lovasz_*, and
+                under torchrun c4dp_* / c5i_sharded_*). c5i / c5ii are measured twice: through the list API the
+                reference's intersect_and_union has (per-image areas, image table built inside the call: *_ms / *_frac)
+                and over a prepared list with in-kernel totals (*_totals_ms / *_totals_frac: the kernel alone).
 
 `--impl reference` times the reference's CPU implementation of the same workload on all host threads: its own files,
 executed from oracle/_ref byte code (the sources stay in /root/reference; see oracle/build_ref.py), else the oracle port.
